@@ -1,0 +1,134 @@
+"""Test helpers: ctypes view of the CPU oracle, fixture materialisation, cross_match text parser.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/ (it is the checker).
+"""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+ORACLE_BUILD = os.path.join(ROOT, "oracle", "_build")
+ORACLE_BIN = os.path.join(ORACLE_BUILD, "cross_match")
+MAXA = 16
+
+
+class OraMatrix(C.Structure):
+    _fields_ = [("n", C.c_int), ("alpha", C.c_char * (MAXA + 1)), ("score", (C.c_int * MAXA) * MAXA),
+                ("freq", C.c_double * MAXA), ("lambda_", C.c_double), ("code_of", C.c_int * 256)]
+
+
+class OraParams(C.Structure):
+    _fields_ = [("gap_init", C.c_int), ("ins_gap_ext", C.c_int), ("del_gap_ext", C.c_int), ("minscore", C.c_int),
+                ("masklevel", C.c_int), ("minmatch", C.c_int), ("bandwidth", C.c_int), ("raw", C.c_int),
+                ("alignments", C.c_int)]
+
+
+_lib = None
+
+
+def oracle_lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(os.path.join(ORACLE_BUILD, "librm_oracle.so"))
+        _lib.ora_matrix_parse.argtypes = [C.c_char_p, C.POINTER(OraMatrix), C.c_char_p, C.c_int]
+        _lib.ora_rescore.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(OraMatrix), C.POINTER(OraParams),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _lib.ora_global_traceback.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(OraMatrix),
+                                              C.POINTER(OraParams), C.c_int, C.c_char_p, C.c_char_p, C.c_char_p,
+                                              C.c_char_p]
+        _lib.ora_sw_score.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(OraMatrix),
+                                      C.POINTER(OraParams)]
+    return _lib
+
+
+def matrices():
+    return json.load(open(os.path.join(GOLD, "matrices.json")))["matrices"]
+
+
+def write_matrix(name, path):
+    """Re-materialise Matrices/crossmatch/<name> from the golden values (same grammar: optional FREQS
+    line, alphabet row, integer rows)."""
+    m = matrices()[name]
+    with open(path, "w") as f:
+        if m["has_freqs_line"]:
+            f.write("FREQS " + " ".join(f"{a} {fr:g}" for a, fr in zip(m["alphabet"], m["freqs"]) if fr > 0) + "\n")
+        f.write(" " + " ".join(f"{a:>3}" for a in m["alphabet"]) + "\n")
+        for row in m["rows"]:
+            f.write(" ".join(f"{v:>3}" for v in row) + "\n")
+    return path
+
+
+def parse_matrix(path):
+    m = OraMatrix()
+    err = C.create_string_buffer(512)
+    rc = oracle_lib().ora_matrix_parse(path.encode(), C.byref(m), err, 512)
+    assert rc == 0, err.value
+    return m
+
+
+def encode(m, letters):
+    return bytes(m.code_of[ord(c)] for c in letters)
+
+
+_HIT = re.compile(r"^\s*\d+\s+\d+\.\d+\s+\d+\.\d+\s+\d+\.\d+\s")
+_ALN = re.compile(r"^(C?)\s+(\S+)\s+(\d+)\s+(\S+)\s+(\d+)\s*$")
+
+
+def parse_crossmatch(text):
+    """Minimal reader of cross_match text with the grammar CrossmatchSearchEngine.pm:549-879 accepts.
+    Alignment rows are kept in DISPLAY orientation."""
+    hits = []
+    cur = None
+    pos = 0
+    for ln in text.splitlines():
+        if ln.startswith("Score histogram:"):
+            break
+        if _HIT.match(ln):
+            f = ln.split()
+            star = f[-1] == "*"
+            if star:
+                f = f[:-1]
+            if f[8] == "C":
+                cur = dict(score=int(f[0]), div=f[1], dele=f[2], ins=f[3], qname=f[4], qstart=int(f[5]), qend=int(f[6]),
+                           qleft=int(f[7].strip("()")), strand="C", sname=f[9], sleft=int(f[10].strip("()")),
+                           send=int(f[11]), sstart=int(f[12]), star=star, qaln="", saln="")
+            else:
+                cur = dict(score=int(f[0]), div=f[1], dele=f[2], ins=f[3], qname=f[4], qstart=int(f[5]), qend=int(f[6]),
+                           qleft=int(f[7].strip("()")), strand="+", sname=f[8], sstart=int(f[9]), send=int(f[10]),
+                           sleft=int(f[11].strip("()")), star=star, qaln="", saln="")
+            hits.append(cur)
+            pos = 0
+            continue
+        m = _ALN.match(ln)
+        if m and cur is not None:
+            if pos == 0:
+                cur["qaln"] += m.group(4)
+            else:
+                cur["saln"] += m.group(4)
+            pos ^= 1
+            continue
+        mm = re.search(r"Transitions / transversions = \S+ \((\d+) / (\d+)\)", ln)
+        if mm and cur is not None:
+            cur["ti"], cur["tv"] = int(mm.group(1)), int(mm.group(2))
+    return hits
+
+
+def oracle_argv(query, subject, matrix, gap_init=-30, ins_gap_ext=-6, del_gap_ext=-5, minscore=225, masklevel=101,
+                minmatch=9, bandwidth=14, raw=False, alignments=True):
+    argv = [ORACLE_BIN]
+    if raw:
+        argv.append("-raw")
+    if alignments:
+        argv.append("-alignments")
+    argv += ["-gap_init", str(gap_init), "-ins_gap_ext", str(ins_gap_ext), "-del_gap_ext", str(del_gap_ext), "-minmatch",
+             str(minmatch), "-minscore", str(minscore), "-bandwidth", str(bandwidth), "-masklevel", str(masklevel),
+             "-matrix", matrix, query, subject]
+    return argv
+
+
+def run_oracle(query, subject, matrix, **kw):
+    res = subprocess.run(oracle_argv(query, subject, matrix, **kw), capture_output=True, text=True, check=True)
+    return parse_crossmatch(res.stdout), res.stdout
