@@ -1,0 +1,134 @@
+/*
+ * rmgpu.h -- C ABI of librmgpu.so, the B200 (sm_100a) repeat-search engine that stands where
+ * RepeatMasker's CrossmatchSearchEngine.pm popen()s the external `cross_match` binary.
+ *
+ * Plain C types only (no torch / CUDA types): this is what an FFI/XS stub binds.  The Perl-side
+ * binding is repeatmasker_b200/perl/{GpuSearchEngine.pm,RMGpu.xs}; INTEGRATION.md shows the two
+ * driver edits.  Each entry point cites the reference interface it replaces (paths are inside the
+ * RepeatMasker tree).
+ *
+ * Threading / fork: no CUDA call is made before the first search in a given PID
+ * (RepeatMasker forks one child per batch, RepeatMasker:1043; a CUDA context cannot cross fork).
+ * A session is bound to the thread's current device and must be used from one thread at a time.
+ */
+#ifndef RMGPU_H
+#define RMGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMGPU_ABI_VERSION 1
+
+/* Search parameters.  Replaces the argv that CrossmatchSearchEngine.pm:277-363 (getParameters) builds from the
+ * SearchEngineI.pm:132-681 setters:
+ *   -raw (scoreMode==basicScoreMode) -word_raw -alignments -gap_init -ins_gap_ext -del_gap_ext
+ *   -minmatch -minscore -bandwidth -masklevel -matrix <file> <query> <subject>                                  */
+typedef struct rmgpu_params {
+  int32_t gap_init;        /* setGapInit,   e.g. -30: cost of the first base of a gap                  */
+  int32_t ins_gap_ext;     /* setInsGapExt, e.g. -6 : further bases of a gap in the SUBJECT row          */
+  int32_t del_gap_ext;     /* setDelGapExt, e.g. -5 : further bases of a gap in the QUERY row            */
+  int32_t minscore;        /* setMinScore                                                               */
+  int32_t masklevel;       /* setMaskLevel 0..101 (RepeatMasker:2920-2926 always passes 101)            */
+  int32_t minmatch;        /* setMinMatch: accepted for interface parity; discovery is exhaustive       */
+  int32_t bandwidth;       /* setBandwidth: initial half-width of the traceback band                    */
+  int32_t raw;             /* 1 = basicScoreMode (-raw), 0 = complexityAdjustedScoreMode                */
+  int32_t word_raw;        /* setWordRaw: accepted, unused                                              */
+  int32_t want_alignments; /* setGenerateAlignments                                                     */
+  int32_t device;          /* CUDA device ordinal, -1 = current                                         */
+  int32_t reserved[5];
+} rmgpu_params;
+
+/* One reported match.  Replaces one hit line + alignment block of cross_match text as parsed by
+ * CrossmatchSearchEngine.pm:549-879 into SearchResult->new(...) (field list SearchResult.pm:235-262).      */
+typedef struct rmgpu_hit {
+  int32_t score;     /* reported score (complexity-adjusted unless params.raw)                         */
+  int32_t raw_score; /* Smith-Waterman-Gotoh score                                                      */
+  int32_t query_index, subject_index; /* 0-based record numbers in the query / subject input          */
+  const char *query_name, *subject_name; /* owned by the result                                        */
+  int32_t qstart, qend, qleft; /* 1-based inclusive, forward-strand query coordinates                  */
+  int32_t sstart, send, sleft;
+  uint8_t strand;       /* 0 forward, 1 = "C" (reverse-complemented query vs forward subject)          */
+  uint8_t overlap_star; /* the trailing '*' of the hit line                                             */
+  uint8_t pad_[2];
+  char pct_div[8], pct_del[8], pct_ins[8]; /* the "%.2f" text cross_match prints (query-span denominators) */
+  int32_t transitions, transversions, ambiguous, gap_inits, gap_bases;
+  const char *qaln, *saln; /* NUL-terminated gapped rows in cross_match DISPLAY orientation: for strand C the
+                              query row is reverse-complemented (descending coordinates), subject row forward.
+                              NULL when want_alignments == 0.                                           */
+} rmgpu_hit;
+
+/* Device-side accounting of one search (all times from CUDA events on the engine's stream). */
+typedef struct rmgpu_stats {
+  double cells;          /* DP cells of the exhaustive pass = sum Q*L*2                                 */
+  double ms_total;       /* whole call, host clock                                                      */
+  double ms_h2d, ms_d2h; /* copies                                                                      */
+  double ms_score;       /* K1: strand-paired int16x2 DPX score pass (the dominant kernel)              */
+  double ms_origin;      /* K2: int32 origin-tracking pass over (query,strand,subject) triples that passed K1 */
+  double ms_traceback;   /* K3: banded traceback                                                        */
+  double ms_host_post;   /* adjusted score, percentages, ordering, masklevel, strings                   */
+  int64_t h2d_bytes, d2h_bytes;
+  int32_t launches;      /* kernels launched                                                            */
+  int32_t score_launches;
+  int32_t n_pairs_passed; /* (query,strand,subject) triples with K1 best >= minscore                    */
+  int32_t n_candidates;   /* origins with raw >= minscore                                               */
+  double origin_cells;    /* cells K2 recomputed                                                        */
+} rmgpu_stats;
+
+typedef struct rmgpu_result {
+  int32_t n_hits;
+  rmgpu_hit *hits;
+  rmgpu_stats stats;
+  void *opaque; /* string arena */
+} rmgpu_result;
+
+/* "cross_match version ..." banner replacement (CrossmatchSearchEngine.pm:244-260 scrapes a version that the driver
+ * prints in the .cat/.tbl trailer, RepeatMasker:1267-1270). */
+const char *rmgpu_version(void);
+int rmgpu_abi_version(void);
+
+/* Last error text of the calling thread ("" if none).  Errors are also returned as non-zero status, which the
+ * driver's retry ladder interprets (RepeatMasker:2068-2107). */
+const char *rmgpu_last_error(void);
+
+/* The one call that replaces `open("$cmdLine 2>/dev/null |")` + parseOutput (CrossmatchSearchEngine.pm:444-480):
+ * query FASTA, subject FASTA and matrix file paths as set by setQuery/setSubject/setMatrix.
+ * Returns 0 on success; *out must be released with rmgpu_free. Host buffers in, host buffers out.             */
+int rmgpu_search(const rmgpu_params *p, const char *query_fasta, const char *subject_fasta, const char *matrix_file,
+                 rmgpu_result **out);
+void rmgpu_free(rmgpu_result *r);
+
+/* ---- Session API: library resident in HBM across batches (one session per GPU worker). ---------- */
+typedef struct rmgpu_session rmgpu_session;
+
+rmgpu_session *rmgpu_session_open(int device); /* NULL on failure (no CUDA device => loud error, no fallback) */
+void rmgpu_session_close(rmgpu_session *s);
+/* Matrix file in the Matrix.pm:308-364 grammar (FREQS line, alphabet row, integer rows). */
+int rmgpu_session_set_matrix_file(rmgpu_session *s, const char *matrix_file);
+/* Subject library: n records, upper/lower-case IUPAC letters; packed to the device layout and kept resident. */
+int rmgpu_session_set_library(rmgpu_session *s, int32_t n, const char *const *names, const char *const *seqs,
+                              const int32_t *lens);
+int rmgpu_session_set_library_fasta(rmgpu_session *s, const char *subject_fasta);
+/* Query batch (SimpleBatcher fragments, SimpleBatcher.pm:592-800): encoded and copied to the device. */
+int rmgpu_session_set_queries(rmgpu_session *s, int32_t n, const char *const *names, const char *const *seqs,
+                              const int32_t *lens);
+int rmgpu_session_set_queries_fasta(rmgpu_session *s, const char *query_fasta);
+/* Run the search on the resident batch x resident library. */
+int rmgpu_session_search(rmgpu_session *s, const rmgpu_params *p, rmgpu_result **out);
+/* K1 only, on resident data: best raw Smith-Waterman-Gotoh score per (query, subject, strand).
+ * best must hold n_queries*n_subjects*2 int32 (strand fastest).  Used by tests and by bench.py's kernel-only leg;
+ * returns the kernel time in *ms (CUDA events). */
+int rmgpu_session_score_only(rmgpu_session *s, const rmgpu_params *p, int32_t *best, double *ms);
+int rmgpu_session_counts(const rmgpu_session *s, int32_t *n_queries, int32_t *n_subjects, int64_t *query_bases,
+                         int64_t *subject_bases);
+
+/* Measured integer-SIMD ("DPX") peak of this GPU: a register-resident loop of the bare recurrence.
+ * Returns 16-bit-lane cell updates per second (GCUPS*1e9) in *cups and raw VIADDMNMX.S16x2 warp-instructions/s. */
+int rmgpu_measure_dpx_peak(int device, double *cups, double *dpx_instr_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

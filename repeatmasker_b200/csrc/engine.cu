@@ -1,0 +1,1051 @@
+// engine.cu -- session, device layout, kernel orchestration and the C ABI of librmgpu.so (include/rmgpu.h).
+//
+// Data layout in HBM:
+//   library   rowcode[nGroups*R] (1 B/row, 0xFF = pad), prof[nGroups*R] (8 B/row, rebuilt per matrix / class map),
+//             gflags/gsubject per 32-lane group, sflags per stripe, scodes (1 B/base) for K2/K3
+//   queries   qpacked (4 bit/base, what crosses PCIe), sel (2 B/column, both strands), codes_fwd/codes_rc (1 B/base)
+//   scratch   stripe boundary ring (K1 8 B/column, K2 16 B/column), candidate table, traceback direction bytes
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/rmgpu.h"
+#include "host.hpp"
+#include "kernels.cuh"
+
+namespace rmgpu {
+
+#define CUDA_CHECK(x)                                                                                         \
+  do {                                                                                                        \
+    cudaError_t e_ = (x);                                                                                     \
+    if (e_ != cudaSuccess)                                                                                    \
+      throw Error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" +          \
+                  std::to_string(__LINE__) + " (" #x ")");                                                    \
+  } while (0)
+
+static thread_local std::string g_last_error;
+
+template <typename T>
+struct DevBuf {  // grow-only device buffer
+  T* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  T* ensure(size_t n) {
+    if (n > cap) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      size_t want = std::max(n, cap + cap / 2);
+      CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
+      cap = want;
+    }
+    return p;
+  }
+  void upload(const std::vector<T>& v, cudaStream_t st) {
+    ensure(std::max<size_t>(v.size(), 1));
+    if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  }
+};
+
+struct EventTimer {
+  cudaEvent_t a, b;
+  EventTimer() {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+  }
+  ~EventTimer() {
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+  void start(cudaStream_t s) { cudaEventRecord(a, s); }
+  void stop(cudaStream_t s) { cudaEventRecord(b, s); }
+  double ms() {
+    float f = 0;
+    cudaEventSynchronize(b);
+    cudaEventElapsedTime(&f, a, b);
+    return f;
+  }
+};
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// -------------------------------------------------------------------------------------------------------------
+struct Candidate {
+  int q, strand, subject;
+  int i0, j0, i1, j1, raw;
+};
+
+struct HitRec {
+  int score, raw, qidx, sidx, strand;
+  int qstart, qend, qleft, sstart, send, sleft;
+  int ti, tv, amb, gap_inits, gap_bases;
+  bool star = false;
+  char div[8], del[8], ins[8];
+  std::string qaln, saln;
+};
+
+}  // namespace rmgpu
+
+using namespace rmgpu;
+
+struct rmgpu_session {
+  int device = 0;
+  int numSMs = 0;
+  cudaStream_t stream = nullptr;
+  static constexpr int R = 8;  // subject rows per lane in K1
+
+  ScoreMatrix matrix;
+  bool haveMatrix = false;
+  SeqSet lib, queries;
+  bool haveLib = false, haveQueries = false;
+
+  // ---- library layout
+  int nGroups = 0, nStripes = 0;
+  std::vector<int32_t> h_gsubject;
+  DevBuf<uint8_t> d_rowcode, d_gflags, d_sflags, d_scodes;
+  DevBuf<uint2> d_prof;
+  DevBuf<int32_t> d_gsubject, d_slen;
+  DevBuf<int64_t> d_soff;
+  std::vector<int64_t> h_soff;
+  bool profileValid = false;
+
+  // ---- query layout
+  std::vector<int64_t> h_qoff, h_selOff;
+  std::vector<int32_t> h_qlen, h_selLen;
+  int maxQ = 0;
+  int64_t selTotal = 0;
+  DevBuf<uint8_t> d_qpacked, d_codes_fwd, d_codes_rc;
+  DevBuf<int64_t> d_qoff, d_selOff;
+  DevBuf<int32_t> d_qlen, d_selLen;
+  DevBuf<uint16_t> d_sel;
+  uint8_t class_of_code[16] = {};
+  int8_t class_score[16][8] = {};
+  bool classesExact = true;
+  std::vector<uint8_t> classKey;  // to detect class-map changes
+  int64_t h2d_bytes_queries = 0;
+  double ms_h2d_queries = 0;
+
+  // ---- scratch
+  DevBuf<int32_t> d_pairbest;
+  DevBuf<uint2> d_bnd1;
+  DevBuf<OriginBoundary> d_bnd2;
+  DevBuf<int> d_progress, d_finished, d_ticket, d_overflow;
+  DevBuf<unsigned long long> d_keys, d_vals;
+  DevBuf<OriginTask> d_tasks;
+  DevBuf<int32_t> d_ticketTask;
+  DevBuf<TraceCand> d_cand;
+  DevBuf<uint8_t> d_dir, d_ops;
+  DevBuf<int32_t> d_rows, d_opsLen, d_status;
+
+  void set_library(SeqSet s);
+  void set_queries(SeqSet s);
+  void build_classes_and_profile();
+  void run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest, double& ms, int& launches);
+  void run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest, std::vector<Candidate>& cands,
+                  rmgpu_stats& st);
+  void run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands, std::vector<std::vector<uint8_t>>& ops,
+                     rmgpu_stats& st);
+  rmgpu_result* search(const rmgpu_params& p);
+};
+
+// -------------------------------------------------------------------------------------------------------------
+// Library packing: subjects -> groups of R rows -> stripes of 32 groups.  A subject longer than one stripe owns
+// consecutive stripes starting at lane 0; the free lanes of its last stripe and all remaining stripes are filled
+// first-fit-decreasing with subjects that fit entirely, so only genuinely long subjects create stripe chains.
+// -------------------------------------------------------------------------------------------------------------
+void rmgpu_session::set_library(SeqSet s) {
+  if (!haveMatrix) throw Error("set the matrix before the library");
+  lib = std::move(s);
+  const int n = (int)lib.seqs.size();
+  std::vector<int> order(n), groups(n);
+  for (int i = 0; i < n; i++) {
+    if (lib.seqs[i].size() >= (1u << 20)) throw Error("subject longer than 1,048,575 bases: " + lib.names[i]);
+    groups[i] = (int)((lib.seqs[i].size() + R - 1) / R);
+  }
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a] > groups[b]; });
+  struct Place {
+    int subject, firstGroup;
+  };
+  std::vector<Place> places;
+  std::vector<std::pair<int, int>> open;  // (stripe, free lanes) for stripes with room at the tail
+  int stripes = 0;
+  for (int idx : order) {
+    int g = groups[idx];
+    if (g == 0) continue;
+    int found = -1;
+    if (g < 32)
+      for (size_t o = 0; o < open.size(); o++)
+        if (open[o].second >= g) {
+          found = (int)o;
+          break;
+        }
+    if (found >= 0) {
+      int stripe = open[found].first, freeL = open[found].second;
+      places.push_back({idx, stripe * 32 + (32 - freeL)});
+      open[found].second -= g;
+      if (open[found].second == 0) open.erase(open.begin() + found);
+    } else {
+      int ns = (g + 31) / 32;
+      places.push_back({idx, stripes * 32});
+      int rem = ns * 32 - g;
+      if (rem > 0) open.push_back({stripes + ns - 1, rem});
+      stripes += ns;
+      if (open.size() > 4096) open.erase(open.begin());  // bound the first-fit scan
+    }
+  }
+  nStripes = std::max(stripes, 1);
+  nGroups = nStripes * 32;
+  std::vector<uint8_t> rowcode((size_t)nGroups * R, 0xFF), gflags(nGroups, 1), sflags(nStripes, 0);
+  h_gsubject.assign(nGroups, -1);
+  for (auto& pl : places) {
+    const std::string& sq = lib.seqs[pl.subject];
+    for (int gi = 0; gi < groups[pl.subject]; gi++) {
+      int g = pl.firstGroup + gi;
+      h_gsubject[g] = pl.subject;
+      gflags[g] = gi == 0 ? 1 : 0;
+      for (int r = 0; r < R; r++) {
+        size_t pos = (size_t)gi * R + r;
+        if (pos < sq.size()) rowcode[(size_t)g * R + r] = matrix.code_of[(unsigned char)sq[pos]];
+      }
+    }
+  }
+  for (int k = 0; k < nStripes; k++) {
+    bool prev = !(gflags[k * 32] & 1);
+    if (prev) {
+      sflags[k] |= 1;
+      sflags[k - 1] |= 2;
+    }
+  }
+  // unpacked subject codes for K2 / K3
+  h_soff.assign(n + 1, 0);
+  std::vector<int32_t> slen(n);
+  for (int i = 0; i < n; i++) {
+    slen[i] = (int32_t)lib.seqs[i].size();
+    h_soff[i + 1] = h_soff[i] + slen[i];
+  }
+  std::vector<uint8_t> scodes((size_t)std::max<int64_t>(h_soff[n], 1));
+  for (int i = 0; i < n; i++)
+    for (size_t k = 0; k < lib.seqs[i].size(); k++)
+      scodes[h_soff[i] + k] = matrix.code_of[(unsigned char)lib.seqs[i][k]];
+  d_rowcode.upload(rowcode, stream);
+  d_gflags.upload(gflags, stream);
+  d_sflags.upload(sflags, stream);
+  d_gsubject.upload(h_gsubject, stream);
+  d_scodes.upload(scodes, stream);
+  d_soff.upload(h_soff, stream);
+  d_slen.upload(slen, stream);
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  haveLib = true;
+  profileValid = false;
+}
+
+void rmgpu_session::set_queries(SeqSet s) {
+  if (!haveMatrix) throw Error("set the matrix before the queries");
+  queries = std::move(s);
+  const int n = (int)queries.seqs.size();
+  h_qoff.assign(n + 1, 0);
+  h_selOff.assign(n + 1, 0);
+  h_qlen.resize(n);
+  h_selLen.resize(n);
+  maxQ = 0;
+  for (int i = 0; i < n; i++) {
+    int64_t Q = (int64_t)queries.seqs[i].size();
+    if (Q >= (1 << 20)) throw Error("query longer than 1,048,575 bases (fragment it: SimpleBatcher.pm:592-800): " + queries.names[i]);
+    h_qlen[i] = (int32_t)Q;
+    h_selLen[i] = (int32_t)((((Q + 31) >> 5) + 1) * 32);
+    h_qoff[i + 1] = h_qoff[i] + ((Q + 1) & ~1ll);  // even nibble offsets
+    h_selOff[i + 1] = h_selOff[i] + h_selLen[i];
+    maxQ = std::max<int>(maxQ, (int)Q);
+  }
+  selTotal = h_selOff[n];
+  std::vector<uint8_t> packed((size_t)(h_qoff[n] / 2 + 1), 0);
+  int64_t counts[16] = {};
+  for (int i = 0; i < n; i++) {
+    const std::string& q = queries.seqs[i];
+    for (size_t k = 0; k < q.size(); k++) {
+      uint8_t c = matrix.code_of[(unsigned char)q[k]];
+      counts[c]++;
+      counts[matrix.comp_code[c]]++;
+      int64_t nib = h_qoff[i] + (int64_t)k;
+      packed[nib >> 1] |= (uint8_t)(c << ((nib & 1) * 4));
+    }
+  }
+  // residue classes: up to 7 exact; beyond that the rarest codes share class 6 with row-wise max scores, which
+  // makes K1 an upper bound (still an exact filter: K2 recomputes every passing pair with the full alphabet)
+  std::vector<int> present;
+  for (int c = 0; c < matrix.n; c++)
+    if (counts[c] > 0) present.push_back(c);
+  std::stable_sort(present.begin(), present.end(), [&](int a, int b) { return counts[a] > counts[b]; });
+  std::vector<uint8_t> key;
+  int nExact = present.size() <= 7 ? (int)present.size() : 6;
+  classesExact = present.size() <= 7;
+  for (int c = 0; c < 16; c++) class_of_code[c] = 6;
+  for (int k = 0; k < nExact; k++) class_of_code[present[k]] = (uint8_t)k;
+  for (int sc = 0; sc < 16; sc++) {
+    for (int k = 0; k < 8; k++) class_score[sc][k] = -128;
+    if (sc >= matrix.n) continue;
+    auto clampv = [&](int v) {
+      if (v > 127) throw Error("matrix score > 127 is not supported by the int8 profile");
+      return (int8_t)std::max(v, -128);
+    };
+    for (int k = 0; k < nExact; k++) class_score[sc][k] = clampv(matrix.score[sc][present[k]]);
+    if (!classesExact) {
+      int mx = -128;
+      for (size_t k = 6; k < present.size(); k++) mx = std::max(mx, matrix.score[sc][present[k]]);
+      class_score[sc][6] = clampv(mx);
+    }
+  }
+  for (int c = 0; c < 16; c++) key.push_back(class_of_code[c]);
+  for (int sc = 0; sc < 16; sc++)
+    for (int k = 0; k < 8; k++) key.push_back((uint8_t)class_score[sc][k]);
+  if (key != classKey) {
+    classKey = key;
+    profileValid = false;
+  }
+  double t0 = now_ms();
+  d_qpacked.upload(packed, stream);
+  d_qoff.upload(h_qoff, stream);
+  d_qlen.upload(h_qlen, stream);
+  d_selOff.upload(h_selOff, stream);
+  d_selLen.upload(h_selLen, stream);
+  d_sel.ensure((size_t)std::max<int64_t>(selTotal, 1));
+  d_codes_fwd.ensure((size_t)std::max<int64_t>(h_qoff[n], 1));
+  d_codes_rc.ensure((size_t)std::max<int64_t>(h_qoff[n], 1));
+  if (n > 0) {
+    StreamArgs a;
+    a.qpacked = d_qpacked.p;
+    a.qoff = d_qoff.p;
+    a.qlen = d_qlen.p;
+    a.selOff = d_selOff.p;
+    a.selLen = d_selLen.p;
+    a.sel = d_sel.p;
+    a.codes_fwd = d_codes_fwd.p;
+    a.codes_rc = d_codes_rc.p;
+    a.nQueries = n;
+    memcpy(a.class_of_code, class_of_code, 16);
+    memcpy(a.comp_code, matrix.comp_code, 16);
+    dim3 grid((unsigned)std::min<int64_t>(((int64_t)maxQ + 64 + 255) / 256, 1024), (unsigned)n);
+    build_streams_kernel<<<grid, 256, 0, stream>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  ms_h2d_queries = now_ms() - t0;
+  h2d_bytes_queries = (int64_t)packed.size() + (int64_t)(n + 1) * 24;
+  haveQueries = true;
+}
+
+void rmgpu_session::build_classes_and_profile() {
+  if (profileValid) return;
+  ProfileArgs a;
+  a.rowcode = d_rowcode.p;
+  a.prof = d_prof.ensure((size_t)nGroups * R);
+  a.nRows = (int64_t)nGroups * R;
+  memcpy(a.class_score, class_score, sizeof(class_score));
+  build_profile_kernel<<<std::min<int64_t>((a.nRows + 255) / 256, 4096), 256, 0, stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  profileValid = true;
+}
+
+static uint32_t pack2(int v) { return ((uint32_t)(uint16_t)(int16_t)v) | ((uint32_t)(uint16_t)(int16_t)v << 16); }
+
+// K1 over the resident batch x library.
+void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest, double& ms, int& launches) {
+  const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
+  pairbest.assign((size_t)nQ * nS * 2, 0);
+  ms = 0;
+  if (nQ == 0 || nS == 0) return;
+  if (p.gap_init >= 0 || p.ins_gap_ext > 0 || p.del_gap_ext > 0 || p.gap_init < -20000)
+    throw Error("gap penalties must be negative");
+  build_classes_and_profile();
+  int blocksPerSM = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R>, 256, 0));
+  if (blocksPerSM < 1) throw Error("K1 does not fit on an SM");
+  const int64_t nTickets = (int64_t)nQ * nStripes;
+  if (nTickets >= (1ll << 31)) throw Error("too many stripe tasks in one batch");
+  int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, (nTickets + 7) / 8);
+  const int warps = grid * 8;
+  const int nslot = (int)std::min<int64_t>(nTickets, 2 * (int64_t)warps + 2);
+  const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
+  ScoreArgs a;
+  a.prof = d_prof.p;
+  a.gflags = d_gflags.p;
+  a.gsubject = d_gsubject.p;
+  a.sflags = d_sflags.p;
+  a.sel = d_sel.p;
+  a.selOff = d_selOff.p;
+  a.qlen = d_qlen.p;
+  a.nQueries = nQ;
+  a.nStripes = nStripes;
+  a.nSubjects = nS;
+  a.pairbest = d_pairbest.ensure(pairbest.size());
+  a.bnd = d_bnd1.ensure((size_t)nslot * bndStride);
+  a.bndStride = bndStride;
+  a.nslot = nslot;
+  a.progress = d_progress.ensure((size_t)nTickets);
+  a.finished = d_finished.ensure((size_t)nTickets);
+  a.ticket = d_ticket.ensure(1);
+  a.gi2 = pack2(p.gap_init);
+  a.ie2 = pack2(p.ins_gap_ext);
+  a.de2 = pack2(p.del_gap_ext);
+  CUDA_CHECK(cudaMemsetAsync(a.pairbest, 0, pairbest.size() * sizeof(int32_t), stream));
+  CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream));
+  CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream));
+  CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), stream));
+  EventTimer tm;
+  tm.start(stream);
+  swg_score_kernel<R><<<grid, 256, 0, stream>>>(a);
+  tm.stop(stream);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpyAsync(pairbest.data(), a.pairbest, pairbest.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  ms = tm.ms();
+  launches += 1;
+}
+
+// K2 over every (query, strand, subject) whose K1 best reached minscore.
+void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest, std::vector<Candidate>& cands,
+                               rmgpu_stats& st) {
+  const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
+  std::vector<OriginTask> tasks;
+  std::vector<int32_t> ticketTask;
+  for (int q = 0; q < nQ; q++)
+    for (int s = 0; s < nS; s++)
+      for (int strand = 0; strand < 2; strand++)
+        if (pairbest[((size_t)q * nS + s) * 2 + strand] >= p.minscore) {
+          int64_t Q = h_qlen[q], L = (int64_t)lib.seqs[s].size();
+          if ((Q + 1) * (L + 1) >= (1ll << 32))
+            throw Error("query x subject too large for one origin pass (" + queries.names[q] + " x " + lib.names[s] +
+                        "): fragment the query as SimpleBatcher does");
+          OriginTask t;
+          t.q = q;
+          t.strand = strand;
+          t.subject = s;
+          t.firstTicket = (int)ticketTask.size();
+          t.nStripes = (int)((L + kR2 * 32 - 1) / (kR2 * 32));
+          for (int k = 0; k < t.nStripes; k++) ticketTask.push_back((int32_t)tasks.size());
+          tasks.push_back(t);
+          st.origin_cells += (double)Q * (double)L;
+        }
+  st.n_pairs_passed = (int)tasks.size();
+  cands.clear();
+  if (tasks.empty()) return;
+  const int nTickets = (int)ticketTask.size();
+  int blocksPerSM = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_origin_kernel, 128, 0));
+  if (blocksPerSM < 1) throw Error("K2 does not fit on an SM");
+  blocksPerSM = std::min(blocksPerSM, 4);
+  int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, ((int64_t)nTickets + 3) / 4);
+  const int warps = grid * 4;
+  const int nslot = std::min(nTickets, 2 * warps + 2);
+  const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
+  size_t tableSize = 1u << 18;
+  for (;;) {
+    OriginArgs a;
+    d_tasks.upload(tasks, stream);
+    d_ticketTask.upload(ticketTask, stream);
+    a.tasks = d_tasks.p;
+    a.ticketTask = d_ticketTask.p;
+    a.nTickets = nTickets;
+    a.codes_fwd = d_codes_fwd.p;
+    a.codes_rc = d_codes_rc.p;
+    a.qoff = d_qoff.p;
+    a.qlen = d_qlen.p;
+    a.scodes = d_scodes.p;
+    a.soff = d_soff.p;
+    a.slen = d_slen.p;
+    for (int i = 0; i < 16; i++)
+      for (int j = 0; j < 16; j++) a.mat[i][j] = (i < matrix.n && j < matrix.n) ? matrix.score[i][j] : -128;
+    a.gap_init = p.gap_init;
+    a.ins_ext = p.ins_gap_ext;
+    a.del_ext = p.del_gap_ext;
+    a.minscore = p.minscore;
+    a.bnd = d_bnd2.ensure((size_t)nslot * bndStride);
+    a.bndStride = bndStride;
+    a.nslot = nslot;
+    a.progress = d_progress.ensure((size_t)nTickets);
+    a.finished = d_finished.ensure((size_t)nTickets);
+    a.ticket = d_ticket.ensure(1);
+    a.keys = d_keys.ensure(tableSize);
+    a.vals = d_vals.ensure(tableSize);
+    a.tableMask = (uint32_t)tableSize - 1;
+    a.overflow = d_overflow.ensure(1);
+    CUDA_CHECK(cudaMemsetAsync(a.keys, 0xFF, tableSize * 8, stream));
+    CUDA_CHECK(cudaMemsetAsync(a.vals, 0, tableSize * 8, stream));
+    CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream));
+    CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream));
+    CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), stream));
+    CUDA_CHECK(cudaMemsetAsync(a.overflow, 0, sizeof(int), stream));
+    EventTimer tm;
+    tm.start(stream);
+    swg_origin_kernel<<<grid, 128, 0, stream>>>(a);
+    tm.stop(stream);
+    CUDA_CHECK(cudaGetLastError());
+    std::vector<unsigned long long> keys(tableSize), vals(tableSize);
+    int overflow = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaMemcpyAsync(keys.data(), a.keys, tableSize * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaMemcpyAsync(vals.data(), a.vals, tableSize * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    st.ms_origin += tm.ms();
+    st.launches += 1;
+    st.d2h_bytes += (int64_t)tableSize * 16;
+    size_t used = 0;
+    for (size_t i = 0; i < tableSize; i++) used += keys[i] != kEmptyKey;
+    if (overflow || used * 2 > tableSize) {  // keep the table sparse; rerun bigger
+      tableSize *= 4;
+      if (tableSize > (1u << 28)) throw Error("candidate table overflow");
+      if (overflow) continue;
+    }
+    for (size_t i = 0; i < tableSize && i < keys.size(); i++) {
+      if (keys[i] == kEmptyKey) continue;
+      int ti = (int)(keys[i] >> 32);
+      uint32_t origin = (uint32_t)keys[i];
+      const OriginTask& t = tasks[ti];
+      Candidate c;
+      c.q = t.q;
+      c.strand = t.strand;
+      c.subject = t.subject;
+      const uint32_t Lp1 = (uint32_t)lib.seqs[t.subject].size() + 1u;
+      c.i0 = (int)(origin / Lp1);
+      c.j0 = (int)(origin % Lp1);
+      c.raw = (int)(vals[i] >> 40);
+      c.i1 = (int)(0xFFFFFu - (uint32_t)((vals[i] >> 20) & 0xFFFFFu));
+      c.j1 = (int)(0xFFFFFu - (uint32_t)(vals[i] & 0xFFFFFu));
+      cands.push_back(c);
+    }
+    break;
+  }
+  std::sort(cands.begin(), cands.end(), [](const Candidate& x, const Candidate& y) {
+    if (x.q != y.q) return x.q < y.q;
+    if (x.strand != y.strand) return x.strand < y.strand;
+    if (x.subject != y.subject) return x.subject < y.subject;
+    if (x.i0 != y.i0) return x.i0 < y.i0;
+    return x.j0 < y.j0;
+  });
+  st.n_candidates = (int)cands.size();
+}
+
+// K3 with the band schedule W = max(bandwidth,1) * 2^k until the banded score reproduces the raw score.
+void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands,
+                                  std::vector<std::vector<uint8_t>>& ops, rmgpu_stats& st) {
+  ops.assign(cands.size(), {});
+  std::vector<int> todo(cands.size()), W(cands.size(), std::max(p.bandwidth, 1));
+  std::iota(todo.begin(), todo.end(), 0);
+  const int64_t kDirBudget = 4ll << 30;  // direction bytes per launch
+  while (!todo.empty()) {
+    std::vector<int> next;
+    size_t at = 0;
+    while (at < todo.size()) {
+      std::vector<TraceCand> tc;
+      std::vector<int> ids;
+      int64_t dirTot = 0, rowTot = 0, opsTot = 0;
+      while (at < todo.size()) {
+        const Candidate& c = cands[todo[at]];
+        int n = c.i1 - c.i0 + 1, m = c.j1 - c.j0 + 1, w = W[todo[at]];
+        int64_t bw = (int64_t)std::abs(n - m) + 2 * (int64_t)w + 1;
+        int64_t dirBytes = (int64_t)(n + 1) * bw;
+        if (!tc.empty() && dirTot + dirBytes > kDirBudget) break;
+        TraceCand t;
+        t.q = c.q;
+        t.strand = c.strand;
+        t.subject = c.subject;
+        t.i0 = c.i0;
+        t.j0 = c.j0;
+        t.i1 = c.i1;
+        t.j1 = c.j1;
+        t.raw = c.raw;
+        t.W = w;
+        t.dirOff = dirTot;
+        t.rowOff = rowTot;
+        t.opsOff = opsTot;
+        dirTot += dirBytes;
+        rowTot += 4 * bw;
+        opsTot += n + m;
+        tc.push_back(t);
+        ids.push_back(todo[at]);
+        at++;
+      }
+      TraceArgs a;
+      d_cand.upload(tc, stream);
+      a.cand = d_cand.p;
+      a.nCand = (int)tc.size();
+      a.codes_fwd = d_codes_fwd.p;
+      a.codes_rc = d_codes_rc.p;
+      a.qoff = d_qoff.p;
+      a.scodes = d_scodes.p;
+      a.soff = d_soff.p;
+      for (int i = 0; i < 16; i++)
+        for (int j = 0; j < 16; j++) a.mat[i][j] = (i < matrix.n && j < matrix.n) ? matrix.score[i][j] : -128;
+      a.gap_init = p.gap_init;
+      a.ins_ext = p.ins_gap_ext;
+      a.del_ext = p.del_gap_ext;
+      a.dir = d_dir.ensure((size_t)dirTot);
+      a.rows = d_rows.ensure((size_t)rowTot);
+      a.ops = d_ops.ensure((size_t)opsTot);
+      a.opsLen = d_opsLen.ensure(tc.size());
+      a.status = d_status.ensure(tc.size());
+      EventTimer tm;
+      tm.start(stream);
+      traceback_kernel<<<((int)tc.size() + 31) / 32, 32, 0, stream>>>(a);
+      tm.stop(stream);
+      CUDA_CHECK(cudaGetLastError());
+      std::vector<uint8_t> hops((size_t)opsTot);
+      std::vector<int32_t> hlen(tc.size());
+      CUDA_CHECK(cudaMemcpyAsync(hops.data(), a.ops, (size_t)opsTot, cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaMemcpyAsync(hlen.data(), a.opsLen, tc.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaStreamSynchronize(stream));
+      st.ms_traceback += tm.ms();
+      st.launches += 1;
+      st.d2h_bytes += opsTot + (int64_t)tc.size() * 4;
+      for (size_t i = 0; i < tc.size(); i++) {
+        int id = ids[i];
+        if (hlen[i] > 0) {
+          ops[id].assign(hops.begin() + tc[i].opsOff, hops.begin() + tc[i].opsOff + hlen[i]);
+          std::reverse(ops[id].begin(), ops[id].end());
+        } else {
+          const Candidate& c = cands[id];
+          int full = std::max(c.i1 - c.i0 + 1, c.j1 - c.j0 + 1);
+          if (W[id] >= full) throw Error("traceback could not reproduce the forward score");
+          W[id] *= 2;
+          next.push_back(id);
+        }
+      }
+    }
+    todo.swap(next);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Host post-processing: alignment rows, percentages, adjusted score, order, '*', masklevel.
+// -------------------------------------------------------------------------------------------------------------
+namespace {
+
+int base_class(char c) {
+  if (c == 'A' || c == 'G') return 0;
+  if (c == 'C' || c == 'T') return 1;
+  return -1;
+}
+
+void fmt_pct(char* out, long num, long den) { snprintf(out, 8, "%.2f", den > 0 ? 100.0 * (double)num / (double)den : 0.0); }
+
+struct IntervalUnion {  // disjoint, merged closed intervals
+  std::map<int, int> iv;  // start -> end
+  bool overlaps(int a, int b) const {
+    auto it = iv.upper_bound(b);
+    if (it == iv.begin()) return false;
+    --it;
+    return it->second >= a;
+  }
+  long covered(int a, int b) const {
+    long c = 0;
+    auto it = iv.upper_bound(a);
+    if (it != iv.begin()) --it;
+    for (; it != iv.end() && it->first <= b; ++it) {
+      int lo = std::max(a, it->first), hi = std::min(b, it->second);
+      if (hi >= lo) c += hi - lo + 1;
+    }
+    return c;
+  }
+  void add(int a, int b) {
+    auto it = iv.upper_bound(a);
+    if (it != iv.begin()) {
+      auto pr = std::prev(it);
+      if (pr->second >= a - 1) it = pr;
+    }
+    while (it != iv.end() && it->first <= b + 1) {
+      a = std::min(a, it->first);
+      b = std::max(b, it->second);
+      it = iv.erase(it);
+    }
+    iv[a] = b;
+  }
+};
+
+}  // namespace
+
+rmgpu_result* rmgpu_session::search(const rmgpu_params& p) {
+  if (!haveMatrix || !haveLib || !haveQueries) throw Error("matrix, library and queries must be set before searching");
+  if (p.minscore < 1) throw Error("minscore must be >= 1");
+  const double t_begin = now_ms();
+  auto* res = new rmgpu_result();
+  memset(res, 0, sizeof(*res));
+  rmgpu_stats& st = res->stats;
+  st.h2d_bytes = h2d_bytes_queries;
+  st.ms_h2d = ms_h2d_queries;
+  const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
+  for (int q = 0; q < nQ; q++)
+    for (int s = 0; s < nS; s++) st.cells += 2.0 * (double)queries.seqs[q].size() * (double)lib.seqs[s].size();
+
+  std::vector<int32_t> pairbest;
+  run_score(p, pairbest, st.ms_score, st.launches);
+  st.score_launches = 1;
+  st.d2h_bytes += (int64_t)pairbest.size() * 4;
+  std::vector<Candidate> cands;
+  run_origin(p, pairbest, cands, st);
+  std::vector<std::vector<uint8_t>> ops;
+  run_traceback(p, cands, ops, st);
+
+  const double t_post = now_ms();
+  std::vector<HitRec> hits;
+  std::vector<std::string> rcCache(nQ);
+  for (size_t ci = 0; ci < cands.size(); ci++) {
+    const Candidate& c = cands[ci];
+    const std::string& qf = queries.seqs[c.q];
+    const std::string& sj = lib.seqs[c.subject];
+    if (c.strand && rcCache[c.q].empty()) rcCache[c.q] = revcomp_letters(qf);
+    const std::string& ql = c.strand ? rcCache[c.q] : qf;
+    const int Q = (int)qf.size(), L = (int)sj.size();
+    HitRec h;
+    h.qaln.reserve(ops[ci].size());
+    h.saln.reserve(ops[ci].size());
+    int64_t counts[kMaxAlpha] = {};
+    long nsub = 0, ndel = 0, nins = 0;
+    h.ti = h.tv = h.amb = h.gap_inits = h.gap_bases = 0;
+    int qi = c.i0 - 1, si = c.j0 - 1, prev = 0;
+    for (uint8_t op : ops[ci]) {
+      if (op == 0) {
+        char a = ql[qi++], b = sj[si++];
+        h.qaln.push_back(a);
+        h.saln.push_back(b);
+        counts[matrix.code_of[(unsigned char)a]]++;
+        if (a != b) {
+          nsub++;
+          int ca = base_class(a), cb = base_class(b);
+          if (ca < 0 || cb < 0)
+            h.amb++;
+          else if (ca == cb)
+            h.ti++;
+          else
+            h.tv++;
+        }
+      } else if (op == 1) {
+        h.qaln.push_back(ql[qi++]);
+        h.saln.push_back('-');
+        nins++;
+        h.gap_bases++;
+        if (prev != 1) h.gap_inits++;
+      } else {
+        h.qaln.push_back('-');
+        h.saln.push_back(sj[si++]);
+        ndel++;
+        h.gap_bases++;
+        if (prev != 2) h.gap_inits++;
+      }
+      prev = op;
+    }
+    h.raw = c.raw;
+    h.score = p.raw ? c.raw : complexity_adjust(c.raw, counts, matrix);
+    if (h.score < p.minscore) continue;
+    h.qidx = c.q;
+    h.sidx = c.subject;
+    h.strand = c.strand;
+    if (!c.strand) {
+      h.qstart = c.i0;
+      h.qend = c.i1;
+    } else {
+      h.qstart = Q + 1 - c.i1;
+      h.qend = Q + 1 - c.i0;
+    }
+    h.qleft = Q - h.qend;
+    h.sstart = c.j0;
+    h.send = c.j1;
+    h.sleft = L - c.j1;
+    const int span = c.i1 - c.i0 + 1;
+    fmt_pct(h.div, nsub, span);
+    fmt_pct(h.del, ndel, span);
+    fmt_pct(h.ins, nins, span);
+    hits.push_back(std::move(h));
+  }
+  // output order: query order, ascending query start, DESCENDING subject order, then subject start, query end, strand
+  std::sort(hits.begin(), hits.end(), [](const HitRec& x, const HitRec& y) {
+    if (x.qidx != y.qidx) return x.qidx < y.qidx;
+    if (x.qstart != y.qstart) return x.qstart < y.qstart;
+    if (x.sidx != y.sidx) return x.sidx > y.sidx;
+    if (x.sstart != y.sstart) return x.sstart < y.sstart;
+    if (x.qend != y.qend) return x.qend < y.qend;
+    if (x.strand != y.strand) return x.strand < y.strand;
+    return x.send < y.send;
+  });
+  // '*' and masklevel: per query, descending score, equal scores handled as a group (strictly higher counts)
+  {
+    std::vector<int> order(hits.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (hits[a].qidx != hits[b].qidx) return hits[a].qidx < hits[b].qidx;
+      return hits[a].score > hits[b].score;
+    });
+    std::vector<char> drop(hits.size(), 0);
+    size_t i = 0;
+    while (i < order.size()) {
+      size_t qend = i;
+      while (qend < order.size() && hits[order[qend]].qidx == hits[order[i]].qidx) qend++;
+      IntervalUnion all, kept;
+      size_t g = i;
+      while (g < qend) {
+        size_t ge = g;
+        while (ge < qend && hits[order[ge]].score == hits[order[g]].score) ge++;
+        for (size_t k = g; k < ge; k++) {
+          HitRec& h = hits[order[k]];
+          h.star = all.overlaps(h.qstart, h.qend);
+          if (p.masklevel < 101) {
+            long len = h.qend - h.qstart + 1, unc = len - kept.covered(h.qstart, h.qend);
+            if (unc * 100 < (long)(100 - p.masklevel) * len) drop[order[k]] = 1;
+          }
+        }
+        for (size_t k = g; k < ge; k++) {
+          HitRec& h = hits[order[k]];
+          all.add(h.qstart, h.qend);
+          if (!drop[order[k]]) kept.add(h.qstart, h.qend);
+        }
+        g = ge;
+      }
+      i = qend;
+    }
+    if (p.masklevel < 101) {
+      std::vector<HitRec> keep;
+      for (size_t k = 0; k < hits.size(); k++)
+        if (!drop[k]) keep.push_back(std::move(hits[k]));
+      hits.swap(keep);
+    }
+  }
+  // marshal
+  struct Arena {
+    std::vector<std::unique_ptr<char[]>> blocks;
+    const char* dup(const std::string& s) {
+      std::unique_ptr<char[]> b(new char[s.size() + 1]);
+      memcpy(b.get(), s.c_str(), s.size() + 1);
+      blocks.push_back(std::move(b));
+      return blocks.back().get();
+    }
+  };
+  auto* arena = new Arena();
+  res->opaque = arena;
+  res->n_hits = (int32_t)hits.size();
+  res->hits = hits.empty() ? nullptr : new rmgpu_hit[hits.size()];
+  std::vector<const char*> qn(nQ, nullptr), sn(nS, nullptr);
+  for (size_t k = 0; k < hits.size(); k++) {
+    const HitRec& h = hits[k];
+    rmgpu_hit& o = res->hits[k];
+    memset(&o, 0, sizeof(o));
+    o.score = h.score;
+    o.raw_score = h.raw;
+    o.query_index = h.qidx;
+    o.subject_index = h.sidx;
+    if (!qn[h.qidx]) qn[h.qidx] = arena->dup(queries.names[h.qidx]);
+    if (!sn[h.sidx]) sn[h.sidx] = arena->dup(lib.names[h.sidx]);
+    o.query_name = qn[h.qidx];
+    o.subject_name = sn[h.sidx];
+    o.qstart = h.qstart;
+    o.qend = h.qend;
+    o.qleft = h.qleft;
+    o.sstart = h.sstart;
+    o.send = h.send;
+    o.sleft = h.sleft;
+    o.strand = (uint8_t)h.strand;
+    o.overlap_star = h.star;
+    memcpy(o.pct_div, h.div, 8);
+    memcpy(o.pct_del, h.del, 8);
+    memcpy(o.pct_ins, h.ins, 8);
+    o.transitions = h.ti;
+    o.transversions = h.tv;
+    o.ambiguous = h.amb;
+    o.gap_inits = h.gap_inits;
+    o.gap_bases = h.gap_bases;
+    if (p.want_alignments) {
+      o.qaln = arena->dup(h.qaln);
+      o.saln = arena->dup(h.saln);
+    }
+  }
+  st.ms_host_post = now_ms() - t_post;
+  st.ms_total = now_ms() - t_begin + ms_h2d_queries;
+  return res;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------------------
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    g_last_error.clear();
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return 1;
+  }
+}
+
+extern "C" {
+
+const char* rmgpu_version(void) { return "rmgpu version 0.1.0 (B200 sm_100a exhaustive Smith-Waterman-Gotoh)"; }
+int rmgpu_abi_version(void) { return RMGPU_ABI_VERSION; }
+const char* rmgpu_last_error(void) { return g_last_error.c_str(); }
+
+rmgpu_session* rmgpu_session_open(int device) {
+  rmgpu_session* s = nullptr;
+  int rc = guarded([&] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      throw Error(std::string("no CUDA device: librmgpu has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    if (device < 0) CUDA_CHECK(cudaGetDevice(&device));
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) throw Error("librmgpu needs DPX instructions (built for sm_100a)");
+    s = new rmgpu_session();
+    s->device = device;
+    s->numSMs = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  });
+  if (rc) {
+    delete s;
+    return nullptr;
+  }
+  return s;
+}
+
+void rmgpu_session_close(rmgpu_session* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int rmgpu_session_set_matrix_file(rmgpu_session* s, const char* f) {
+  return guarded([&] {
+    CUDA_CHECK(cudaSetDevice(s->device));
+    s->matrix = ScoreMatrix::from_file(f);
+    s->haveMatrix = true;
+    s->profileValid = false;
+    s->classKey.clear();
+    s->haveLib = s->haveQueries = false;  // codes depend on the matrix alphabet
+  });
+}
+
+int rmgpu_session_set_library(rmgpu_session* s, int32_t n, const char* const* names, const char* const* seqs,
+                              const int32_t* lens) {
+  return guarded([&] {
+    CUDA_CHECK(cudaSetDevice(s->device));
+    s->set_library(SeqSet::from_arrays(n, names, seqs, lens));
+  });
+}
+int rmgpu_session_set_library_fasta(rmgpu_session* s, const char* f) {
+  return guarded([&] {
+    CUDA_CHECK(cudaSetDevice(s->device));
+    s->set_library(SeqSet::from_fasta(f));
+  });
+}
+int rmgpu_session_set_queries(rmgpu_session* s, int32_t n, const char* const* names, const char* const* seqs,
+                              const int32_t* lens) {
+  return guarded([&] {
+    CUDA_CHECK(cudaSetDevice(s->device));
+    s->set_queries(SeqSet::from_arrays(n, names, seqs, lens));
+  });
+}
+int rmgpu_session_set_queries_fasta(rmgpu_session* s, const char* f) {
+  return guarded([&] {
+    CUDA_CHECK(cudaSetDevice(s->device));
+    s->set_queries(SeqSet::from_fasta(f));
+  });
+}
+
+int rmgpu_session_search(rmgpu_session* s, const rmgpu_params* p, rmgpu_result** out) {
+  *out = nullptr;
+  return guarded([&] {
+    CUDA_CHECK(cudaSetDevice(s->device));
+    *out = s->search(*p);
+  });
+}
+
+int rmgpu_session_score_only(rmgpu_session* s, const rmgpu_params* p, int32_t* best, double* ms) {
+  return guarded([&] {
+    CUDA_CHECK(cudaSetDevice(s->device));
+    if (!s->haveMatrix || !s->haveLib || !s->haveQueries) throw Error("matrix, library and queries must be set");
+    std::vector<int32_t> pb;
+    double t = 0;
+    int launches = 0;
+    s->run_score(*p, pb, t, launches);
+    if (best) memcpy(best, pb.data(), pb.size() * sizeof(int32_t));
+    if (ms) *ms = t;
+  });
+}
+
+int rmgpu_session_counts(const rmgpu_session* s, int32_t* nq, int32_t* ns, int64_t* qb, int64_t* sb) {
+  if (nq) *nq = (int32_t)s->queries.seqs.size();
+  if (ns) *ns = (int32_t)s->lib.seqs.size();
+  if (qb) *qb = s->queries.total_bases();
+  if (sb) *sb = s->lib.total_bases();
+  return 0;
+}
+
+int rmgpu_search(const rmgpu_params* p, const char* query_fasta, const char* subject_fasta, const char* matrix_file,
+                 rmgpu_result** out) {
+  *out = nullptr;
+  rmgpu_session* s = rmgpu_session_open(p->device);
+  if (!s) return 1;
+  int rc = rmgpu_session_set_matrix_file(s, matrix_file);
+  if (!rc) rc = rmgpu_session_set_library_fasta(s, subject_fasta);
+  if (!rc) rc = rmgpu_session_set_queries_fasta(s, query_fasta);
+  if (!rc) rc = rmgpu_session_search(s, p, out);
+  std::string keep = g_last_error;
+  rmgpu_session_close(s);
+  g_last_error = keep;
+  return rc;
+}
+
+void rmgpu_free(rmgpu_result* r) {
+  if (!r) return;
+  delete[] r->hits;
+  struct Arena {
+    std::vector<std::unique_ptr<char[]>> blocks;
+  };
+  delete reinterpret_cast<Arena*>(r->opaque);
+  delete r;
+}
+
+int rmgpu_measure_dpx_peak(int device, double* cups, double* dpx_instr_per_s) {
+  return guarded([&] {
+    if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+    uint32_t* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, (size_t)blocks * threads * 4));
+    EventTimer tm;
+    double bestMs = 1e30;
+    for (int rep = 0; rep < 5; rep++) {
+      tm.start(0);
+      dpx_peak_kernel<8><<<blocks, threads>>>(d, iters, rep);
+      tm.stop(0);
+      CUDA_CHECK(cudaGetLastError());
+      bestMs = std::min(bestMs, tm.ms());
+    }
+    if (cups) *cups = (double)blocks * threads * 8.0 * iters * 2.0 / (bestMs * 1e-3);
+    bestMs = 1e30;
+    for (int rep = 0; rep < 5; rep++) {
+      tm.start(0);
+      dpx_instr_kernel<<<blocks, threads>>>(d, iters);
+      tm.stop(0);
+      CUDA_CHECK(cudaGetLastError());
+      bestMs = std::min(bestMs, tm.ms());
+    }
+    if (dpx_instr_per_s) *dpx_instr_per_s = (double)blocks * (threads / 32) * 8.0 * iters / (bestMs * 1e-3);
+    cudaFree(d);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// host.hpp -- host-side data model of librmgpu (C++17).  No oracle code is used anywhere in this directory.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace rmgpu {
+
+constexpr int kMaxAlpha = 16;  // 4-bit residue codes on the device
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+// Scoring matrix in the grammar of Matrix.pm:308-364; score[subject][query] (SearchResult.pm:1894-1917).
+struct ScoreMatrix {
+  int n = 0;
+  std::string alphabet;
+  int score[kMaxAlpha][kMaxAlpha] = {};
+  double freq[kMaxAlpha] = {};
+  double lambda = 0;
+  uint8_t code_of[256] = {};  // letter -> matrix column (fallback: N, else last column)
+  uint8_t comp_code[kMaxAlpha] = {};  // column of the complementary letter
+  std::string name;           // basename, reported as matrixName (CrossmatchSearchEngine.pm:398-409)
+
+  static ScoreMatrix from_file(const std::string& path);
+  void finish();  // freqs -> lambda (Matrix.pm:397-464), letter maps
+  int min_score() const;
+  int max_score() const;
+};
+
+struct SeqSet {
+  std::vector<std::string> names;
+  std::vector<std::string> seqs;  // upper-case letters (FastaDB.pm:1110-1118 upper-cases on load)
+  int64_t total_bases() const {
+    int64_t t = 0;
+    for (auto& s : seqs) t += (int64_t)s.size();
+    return t;
+  }
+  static SeqSet from_fasta(const std::string& path);
+  static SeqSet from_arrays(int32_t n, const char* const* names, const char* const* seqs, const int32_t* lens);
+};
+
+char complement_letter(char c);  // table of CrossmatchSearchEngine.pm:833
+std::string revcomp_letters(const std::string& s);
+
+// SearchResult.pm:2111-2150 in double precision, perl int() truncation.
+int complexity_adjust(int raw, const int64_t counts[kMaxAlpha], const ScoreMatrix& m);
+
+}  // namespace rmgpu

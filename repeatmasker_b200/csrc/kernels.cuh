@@ -1,0 +1,706 @@
+// kernels.cuh -- sm_100a device code of librmgpu.
+//
+//   K0 build_streams      packed 4-bit query -> per-column PRMT selector stream (both strands) + 1-byte code streams
+//   K0 build_profile      packed library rows -> 8-byte per-row score profile for the batch's residue classes
+//   K1 swg_score_kernel   strand-paired int16x2 Smith-Waterman-Gotoh score pass (DPX: VIADDMNMX/VIMNMX3/VIADD.16x2)
+//   K2 swg_origin_kernel  int32 Smith-Waterman-Gotoh with alignment-origin propagation -> candidate table
+//   K3 traceback_kernel   banded global traceback between origin and end cell
+//
+// Scoring convention (SearchResult.pm:1829-1852, :1894-1917): score = M[subject][query]; the first base of a gap
+// costs gap_init, further bases ins_gap_ext (gap in the subject row, "E") or del_gap_ext (gap in the query row, "F").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rmgpu {
+
+constexpr int kPadClass = 7;            // residue class whose score is very negative: columns outside the query
+constexpr uint32_t kPadSel = 0xF7F7u;   // PRMT selector picking class 7 for both strands (sign-replicated)
+constexpr int kWarp = 32;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Inter-warp systolic pipeline through global memory.
+// A "stripe" is 32 lanes x R subject rows.  A subject longer than one stripe spans consecutive stripes; stripe k+1
+// consumes, per query column, the (H, F) of stripe k's last row.  Stripes are claimed through a global ticket
+// counter in order, by persistent warps that are all co-resident, so a consumer only ever waits on an older ticket
+// that is running or finished (no deadlock).  Progress is published per 32-column block.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// prmt.b32 in its generic form: selector nibble bit 3 replicates the sign of the selected byte.  (__byte_perm masks
+// the selector with 0x7777, which would drop exactly that bit.)
+__device__ __forceinline__ uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ void wait_ge(const int* p, int want) {
+  unsigned ns = 32;
+  while (ld_acquire(p) < want) {
+    __nanosleep(ns);
+    if (ns < 1024) ns <<= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K0: query streams.  qpacked: 4-bit codes, two per byte (low nibble first), query q at nibble offset qoff[q].
+// sel[selOff[q] + i], i in [0, selLen[q]): 16-bit PRMT selector {cf, cf|8, cr, cr|8} (cf/cr = residue class of the
+// forward / reverse-complement strand at column i); columns >= Q get kPadSel.
+// codes_fwd / codes_rc: matrix-column codes per column (1 byte) for K2/K3.
+// ---------------------------------------------------------------------------------------------------------------
+struct StreamArgs {
+  const uint8_t* qpacked;
+  const int64_t* qoff;    // nibble offset of query q (even)
+  const int32_t* qlen;
+  const int64_t* selOff;  // element offset into sel
+  const int32_t* selLen;
+  uint16_t* sel;
+  uint8_t* codes_fwd;     // [qoff[q] + i]
+  uint8_t* codes_rc;
+  int nQueries;
+  uint8_t class_of_code[16];
+  uint8_t comp_code[16];
+};
+
+__global__ void build_streams_kernel(StreamArgs a) {
+  int q = blockIdx.y;
+  int Q = a.qlen[q];
+  int n = a.selLen[q];
+  int64_t base = a.qoff[q];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t s = kPadSel;
+    if (i < Q) {
+      int64_t nf = base + i, nr = base + (Q - 1 - i);
+      uint8_t cf = (a.qpacked[nf >> 1] >> ((nf & 1) * 4)) & 15;
+      uint8_t cr = a.comp_code[(a.qpacked[nr >> 1] >> ((nr & 1) * 4)) & 15];
+      a.codes_fwd[base + i] = cf;
+      a.codes_rc[base + i] = cr;
+      uint32_t kf = a.class_of_code[cf], kr = a.class_of_code[cr];
+      s = kf | ((kf | 8u) << 4) | (kr << 8) | ((kr | 8u) << 12);
+    }
+    a.sel[a.selOff[q] + i] = (uint16_t)s;
+  }
+}
+
+// K0: profile.  rowcode[g*R + r] = matrix row (subject residue) or 0xFF for pad rows.
+// prof[g*R + r] = 8 signed bytes: score of that subject residue against residue classes 0..6, class 7 = pad.
+struct ProfileArgs {
+  const uint8_t* rowcode;
+  uint2* prof;
+  int64_t nRows;
+  int8_t class_score[16][8];  // [subject code][class]; for merged classes: max over member codes (upper bound)
+};
+
+__global__ void build_profile_kernel(ProfileArgs a) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.nRows; i += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t c = a.rowcode[i];
+    uint32_t lo, hi;
+    if (c == 0xFF) {
+      lo = 0x80808080u;
+      hi = 0x80808080u;
+    } else {
+      const int8_t* s = a.class_score[c];
+      lo = (uint8_t)s[0] | ((uint32_t)(uint8_t)s[1] << 8) | ((uint32_t)(uint8_t)s[2] << 16) | ((uint32_t)(uint8_t)s[3] << 24);
+      hi = (uint8_t)s[4] | ((uint32_t)(uint8_t)s[5] << 8) | ((uint32_t)(uint8_t)s[6] << 16) | (0x80u << 24);
+    }
+    a.prof[i] = make_uint2(lo, hi);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1: score pass.  Each lane owns R consecutive subject rows (a "group"); the two 16-bit halves of every register
+// are the forward and the reverse-complement strand of the same query (identical dimensions, so they pair
+// perfectly).  With E' = E - gap_init and F' = F - gap_init every state value is >= 0:
+//     E'[i][j] = max(E'[i-1][j] + ins_ext, H[i-1][j])                  VIADDMNMX.S16x2
+//     F'[i][j] = max(F'[i][j-1] + del_ext, H[i][j-1])                  VIADDMNMX.S16x2
+//     H[i][j]  = max(0, H[i-1][j-1] + s, max(E',F') + gap_init)        PRMT, VIADD.16x2, VIMNMX.S16x2, VIADDMNMX.S16x2.RELU
+// Lane t works on column (step - t): an anti-diagonal wavefront; the last row's (H, F') and the column's selector
+// move one lane down per step by warp shuffle.  int16 overflow: a pair whose best reaches 32000 is re-done by K2 in
+// int32 like every pair with best >= minscore, so wrapped values never reach a result.
+// ---------------------------------------------------------------------------------------------------------------
+struct ScoreArgs {
+  const uint2* prof;          // [nGroups * R]
+  const uint8_t* gflags;      // [nGroups] bit0: group starts a subject
+  const int32_t* gsubject;    // [nGroups] subject id or -1 (unused lanes)
+  const uint8_t* sflags;      // [nStripes] bit0 has_prev, bit1 has_next
+  const uint16_t* sel;
+  const int64_t* selOff;
+  const int32_t* qlen;
+  int nQueries, nStripes, nSubjects;
+  int32_t* pairbest;          // [nQueries * nSubjects * 2] raw best per strand (atomicMax)
+  uint2* bnd;                 // [nslot * bndStride] (H, F') of the stripe's last row per column
+  int64_t bndStride;
+  int nslot;
+  int* progress;              // [nTickets] completed 32-column blocks of the boundary
+  int* finished;              // [nTickets]
+  int* ticket;                // global ticket counter
+  uint32_t gi2, ie2, de2;     // penalties replicated in both halves
+};
+
+template <int R>
+__global__ void __launch_bounds__(256) swg_score_kernel(ScoreArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int nTickets = a.nQueries * a.nStripes;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= nTickets) break;
+    const int q = t / a.nStripes, k = t - q * a.nStripes;
+    const int g = k * 32 + lane;
+    const int Q = a.qlen[q];
+    const uint8_t sf = a.sflags[k];
+    const bool hasPrev = sf & 1, hasNext = sf & 2;
+    const bool startFlag = a.gflags[g] & 1;
+    const uint16_t* sel = a.sel + a.selOff[q];
+    uint32_t Plo[R], Phi[R], H[R], E[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      uint2 p = __ldg(&a.prof[(int64_t)g * R + r]);
+      Plo[r] = p.x;
+      Phi[r] = p.y;
+      H[r] = 0;
+      E[r] = 0;
+    }
+    const int qBlocks = (Q + 31) >> 5;
+    const int nBlocks = qBlocks + 1;  // lane 31 reaches column qBlocks*32 >= Q
+    const uint2* bndIn = a.bnd + (int64_t)((t - 1 + a.nslot) % a.nslot) * a.bndStride;
+    uint2* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
+    if (hasNext && t >= a.nslot) {  // the slot's previous reader must be done
+      if (lane == 0) wait_ge(&a.finished[t - a.nslot + 1], 1);
+      __syncwarp();
+    }
+    uint32_t best = 0, outH = 0, outF = 0, diag = 0, curSel = kPadSel;
+    uint32_t wbH = 0, wbF = 0;
+    for (int b = 0; b < nBlocks; b++) {
+      uint32_t selv = sel[b * 32 + lane];
+      uint2 bv = make_uint2(0u, 0u);
+      if (hasPrev && b < qBlocks) {
+        if (lane == 0) wait_ge(&a.progress[t - 1], b + 1);
+        __syncwarp();
+        bv = __ldcg(&bndIn[b * 32 + lane]);
+      }
+#pragma unroll 4
+      for (int j = 0; j < 32; j++) {
+        uint32_t inSel = __shfl_up_sync(0xffffffffu, curSel, 1);
+        uint32_t inH = __shfl_up_sync(0xffffffffu, outH, 1);
+        uint32_t inF = __shfl_up_sync(0xffffffffu, outF, 1);
+        uint32_t fs = __shfl_sync(0xffffffffu, selv, j);
+        uint32_t fh = __shfl_sync(0xffffffffu, bv.x, j);
+        uint32_t ff = __shfl_sync(0xffffffffu, bv.y, j);
+        if (lane == 0) {
+          inSel = fs;
+          inH = fh;
+          inF = ff;
+        }
+        if (startFlag) {
+          inH = 0;
+          inF = 0;
+        }
+        curSel = inSel;
+        uint32_t hd = diag, hu = inH, f = inF;
+        diag = inH;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          uint32_t s = prmt(Plo[r], Phi[r], curSel);
+          uint32_t hl = H[r];
+          E[r] = __viaddmax_s16x2(E[r], a.ie2, hl);
+          f = __viaddmax_s16x2(f, a.de2, hu);
+          uint32_t m = __vmaxs2(E[r], f);
+          uint32_t d = __vadd2(hd, s);
+          uint32_t h = __viaddmax_s16x2_relu(m, a.gi2, d);
+          hd = hl;
+          H[r] = h;
+          hu = h;
+          best = __vmaxs2(best, h);
+        }
+        outH = hu;
+        outF = f;
+        if (hasNext) {
+          // lane 31 has just finished column c = b*32 + j - 31; lane (c & 31) keeps it for a coalesced store
+          uint32_t oh = __shfl_sync(0xffffffffu, outH, 31);
+          uint32_t of = __shfl_sync(0xffffffffu, outF, 31);
+          int c = b * 32 + j - 31;
+          if (lane == (c & 31)) {
+            wbH = oh;
+            wbF = of;
+          }
+          if (c >= 0 && (c & 31) == 31) {  // column block complete
+            bndOut[(c & ~31) + lane] = make_uint2(wbH, wbF);
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release(&a.progress[t], (c >> 5) + 1);
+          }
+        }
+      }
+    }
+    // per (query, subject, strand) best
+    int sj = a.gsubject[g];
+    if (sj >= 0) {
+      int f = (int)(int16_t)(best & 0xffffu), rc = (int)(int16_t)(best >> 16);
+      // an int16 wrap shows up as a negative or >= 32000 best: report 32767 so the pair goes to the int32 pass
+      if (f < 0 || f >= 32000) f = 32767;
+      if (rc < 0 || rc >= 32000) rc = 32767;
+      int32_t* pb = a.pairbest + ((int64_t)q * a.nSubjects + sj) * 2;
+      if (f > 0) atomicMax(pb, f);
+      if (rc > 0) atomicMax(pb + 1, rc);
+    }
+    __syncwarp();
+    if (lane == 0) st_release(&a.finished[t], 1);
+  }
+}
+
+// Register-resident loop of the bare K1 recurrence: the measured integer-SIMD peak used as the roofline denominator
+// (SURVEY 8d).  No shuffles, no memory: 32 lanes x R rows x iters columns x 2 strands cells per warp.
+template <int R>
+__global__ void dpx_peak_kernel(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t Plo[R], Phi[R], H[R], E[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    Plo[r] = 0x090af1f0u + r * 0x01010101u + threadIdx.x;
+    Phi[r] = 0xf1f60a09u ^ (r * 0x00010001u);
+    H[r] = 0;
+    E[r] = 0;
+  }
+  uint32_t best = 0, sel = 0x9180u | (seed & 0x0303u), diag = 0, hu = 0, f = 0;
+  const uint32_t gi2 = 0xffe2ffe2u, ie2 = 0xfffafffau, de2 = 0xfffbfffbu;
+  for (int it = 0; it < iters; it++) {
+    uint32_t hd = diag;
+    diag = hu;
+    sel = ((sel + 0x0101u) & 0x0303u) | 0x9180u;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      uint32_t s = prmt(Plo[r], Phi[r], sel);
+      uint32_t hl = H[r];
+      E[r] = __viaddmax_s16x2(E[r], ie2, hl);
+      f = __viaddmax_s16x2(f, de2, hu);
+      uint32_t m = __vmaxs2(E[r], f);
+      uint32_t d = __vadd2(hd, s);
+      uint32_t h = __viaddmax_s16x2_relu(m, gi2, d);
+      hd = hl;
+      H[r] = h;
+      hu = h;
+      best = __vmaxs2(best, h);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = best;
+}
+
+// Pure VIADDMNMX.S16x2 issue rate (8 independent chains per thread).
+__global__ void dpx_instr_kernel(uint32_t* out, int iters) {
+  uint32_t x[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) x[r] = threadIdx.x + r;
+  const uint32_t c1 = 0x00010003u, c2 = 0x00050007u;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = __viaddmax_s16x2(x[r], c1, c2 + it);
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int r = 0; r < 8; r++) s ^= x[r];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2: origin pass.  int32 Smith-Waterman-Gotoh over one (query, strand, subject) triple, every positive cell carrying
+// the origin (i0, j0) of its alignment.  Tie-breaks: E over F over diagonal; extension over opening (the rule that
+// reproduces real cross_match alignments, tests/test_oracle_golden.py).  A cell reached by the diagonal with
+// H >= minscore is a candidate end: per (task, origin) the table keeps max score, then min i, then min j.
+// Same stripe pipeline as K1 with R2 rows per lane.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kR2 = 4;
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+struct OriginTask {
+  int32_t q, strand, subject;
+  int32_t firstTicket, nStripes;  // stripes of kR2*32 rows
+};
+
+struct OriginBoundary {  // per column, last row of the stripe above
+  int32_t h, f;
+  uint32_t oh, of;
+};
+
+struct OriginArgs {
+  const OriginTask* tasks;
+  const int32_t* ticketTask;   // [nTickets] task index
+  int nTickets;
+  const uint8_t* codes_fwd;    // query columns
+  const uint8_t* codes_rc;
+  const int64_t* qoff;
+  const int32_t* qlen;
+  const uint8_t* scodes;       // subject rows (1 byte per base)
+  const int64_t* soff;
+  const int32_t* slen;
+  int32_t mat[16][16];         // [subject][query]
+  int32_t gap_init, ins_ext, del_ext, minscore;
+  OriginBoundary* bnd;         // [nslot * bndStride]
+  int64_t bndStride;
+  int nslot;
+  int* progress;
+  int* finished;
+  int* ticket;
+  unsigned long long* keys;    // open-addressing table
+  unsigned long long* vals;
+  uint32_t tableMask;
+  int* overflow;
+};
+
+// An origin (i0, j0) is carried as one 32-bit word i0 * (L + 1) + j0 (L = subject length); the host checks
+// (Q + 1) * (L + 1) < 2^32 per task (any SimpleBatcher fragment, <= 75 kbp, against subjects up to 57 kbp).
+__device__ __forceinline__ void origin_emit(const OriginArgs& a, int task, uint32_t origin, int h, int i, int j) {
+  uint64_t key = ((uint64_t)(uint32_t)task << 32) | origin;
+  uint64_t val = ((uint64_t)(uint32_t)h << 40) | ((uint64_t)(0xFFFFFu - (uint32_t)i) << 20) | (uint64_t)(0xFFFFFu - (uint32_t)j);
+  uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & a.tableMask;
+  for (uint32_t probe = 0; probe <= a.tableMask; probe++) {
+    unsigned long long old = atomicCAS(&a.keys[slot], kEmptyKey, key);
+    if (old == kEmptyKey || old == key) {
+      atomicMax(&a.vals[slot], val);
+      return;
+    }
+    slot = (slot + 1) & a.tableMask;
+  }
+  atomicExch(a.overflow, 1);
+}
+
+__global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
+  __shared__ int32_t smat[16 * 16];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  constexpr int R = kR2;
+  const int NEGI = -(1 << 28);
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= a.nTickets) break;
+    const int ti = a.ticketTask[t];
+    const OriginTask tk = a.tasks[ti];
+    const int k = t - tk.firstTicket;
+    const int Q = a.qlen[tk.q], L = a.slen[tk.subject];
+    const uint32_t Lp1 = (uint32_t)L + 1u;
+    const uint8_t* qc = (tk.strand ? a.codes_rc : a.codes_fwd) + a.qoff[tk.q];
+    const uint8_t* sc = a.scodes + a.soff[tk.subject];
+    const bool hasPrev = k > 0, hasNext = k + 1 < tk.nStripes;
+    const int row0 = (k * 32 + lane) * R;  // 0-based subject row of this lane's first row
+    int srow[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) srow[r] = (row0 + r < L) ? (int)sc[row0 + r] * 16 : -1;
+    int H[R], E[R];
+    uint32_t oH[R], oE[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      H[r] = 0;
+      E[r] = NEGI;
+      oH[r] = 0;
+      oE[r] = 0;
+    }
+    const int qBlocks = (Q + 31) >> 5, nBlocks = qBlocks + 1;
+    const OriginBoundary* bndIn = a.bnd + (int64_t)((t - 1 + a.nslot) % a.nslot) * a.bndStride;
+    OriginBoundary* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
+    if (hasNext && t >= a.nslot) {
+      if (lane == 0) wait_ge(&a.finished[t - a.nslot + 1], 1);
+      __syncwarp();
+    }
+    int outH = 0, outF = NEGI, diagH = 0, curQ = -1;
+    uint32_t outOH = 0, outOF = 0, diagO = 0;
+    OriginBoundary wb = {0, NEGI, 0, 0};
+    uint32_t lastOrigin = 0xFFFFFFFFu;
+    int lastBest = 0;
+    for (int b = 0; b < nBlocks; b++) {
+      int col = b * 32 + lane;
+      int qv = (col < Q) ? (int)qc[col] : -1;
+      OriginBoundary bv = {0, NEGI, 0, 0};
+      if (hasPrev && b < qBlocks) {
+        if (lane == 0) wait_ge(&a.progress[t - 1], b + 1);
+        __syncwarp();
+        const int4 raw = __ldcg(reinterpret_cast<const int4*>(&bndIn[col]));
+        bv.h = raw.x;
+        bv.f = raw.y;
+        bv.oh = (uint32_t)raw.z;
+        bv.of = (uint32_t)raw.w;
+      }
+      for (int j = 0; j < 32; j++) {
+        int inQ = __shfl_up_sync(0xffffffffu, curQ, 1);
+        int inH = __shfl_up_sync(0xffffffffu, outH, 1);
+        int inF = __shfl_up_sync(0xffffffffu, outF, 1);
+        uint32_t inOH = __shfl_up_sync(0xffffffffu, outOH, 1);
+        uint32_t inOF = __shfl_up_sync(0xffffffffu, outOF, 1);
+        int fq = __shfl_sync(0xffffffffu, qv, j);
+        int fh = __shfl_sync(0xffffffffu, bv.h, j);
+        int ff = __shfl_sync(0xffffffffu, bv.f, j);
+        uint32_t foh = __shfl_sync(0xffffffffu, bv.oh, j);
+        uint32_t fof = __shfl_sync(0xffffffffu, bv.of, j);
+        if (lane == 0) {
+          inQ = fq;
+          inH = fh;
+          inF = ff;
+          inOH = foh;
+          inOF = fof;
+        }
+        curQ = inQ;
+        const int i1 = b * 32 + j - lane + 1;  // 1-based query column of this lane at this step
+        int hd = diagH, hu = inH, f = inF;
+        uint32_t od = diagO, ou = inOH, of = inOF;
+        diagH = inH;
+        diagO = inOH;
+        const bool active = curQ >= 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          int hl = H[r];
+          uint32_t ol = oH[r];
+          int hnew = 0;
+          uint32_t onew = 0;
+          if (active && srow[r] >= 0) {
+            int e_ext = E[r] + a.ins_ext, e_open = hl + a.gap_init;
+            if (e_ext >= e_open) {
+              E[r] = e_ext;
+            } else {
+              E[r] = e_open;
+              oE[r] = ol;
+            }
+            int f_ext = f + a.del_ext, f_open = hu + a.gap_init;
+            if (f_ext >= f_open) {
+              f = f_ext;
+            } else {
+              f = f_open;
+              of = ou;
+            }
+            int s = smat[srow[r] + curQ];
+            int d = hd + s;
+            uint32_t odd = hd > 0 ? od : ((uint32_t)i1 * Lp1 + (uint32_t)(row0 + r + 1));
+            hnew = E[r];
+            onew = oE[r];
+            bool viaDiag = false;
+            if (f > hnew) {
+              hnew = f;
+              onew = of;
+            }
+            if (d > hnew) {
+              hnew = d;
+              onew = odd;
+              viaDiag = true;
+            }
+            if (hnew <= 0) {
+              hnew = 0;
+              onew = 0;
+              viaDiag = false;
+            }
+            if (viaDiag && hnew >= a.minscore) {
+              if (onew != lastOrigin || hnew > lastBest) {
+                origin_emit(a, ti, onew, hnew, i1, row0 + r + 1);
+                lastOrigin = onew;
+                lastBest = hnew;
+              }
+            }
+          } else {
+            // outside the matrix: keep a clean zero boundary
+            E[r] = NEGI;
+            f = NEGI;
+          }
+          hd = hl;
+          od = ol;
+          H[r] = hnew;
+          oH[r] = onew;
+          hu = hnew;
+          ou = onew;
+        }
+        outH = hu;
+        outF = f;
+        outOH = ou;
+        outOF = of;
+        if (hasNext) {
+          int oh = __shfl_sync(0xffffffffu, outH, 31);
+          int of2 = __shfl_sync(0xffffffffu, outF, 31);
+          uint32_t ooh = __shfl_sync(0xffffffffu, outOH, 31);
+          uint32_t oof = __shfl_sync(0xffffffffu, outOF, 31);
+          int c = b * 32 + j - 31;
+          if (lane == (c & 31)) {
+            wb.h = oh;
+            wb.f = of2;
+            wb.oh = ooh;
+            wb.of = oof;
+          }
+          if (c >= 0 && (c & 31) == 31) {
+            *reinterpret_cast<int4*>(&bndOut[(c & ~31) + lane]) = make_int4(wb.h, wb.f, (int)wb.oh, (int)wb.of);
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release(&a.progress[t], (c >> 5) + 1);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) st_release(&a.finished[t], 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3: banded global traceback, one thread per candidate (latency-bound; a few % of a stage).
+// Local coordinates u=1..n (query), v=1..m (subject); diagonals d=u-v in [dlo, dhi], dlo=min(0,n-m)-W,
+// dhi=max(0,n-m)+W.  The alignment must open with a diagonal at (1,1) and close with one at (n,m).
+// ops (written back to front): 0 = aligned pair, 1 = gap in subject row (query base), 2 = gap in query row.
+// status: 1 ok (banded score == raw), 0 band too narrow -> the host doubles W and retries that candidate.
+// ---------------------------------------------------------------------------------------------------------------
+struct TraceCand {
+  int32_t q, strand, subject;
+  int32_t i0, j0, i1, j1;   // 1-based, strand coordinates
+  int32_t raw;
+  int32_t W;                // band half-width for this attempt
+  int64_t dirOff;           // offset into dir scratch
+  int64_t rowOff;           // offset into row scratch (4 * bw ints)
+  int64_t opsOff;           // offset into ops
+};
+
+struct TraceArgs {
+  const TraceCand* cand;
+  int nCand;
+  const uint8_t* codes_fwd;
+  const uint8_t* codes_rc;
+  const int64_t* qoff;
+  const uint8_t* scodes;
+  const int64_t* soff;
+  int32_t mat[16][16];
+  int32_t gap_init, ins_ext, del_ext;
+  uint8_t* dir;
+  int32_t* rows;
+  uint8_t* ops;
+  int32_t* opsLen;   // [nCand] number of ops, or -1
+  int32_t* status;   // [nCand]
+};
+
+__global__ void traceback_kernel(TraceArgs a) {
+  __shared__ int32_t smat[16 * 16];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
+  __syncthreads();
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.nCand) return;
+  const TraceCand tc = a.cand[c];
+  const int NEGI = -(1 << 28);
+  const int n = tc.i1 - tc.i0 + 1, m = tc.j1 - tc.j0 + 1;
+  const uint8_t* qc = (tc.strand ? a.codes_rc : a.codes_fwd) + a.qoff[tc.q] + (tc.i0 - 1);
+  const uint8_t* sc = a.scodes + a.soff[tc.subject] + (tc.j0 - 1);
+  const int dlo = min(0, n - m) - tc.W, dhi = max(0, n - m) + tc.W;
+  const int bw = dhi - dlo + 1;
+  uint8_t* dir = a.dir + tc.dirOff;
+  int32_t* Hp = a.rows + tc.rowOff;
+  int32_t* Hn = Hp + bw;
+  int32_t* Ep = Hn + bw;
+  int32_t* En = Ep + bw;
+  for (int k = 0; k < bw; k++) {
+    Hp[k] = NEGI;
+    Ep[k] = NEGI;
+  }
+  Hp[-dlo] = 0;
+  for (int u = 1; u <= n; u++) {
+    const int qi = qc[u - 1];
+    int F = NEGI, hleft = NEGI;
+    for (int k = bw - 1; k >= 0; k--) {
+      const int v = u - (dlo + k);
+      if (v < 1 || v > m) {
+        Hn[k] = NEGI;
+        En[k] = NEGI;
+        if (v < 1) {
+          F = NEGI;
+          hleft = NEGI;
+        }
+        continue;
+      }
+      uint8_t bits = 0;
+      int e_ext = (k > 0 ? Ep[k - 1] : NEGI) + a.ins_ext;
+      int e_open = (k > 0 ? Hp[k - 1] : NEGI) + a.gap_init;
+      int E;
+      if (e_ext >= e_open) {
+        E = e_ext;
+        bits |= 4;
+      } else
+        E = e_open;
+      int f_ext = F + a.del_ext, f_open = hleft + a.gap_init;
+      if (f_ext >= f_open) {
+        F = f_ext;
+        bits |= 8;
+      } else
+        F = f_open;
+      int hd = Hp[k];
+      int D = hd > NEGI / 2 ? hd + smat[(int)sc[v - 1] * 16 + qi] : NEGI;
+      if (u == 1 && v == 1) {
+        E = NEGI;
+        F = NEGI;
+      }
+      int h = E;
+      uint8_t ch = 1;
+      if (F > h) {
+        h = F;
+        ch = 2;
+      }
+      if (D > h) {
+        h = D;
+        ch = 3;
+      }
+      if (h < NEGI / 2) h = NEGI;
+      if (E < NEGI / 2) E = NEGI;
+      if (F < NEGI / 2) F = NEGI;
+      Hn[k] = h;
+      En[k] = E;
+      hleft = h;
+      dir[(int64_t)u * bw + k] = bits | ch;
+    }
+    int32_t* tmp = Hp;
+    Hp = Hn;
+    Hn = tmp;
+    tmp = Ep;
+    Ep = En;
+    En = tmp;
+  }
+  const int kend = (n - m) - dlo;
+  int len = -1;
+  if (Hp[kend] == tc.raw && (dir[(int64_t)n * bw + kend] & 3) == 3) {
+    uint8_t* ops = a.ops + tc.opsOff;
+    int uu = n, vv = m, state = 0, pos = 0;
+    bool ok = true;
+    while (uu > 0 || vv > 0) {
+      if (uu < 1 || vv < 1) {
+        ok = false;
+        break;
+      }
+      int kk = (uu - vv) - dlo;
+      if (kk < 0 || kk >= bw) {
+        ok = false;
+        break;
+      }
+      uint8_t bch = dir[(int64_t)uu * bw + kk];
+      if (state == 0) {
+        int ch = bch & 3;
+        if (ch == 3) {
+          ops[pos++] = 0;
+          uu--;
+          vv--;
+        } else if (ch == 1)
+          state = 1;
+        else
+          state = 2;
+      } else if (state == 1) {
+        ops[pos++] = 1;
+        state = (bch & 4) ? 1 : 0;
+        uu--;
+      } else {
+        ops[pos++] = 2;
+        state = (bch & 8) ? 2 : 0;
+        vv--;
+      }
+    }
+    if (ok) len = pos;
+  }
+  a.opsLen[c] = len;
+  a.status[c] = len > 0 ? 1 : 0;
+}
+
+}  // namespace rmgpu

@@ -1,0 +1,251 @@
+"""ctypes binding of librmgpu.so and a Python mirror of the reference's engine interface.
+
+`GpuSearchEngine` follows SearchEngineI.pm:132-681 (the same setters) and CrossmatchSearchEngine.pm:381-524
+(`search()` returning `(status, results)`), so parity tests read like the reference's own engine tests.  The Perl
+plug-in that RepeatMasker itself loads is repeatmasker_b200/perl/GpuSearchEngine.pm; both sit on the same C ABI
+(include/rmgpu.h).  There is no CPU fallback: without the CUDA library or a device every call raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librmgpu.so")
+
+
+class RmgpuError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("gap_init", C.c_int32), ("ins_gap_ext", C.c_int32), ("del_gap_ext", C.c_int32),
+                ("minscore", C.c_int32), ("masklevel", C.c_int32), ("minmatch", C.c_int32), ("bandwidth", C.c_int32),
+                ("raw", C.c_int32), ("word_raw", C.c_int32), ("want_alignments", C.c_int32), ("device", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("score", C.c_int32), ("raw_score", C.c_int32), ("query_index", C.c_int32),
+                ("subject_index", C.c_int32), ("query_name", C.c_char_p), ("subject_name", C.c_char_p),
+                ("qstart", C.c_int32), ("qend", C.c_int32), ("qleft", C.c_int32), ("sstart", C.c_int32),
+                ("send", C.c_int32), ("sleft", C.c_int32), ("strand", C.c_uint8), ("overlap_star", C.c_uint8),
+                ("pad_", C.c_uint8 * 2), ("pct_div", C.c_char * 8), ("pct_del", C.c_char * 8),
+                ("pct_ins", C.c_char * 8), ("transitions", C.c_int32), ("transversions", C.c_int32),
+                ("ambiguous", C.c_int32), ("gap_inits", C.c_int32), ("gap_bases", C.c_int32), ("qaln", C.c_char_p),
+                ("saln", C.c_char_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("cells", C.c_double), ("ms_total", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double),
+                ("ms_score", C.c_double), ("ms_origin", C.c_double), ("ms_traceback", C.c_double),
+                ("ms_host_post", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("launches", C.c_int32), ("score_launches", C.c_int32), ("n_pairs_passed", C.c_int32),
+                ("n_candidates", C.c_int32), ("origin_cells", C.c_double)]
+
+
+class Result(C.Structure):
+    _fields_ = [("n_hits", C.c_int32), ("hits", C.POINTER(Hit)), ("stats", Stats), ("opaque", C.c_void_p)]
+
+
+_lib = None
+
+EXPORTS = ["rmgpu_version", "rmgpu_abi_version", "rmgpu_last_error", "rmgpu_search", "rmgpu_free",
+           "rmgpu_session_open", "rmgpu_session_close", "rmgpu_session_set_matrix_file", "rmgpu_session_set_library",
+           "rmgpu_session_set_library_fasta", "rmgpu_session_set_queries", "rmgpu_session_set_queries_fasta",
+           "rmgpu_session_search", "rmgpu_session_score_only", "rmgpu_session_counts", "rmgpu_measure_dpx_peak"]
+
+
+def lib():
+    """Load librmgpu.so (built in-tree by repeatmasker_b200/build.py).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RmgpuError(f"{LIB_PATH} is missing: run `python -m repeatmasker_b200.build` (no CPU fallback exists)")
+    L = C.CDLL(LIB_PATH)
+    L.rmgpu_version.restype = C.c_char_p
+    L.rmgpu_last_error.restype = C.c_char_p
+    L.rmgpu_search.argtypes = [C.POINTER(Params), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.POINTER(Result))]
+    L.rmgpu_free.argtypes = [C.POINTER(Result)]
+    L.rmgpu_session_open.restype = C.c_void_p
+    L.rmgpu_session_open.argtypes = [C.c_int]
+    L.rmgpu_session_close.argtypes = [C.c_void_p]
+    L.rmgpu_session_set_matrix_file.argtypes = [C.c_void_p, C.c_char_p]
+    seqargs = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]
+    L.rmgpu_session_set_library.argtypes = seqargs
+    L.rmgpu_session_set_queries.argtypes = seqargs
+    L.rmgpu_session_set_library_fasta.argtypes = [C.c_void_p, C.c_char_p]
+    L.rmgpu_session_set_queries_fasta.argtypes = [C.c_void_p, C.c_char_p]
+    L.rmgpu_session_search.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(C.POINTER(Result))]
+    L.rmgpu_session_score_only.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.rmgpu_session_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64)]
+    L.rmgpu_measure_dpx_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise RmgpuError(lib().rmgpu_last_error().decode())
+
+
+def _hits_to_dicts(res):
+    out = []
+    r = res.contents
+    for i in range(r.n_hits):
+        h = r.hits[i]
+        out.append(dict(score=h.score, raw_score=h.raw_score, div=h.pct_div.decode(), dele=h.pct_del.decode(),
+                        ins=h.pct_ins.decode(), qname=h.query_name.decode(), qstart=h.qstart, qend=h.qend,
+                        qleft=h.qleft, strand="C" if h.strand else "+", sname=h.subject_name.decode(),
+                        sstart=h.sstart, send=h.send, sleft=h.sleft, star=bool(h.overlap_star),
+                        qaln=(h.qaln or b"").decode(), saln=(h.saln or b"").decode(), ti=h.transitions,
+                        tv=h.transversions, query_index=h.query_index, subject_index=h.subject_index))
+    st = {k: getattr(r.stats, k) for k, _ in Stats._fields_}
+    return out, st
+
+
+def make_params(gap_init=-30, ins_gap_ext=-6, del_gap_ext=-5, minscore=225, masklevel=101, minmatch=9, bandwidth=14,
+                raw=False, word_raw=False, alignments=True, device=-1):
+    return Params(gap_init=gap_init, ins_gap_ext=ins_gap_ext, del_gap_ext=del_gap_ext, minscore=minscore,
+                  masklevel=masklevel, minmatch=minmatch, bandwidth=bandwidth, raw=int(raw), word_raw=int(word_raw),
+                  want_alignments=int(alignments), device=device)
+
+
+def _seq_arrays(names, seqs):
+    n = len(seqs)
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    bn = [(names[i] if names else f"seq{i}").encode() for i in range(n)]
+    return (n, (C.c_char_p * n)(*bn), (C.c_char_p * n)(*bs), (C.c_int32 * n)(*[len(b) for b in bs]))
+
+
+class Session:
+    """One GPU worker: matrix + library resident in HBM, query batches streamed through (rmgpu_session_*)."""
+
+    def __init__(self, device=-1):
+        self._h = lib().rmgpu_session_open(device)
+        if not self._h:
+            raise RmgpuError(lib().rmgpu_last_error().decode())
+
+    def close(self):
+        if self._h:
+            lib().rmgpu_session_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_matrix(self, path):
+        _check(lib().rmgpu_session_set_matrix_file(self._h, path.encode()))
+
+    def set_library(self, seqs, names=None):
+        _check(lib().rmgpu_session_set_library(self._h, *_seq_arrays(names, seqs)))
+
+    def set_library_fasta(self, path):
+        _check(lib().rmgpu_session_set_library_fasta(self._h, path.encode()))
+
+    def set_queries(self, seqs, names=None):
+        _check(lib().rmgpu_session_set_queries(self._h, *_seq_arrays(names, seqs)))
+
+    def set_queries_fasta(self, path):
+        _check(lib().rmgpu_session_set_queries_fasta(self._h, path.encode()))
+
+    def counts(self):
+        nq, ns, qb, sb = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+        lib().rmgpu_session_counts(self._h, C.byref(nq), C.byref(ns), C.byref(qb), C.byref(sb))
+        return nq.value, ns.value, qb.value, sb.value
+
+    def search(self, params):
+        res = C.POINTER(Result)()
+        _check(lib().rmgpu_session_search(self._h, C.byref(params), C.byref(res)))
+        try:
+            return _hits_to_dicts(res)
+        finally:
+            lib().rmgpu_free(res)
+
+    def score_only(self, params):
+        """K1 only: (best[nq][ns][2] as a flat list, kernel ms)."""
+        nq, ns, _, _ = self.counts()
+        buf = (C.c_int32 * max(nq * ns * 2, 1))()
+        ms = C.c_double()
+        _check(lib().rmgpu_session_score_only(self._h, C.byref(params), buf, C.byref(ms)))
+        return list(buf)[: nq * ns * 2], ms.value
+
+
+def search_files(query, subject, matrix, **kw):
+    """rmgpu_search(): the call that stands where CrossmatchSearchEngine.pm:444 popen()s cross_match."""
+    p = make_params(**kw)
+    res = C.POINTER(Result)()
+    _check(lib().rmgpu_search(C.byref(p), query.encode(), subject.encode(), matrix.encode(), C.byref(res)))
+    try:
+        return _hits_to_dicts(res)
+    finally:
+        lib().rmgpu_free(res)
+
+
+def measure_dpx_peak(device=-1):
+    cups, ips = C.c_double(), C.c_double()
+    _check(lib().rmgpu_measure_dpx_peak(device, C.byref(cups), C.byref(ips)))
+    return cups.value, ips.value
+
+
+class GpuSearchEngine:
+    """Python mirror of the engine plug-in contract (SearchEngineI.pm), GPU sibling of CrossmatchSearchEngine.pm."""
+
+    basicScoreMode = 1  # SearchEngineI.pm:77
+    complexityAdjustedScoreMode = 2  # SearchEngineI.pm:78
+
+    def __init__(self, device=-1):
+        self._v = dict(query=None, subject=None, matrix=None, gapInit=None, insGapExt=None, delGapExt=None,
+                       minMatch=None, minScore=None, bandwidth=None, maskLevel=None, scoreMode=2,
+                       generateAlignments=0, wordRaw=0, device=device)
+        self.last_stats = None
+
+    def __getattr__(self, name):
+        if name.startswith("set") or name.startswith("get"):
+            key = name[3].lower() + name[4:]
+            if key in self.__dict__.get("_v", {}):
+                if name.startswith("set"):
+                    def setter(value):
+                        old = self._v[key]
+                        self._v[key] = value
+                        return old
+                    return setter
+                return lambda: self._v[key]
+        raise AttributeError(name)
+
+    def getVersion(self):
+        return lib().rmgpu_version().decode()
+
+    def getParameters(self):
+        v = self._v
+        for k in ("query", "subject", "matrix"):
+            if not v[k] or not os.path.isfile(v[k]):
+                raise RmgpuError(f"GpuSearchEngine::getParameters: Error...{k} ({v[k]}) does not exist!")
+        s = "rmgpu"
+        if v["scoreMode"] == self.basicScoreMode:
+            s += " -raw"
+        if v["wordRaw"]:
+            s += " -word_raw"
+        if v["generateAlignments"]:
+            s += " -alignments"
+        for opt, key in (("gap_init", "gapInit"), ("ins_gap_ext", "insGapExt"), ("del_gap_ext", "delGapExt"),
+                         ("minmatch", "minMatch"), ("minscore", "minScore"), ("bandwidth", "bandwidth"),
+                         ("masklevel", "maskLevel")):
+            if v[key] is not None:
+                s += f" -{opt} {v[key]}"
+        return s + f" -matrix {v['matrix']} {v['query']} {v['subject']}"
+
+    def search(self, **kw):
+        """Returns (status, hits) like CrossmatchSearchEngine.pm:381-524; status 0 = success."""
+        for k, val in kw.items():
+            getattr(self, "set" + k[0].upper() + k[1:])(val)
+        self.getParameters()  # croaks on missing files like the reference
+        v = self._v
+        d = lambda x, dflt: dflt if x is None else x
+        hits, st = search_files(v["query"], v["subject"], v["matrix"], gap_init=d(v["gapInit"], -4),
+                                ins_gap_ext=d(v["insGapExt"], -3), del_gap_ext=d(v["delGapExt"], -3),
+                                minscore=d(v["minScore"], 30), masklevel=d(v["maskLevel"], 80),
+                                minmatch=d(v["minMatch"], 14), bandwidth=d(v["bandwidth"], 14),
+                                raw=v["scoreMode"] == self.basicScoreMode, word_raw=bool(v["wordRaw"]),
+                                alignments=bool(v["generateAlignments"]), device=v["device"])
+        self.last_stats = st
+        return 0, hits

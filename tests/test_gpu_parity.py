@@ -1,0 +1,182 @@
+"""GPU parity tests: librmgpu (through the C ABI) against the CPU oracle and the committed golden fixtures.
+Bit-exact on every reported field.  Run on the B200 box: python -m pytest tests -m gpu"""
+import ctypes as C
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import util
+from repeatmasker_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("score", "div", "dele", "ins", "qname", "qstart", "qend", "qleft", "strand", "sname", "sstart", "send",
+          "sleft", "star")
+
+
+def assert_same_hits(got, want, aln=True):
+    assert len(got) == len(want), (len(got), len(want))
+    for g, w in zip(got, want):
+        for k in FIELDS:
+            assert g[k] == w[k], (k, g, w)
+        if aln:
+            assert g["qaln"] == w["qaln"] and g["saln"] == w["saln"], (g, w)
+            if "ti" in w:
+                assert (g["ti"], g["tv"]) == (w["ti"], w["tv"])
+
+
+def both(tmp_path, qnames, qseqs, snames, sseqs, matrix="20p43g.matrix", **kw):
+    q, s, m = str(tmp_path / "q.fa"), str(tmp_path / "s.fa"), str(tmp_path / "m.matrix")
+    synth.write_fasta(q, qnames, qseqs)
+    synth.write_fasta(s, snames, sseqs)
+    if os.path.exists(matrix):
+        m = matrix
+    else:
+        util.write_matrix(matrix, m)
+    want, _ = util.run_oracle(q, s, m, **kw)
+    got, st = engine.search_files(q, s, m, **kw)
+    return got, want, st
+
+
+KAT = json.load(open(os.path.join(util.GOLD, "seq1_2.json")))
+
+
+@pytest.mark.parametrize("ml", [101, 98, 97])
+def test_kat_seq1_2_against_real_cross_match_fixture(tmp_path, ml):
+    """t/seqs/masklevel/seq1-2-ml*.out: the hit lines real cross_match printed, through the GPU engine."""
+    (tmp_path / "q.fa").write_text(KAT["query_fasta"])
+    (tmp_path / "s.fa").write_text(KAT["subject_fasta"])
+    (tmp_path / "m.matrix").write_text(KAT["matrix_text"])
+    p = KAT["params"]
+    kw = dict(gap_init=p["gap_init"], ins_gap_ext=p["ins_gap_ext"], del_gap_ext=p["del_gap_ext"], minscore=p["minscore"],
+              masklevel=ml, minmatch=p["minmatch"], bandwidth=p["bandwidth"])
+    got, st = engine.search_files(str(tmp_path / "q.fa"), str(tmp_path / "s.fa"), str(tmp_path / "m.matrix"), **kw)
+    assert_same_hits(got, KAT[f"hits_ml{ml}"], aln=False)
+    want, _ = util.run_oracle(str(tmp_path / "q.fa"), str(tmp_path / "s.fa"), str(tmp_path / "m.matrix"), **kw)
+    assert_same_hits(got, want)
+    assert st["launches"] >= 3 and st["cells"] == 2 * 2604 * 2797
+
+
+def test_score_pass_equals_oracle_best(tmp_path):
+    """K1 (int16x2 DPX) best score per (query, subject, strand) == the oracle's exhaustive best, ragged sizes."""
+    rng = np.random.default_rng(7)
+    m = util.write_matrix("20p43g.matrix", str(tmp_path / "m.matrix"))
+    om = util.parse_matrix(m)
+    snames, sseqs = synth.make_library(11, n_families=40, lo=20, hi=3000)
+    sseqs[3] = sseqs[3][:7]  # shorter than one row group
+    sseqs[5] = sseqs[5] * 3 if len(sseqs[5]) < 1500 else sseqs[5]
+    genome, _ = synth.make_genome(12, 6000, sseqs, coverage=0.5)
+    qseqs = [genome[:3111], genome[3111:3143], genome[3143:], "ACGT"]
+    s = engine.Session()
+    s.set_matrix(m)
+    s.set_library(sseqs, snames)
+    s.set_queries(qseqs)
+    p = engine.make_params()
+    best, ms = s.score_only(p)
+    op = util.OraParams(gap_init=-30, ins_gap_ext=-6, del_gap_ext=-5)
+    lib = util.oracle_lib()
+    for qi, q in enumerate(qseqs):
+        for strand, ql in enumerate((q, synth.revcomp(q))):
+            qc = util.encode(om, ql)
+            for si, sq in enumerate(sseqs):
+                want = lib.ora_sw_score(qc, len(qc), util.encode(om, sq), len(sq), C.byref(om), C.byref(op))
+                assert best[(qi * len(sseqs) + si) * 2 + strand] == want, (qi, si, strand)
+    s.close()
+
+
+def test_synthetic_genome_full_parity(tmp_path):
+    """Implanted diverged copies, both strands, several fragments: every hit field and alignment row identical."""
+    snames, sseqs = synth.make_library(101, n_families=60, lo=60, hi=2500)
+    genome, truth = synth.make_genome(102, 30000, sseqs, coverage=0.45)
+    qn, qs = synth.fragment(genome, "chrS", frag=12000, overlap=500)
+    got, want, st = both(tmp_path, qn, qs, snames, sseqs)
+    assert len(want) > 10
+    assert_same_hits(got, want)
+    assert any(h["strand"] == "C" for h in got) and any(h["strand"] == "+" for h in got)
+
+
+def test_long_subject_chains_and_int16_overflow(tmp_path):
+    """A 9 kbp subject (35 stripes of 256 rows) and a near-identical 6 kbp copy: raw score > 32767 forces the
+    int32 pass; stripe-to-stripe boundaries must be exact."""
+    rng = np.random.default_rng(5)
+    long_s = synth.random_dna(rng, 9000).tobytes().decode()
+    other = synth.random_dna(rng, 700).tobytes().decode()
+    copy = synth.mutate(rng, long_s[1500:7600], 0.02, 0.002)
+    bg = synth.random_dna(rng, 9000).tobytes().decode()
+    q = bg[:2000] + copy + bg[2000:4000] + synth.revcomp(synth.mutate(rng, other, 0.15, 0.02)) + bg[4000:]
+    got, want, st = both(tmp_path, ["q1"], [q], ["longS#LINE/L1", "short#SINE/x"], [long_s, other])
+    assert max(h["score"] for h in want) > 32767
+    assert_same_hits(got, want)
+
+
+def test_alphabet_edge_cases(tmp_path):
+    """N runs, X (masked), lower-case x (excision sentinel), IUPAC codes incl. B/D/H/V, >7 residue classes."""
+    rng = np.random.default_rng(9)
+    cons = synth.random_dna(rng, 600).tobytes().decode()
+    c2 = synth.random_dna(rng, 400).tobytes().decode()
+    cons_amb = cons[:100] + "R" + cons[101:200] + "Y" + cons[201:300] + "N" + cons[301:]
+    copy = list(synth.mutate(rng, cons, 0.1, 0.01))
+    for pos, ch in ((50, "N"), (51, "N"), (120, "R"), (200, "K"), (260, "M"), (300, "S"), (310, "W"), (320, "B"),
+                    (330, "D"), (340, "H"), (350, "V"), (400, "X")):
+        copy[pos] = ch
+    copy = "".join(copy)
+    bg = synth.random_dna(rng, 3000).tobytes().decode()
+    q = bg[:700] + copy + "NNNNNNNNNNNNNNNNNNNN" + bg[700:1500] + "x" + synth.mutate(rng, c2, 0.12, 0.01) + "XXXXXXXXXX" + bg[1500:]
+    got, want, st = both(tmp_path, ["amb"], [q], ["cons#DNA/x", "c2#LTR/y"], [cons_amb, c2])
+    assert len(want) >= 2
+    assert_same_hits(got, want)
+
+
+@pytest.mark.parametrize("matrix,gi,ie,de", [("14p41g.matrix", -35, -7, -6), ("18p41g.matrix", -30, -6, -5),
+                                            ("25p41g.matrix", -27, -6, -5)])
+@pytest.mark.parametrize("raw", [False, True])
+def test_matrix_sweep(tmp_path, matrix, gi, ie, de, raw):
+    """BASELINE config 4 in miniature: GC-binned matrices x recipes (RepeatMasker:2146-2366), adjusted and -raw,
+    with simple-repeat / low-complexity content."""
+    rng = np.random.default_rng(31)
+    snames, sseqs = synth.make_library(33, n_families=25, lo=80, hi=1200)
+    sseqs.append("CA" * 90)
+    snames.append("(CA)n#Simple_repeat")
+    sseqs.append("A" * 150)
+    snames.append("(A)n#Simple_repeat")
+    genome, _ = synth.make_genome(34, 12000, sseqs[:25], coverage=0.4)
+    g = genome[:5000] + "CA" * 40 + "CG" + "CA" * 30 + genome[5000:9000] + "A" * 70 + "G" + "A" * 40 + genome[9000:]
+    got, want, st = both(tmp_path, ["gcblock"], [g], snames, sseqs, matrix=matrix, gap_init=gi, ins_gap_ext=ie,
+                         del_gap_ext=de, minscore=180, raw=raw)
+    assert len(want) > 5
+    assert_same_hits(got, want)
+
+
+def test_empty_and_tiny_inputs(tmp_path):
+    got, want, _ = both(tmp_path, ["tiny"], ["ACGTACGTAC"], ["s"], ["ACGTTTTACG"])
+    assert got == [] and want == []
+    # a query record with no bases and a subject with no bases
+    q, s, m = str(tmp_path / "q.fa"), str(tmp_path / "s.fa"), str(tmp_path / "m.matrix")
+    open(q, "w").write(">empty\n>one\nACGTACGTAGCTAGCTAGCTAGCATCGATCGATCGATCGTAGCTAGCTAGCTAGCTAGTCGATCGATGCTAGCTAGCTAGC\n")
+    open(s, "w").write(">nothing\n>same\nACGTACGTAGCTAGCTAGCTAGCATCGATCGATCGATCGTAGCTAGCTAGCTAGCTAGTCGATCGATGCTAGCTAGCTAGC\n")
+    util.write_matrix("20p43g.matrix", m)
+    want, _ = util.run_oracle(q, s, m, minscore=100)
+    got, _ = engine.search_files(q, s, m, minscore=100)
+    assert len(want) == 1
+    assert_same_hits(got, want)
+
+
+def test_python_mirror_of_engine_interface(tmp_path):
+    """The SearchEngineI-style call sequence RepeatMasker::search makes (RepeatMasker:2022-2066)."""
+    snames, sseqs = synth.make_library(5, n_families=10, lo=100, hi=600)
+    genome, _ = synth.make_genome(6, 5000, sseqs, coverage=0.5)
+    q, s, m = str(tmp_path / "q.fa"), str(tmp_path / "s.fa"), str(tmp_path / "m.matrix")
+    synth.write_fasta(q, ["g"], [genome])
+    synth.write_fasta(s, snames, sseqs)
+    util.write_matrix("20p43g.matrix", m)
+    e = engine.GpuSearchEngine()
+    e.setQuery(q); e.setSubject(s); e.setMatrix(m); e.setWordRaw(0)
+    e.setScoreMode(engine.GpuSearchEngine.complexityAdjustedScoreMode); e.setGenerateAlignments(1)
+    e.setGapInit(-30); e.setInsGapExt(-6); e.setDelGapExt(-5); e.setMaskLevel(101); e.setMinScore(225)
+    status, hits = e.search(minMatch=9, bandwidth=14)
+    want, _ = util.run_oracle(q, s, m)
+    assert status == 0
+    assert_same_hits(hits, want)
