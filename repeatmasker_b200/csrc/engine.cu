@@ -569,7 +569,7 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
         t.rowOff = rowTot;
         t.opsOff = opsTot;
         dirTot += dirBytes;
-        rowTot += 4 * bw;
+        rowTot += 3 * bw;
         opsTot += n + m;
         tc.push_back(t);
         ids.push_back(todo[at]);
@@ -596,7 +596,7 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
       a.status = d_status.ensure(tc.size());
       EventTimer tm;
       tm.start(stream);
-      traceback_kernel<<<((int)tc.size() + 31) / 32, 32, 0, stream>>>(a);
+      traceback_kernel<<<((int)tc.size() + kTraceWarps - 1) / kTraceWarps, kTraceWarps * 32, 0, stream>>>(a);
       tm.stop(stream);
       CUDA_CHECK(cudaGetLastError());
       std::vector<uint8_t> hops((size_t)opsTot);

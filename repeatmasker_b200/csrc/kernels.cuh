@@ -577,11 +577,20 @@ struct TraceArgs {
   int32_t* status;   // [nCand]
 };
 
-__global__ void traceback_kernel(TraceArgs a) {
+// One warp per candidate.  Band cell (u, k) (k = d - dlo, v = u - dlo - k) depends on (u-1, k-1) [E], (u-1, k) [D]
+// and (u, k+1) [F]; all cells with the same w = 2u - k are independent, so the warp sweeps waves w, lane l owning
+// k = l, l+32, ... of the right parity.  H/E/F live in place in shared memory (global scratch when the band is wider
+// than kTraceSmemBand); entries of parity w hold wave w-2 (the diagonal source), the others wave w-1.
+constexpr int kTraceSmemBand = 384;
+constexpr int kTraceWarps = 4;
+
+__global__ void __launch_bounds__(kTraceWarps * 32) traceback_kernel(TraceArgs a) {
   __shared__ int32_t smat[16 * 16];
+  __shared__ int32_t sband[kTraceWarps][3][kTraceSmemBand];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
   __syncthreads();
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int c = blockIdx.x * kTraceWarps + wib;
   if (c >= a.nCand) return;
   const TraceCand tc = a.cand[c];
   const int NEGI = -(1 << 28);
@@ -591,116 +600,122 @@ __global__ void traceback_kernel(TraceArgs a) {
   const int dlo = min(0, n - m) - tc.W, dhi = max(0, n - m) + tc.W;
   const int bw = dhi - dlo + 1;
   uint8_t* dir = a.dir + tc.dirOff;
-  int32_t* Hp = a.rows + tc.rowOff;
-  int32_t* Hn = Hp + bw;
-  int32_t* Ep = Hn + bw;
-  int32_t* En = Ep + bw;
-  for (int k = 0; k < bw; k++) {
-    Hp[k] = NEGI;
-    Ep[k] = NEGI;
+  int32_t *Hb, *Eb, *Fb;
+  if (bw <= kTraceSmemBand) {
+    Hb = sband[wib][0];
+    Eb = sband[wib][1];
+    Fb = sband[wib][2];
+  } else {
+    Hb = a.rows + tc.rowOff;
+    Eb = Hb + bw;
+    Fb = Eb + bw;
   }
-  Hp[-dlo] = 0;
-  for (int u = 1; u <= n; u++) {
-    const int qi = qc[u - 1];
-    int F = NEGI, hleft = NEGI;
-    for (int k = bw - 1; k >= 0; k--) {
-      const int v = u - (dlo + k);
-      if (v < 1 || v > m) {
-        Hn[k] = NEGI;
-        En[k] = NEGI;
-        if (v < 1) {
-          F = NEGI;
-          hleft = NEGI;
-        }
-        continue;
-      }
+  // row u = 0: only (0,0) (d = 0) is reachable
+  for (int k = lane; k < bw; k += 32) {
+    Hb[k] = (k == -dlo) ? 0 : NEGI;
+    Eb[k] = NEGI;
+    Fb[k] = NEGI;
+  }
+  __syncwarp();
+  // waves: u >= 1, 0 <= k < bw  ->  w = 2u - k in [2 - (bw-1), 2n]
+  for (int w = 3 - bw; w <= 2 * n; w++) {
+    for (int k0 = 0; k0 < bw; k0 += 64) {
+      // lane's k with k == w (mod 2)
+      const int k = k0 + 2 * lane + ((w ^ k0) & 1);
+      const int u2 = w + k;  // = 2u
+      const int u = u2 >> 1;
+      const int v = u - dlo - k;
+      const bool inBand = k < bw && u >= 1 && u <= n;
+      int hnew = NEGI, enew = NEGI, fnew = NEGI;
       uint8_t bits = 0;
-      int e_ext = (k > 0 ? Ep[k - 1] : NEGI) + a.ins_ext;
-      int e_open = (k > 0 ? Hp[k - 1] : NEGI) + a.gap_init;
-      int E;
-      if (e_ext >= e_open) {
-        E = e_ext;
-        bits |= 4;
-      } else
-        E = e_open;
-      int f_ext = F + a.del_ext, f_open = hleft + a.gap_init;
-      if (f_ext >= f_open) {
-        F = f_ext;
-        bits |= 8;
-      } else
-        F = f_open;
-      int hd = Hp[k];
-      int D = hd > NEGI / 2 ? hd + smat[(int)sc[v - 1] * 16 + qi] : NEGI;
-      if (u == 1 && v == 1) {
-        E = NEGI;
-        F = NEGI;
+      if (inBand && v >= 1 && v <= m) {
+        const int e_src_e = k > 0 ? Eb[k - 1] : NEGI, e_src_h = k > 0 ? Hb[k - 1] : NEGI;
+        const int f_src_f = k + 1 < bw ? Fb[k + 1] : NEGI, f_src_h = k + 1 < bw ? Hb[k + 1] : NEGI;
+        const int hd = Hb[k];
+        int e_ext = e_src_e + a.ins_ext, e_open = e_src_h + a.gap_init;
+        if (e_ext >= e_open) {
+          enew = e_ext;
+          bits |= 4;
+        } else
+          enew = e_open;
+        int f_ext = f_src_f + a.del_ext, f_open = f_src_h + a.gap_init;
+        if (f_ext >= f_open) {
+          fnew = f_ext;
+          bits |= 8;
+        } else
+          fnew = f_open;
+        int D = hd > NEGI / 2 ? hd + smat[(int)sc[v - 1] * 16 + (int)qc[u - 1]] : NEGI;
+        if (u == 1 && v == 1) {
+          enew = NEGI;
+          fnew = NEGI;
+        }
+        hnew = enew;
+        uint8_t ch = 1;
+        if (fnew > hnew) {
+          hnew = fnew;
+          ch = 2;
+        }
+        if (D > hnew) {
+          hnew = D;
+          ch = 3;
+        }
+        if (hnew < NEGI / 2) hnew = NEGI;
+        if (enew < NEGI / 2) enew = NEGI;
+        if (fnew < NEGI / 2) fnew = NEGI;
+        dir[(int64_t)u * bw + k] = bits | ch;
       }
-      int h = E;
-      uint8_t ch = 1;
-      if (F > h) {
-        h = F;
-        ch = 2;
+      if (inBand) {
+        Hb[k] = hnew;
+        Eb[k] = enew;
+        Fb[k] = fnew;
       }
-      if (D > h) {
-        h = D;
-        ch = 3;
-      }
-      if (h < NEGI / 2) h = NEGI;
-      if (E < NEGI / 2) E = NEGI;
-      if (F < NEGI / 2) F = NEGI;
-      Hn[k] = h;
-      En[k] = E;
-      hleft = h;
-      dir[(int64_t)u * bw + k] = bits | ch;
     }
-    int32_t* tmp = Hp;
-    Hp = Hn;
-    Hn = tmp;
-    tmp = Ep;
-    Ep = En;
-    En = tmp;
+    __syncwarp();
   }
+  // after the last wave: H(n, k) sits in Hb[k] for every k (each k's last in-range wave is row n)
   const int kend = (n - m) - dlo;
   int len = -1;
-  if (Hp[kend] == tc.raw && (dir[(int64_t)n * bw + kend] & 3) == 3) {
-    uint8_t* ops = a.ops + tc.opsOff;
-    int uu = n, vv = m, state = 0, pos = 0;
-    bool ok = true;
-    while (uu > 0 || vv > 0) {
-      if (uu < 1 || vv < 1) {
-        ok = false;
-        break;
-      }
-      int kk = (uu - vv) - dlo;
-      if (kk < 0 || kk >= bw) {
-        ok = false;
-        break;
-      }
-      uint8_t bch = dir[(int64_t)uu * bw + kk];
-      if (state == 0) {
-        int ch = bch & 3;
-        if (ch == 3) {
-          ops[pos++] = 0;
+  if (lane == 0) {
+    if (Hb[kend] == tc.raw && (dir[(int64_t)n * bw + kend] & 3) == 3) {
+      uint8_t* ops = a.ops + tc.opsOff;
+      int uu = n, vv = m, state = 0, pos = 0;
+      bool ok = true;
+      while (uu > 0 || vv > 0) {
+        if (uu < 1 || vv < 1) {
+          ok = false;
+          break;
+        }
+        int kk = (uu - vv) - dlo;
+        if (kk < 0 || kk >= bw) {
+          ok = false;
+          break;
+        }
+        uint8_t bch = dir[(int64_t)uu * bw + kk];
+        if (state == 0) {
+          int ch = bch & 3;
+          if (ch == 3) {
+            ops[pos++] = 0;
+            uu--;
+            vv--;
+          } else if (ch == 1)
+            state = 1;
+          else
+            state = 2;
+        } else if (state == 1) {
+          ops[pos++] = 1;
+          state = (bch & 4) ? 1 : 0;
           uu--;
+        } else {
+          ops[pos++] = 2;
+          state = (bch & 8) ? 2 : 0;
           vv--;
-        } else if (ch == 1)
-          state = 1;
-        else
-          state = 2;
-      } else if (state == 1) {
-        ops[pos++] = 1;
-        state = (bch & 4) ? 1 : 0;
-        uu--;
-      } else {
-        ops[pos++] = 2;
-        state = (bch & 8) ? 2 : 0;
-        vv--;
+        }
       }
+      if (ok) len = pos;
     }
-    if (ok) len = pos;
+    a.opsLen[c] = len;
+    a.status[c] = len > 0 ? 1 : 0;
   }
-  a.opsLen[c] = len;
-  a.status[c] = len > 0 ? 1 : 0;
 }
 
 }  // namespace rmgpu

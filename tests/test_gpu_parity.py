@@ -160,7 +160,7 @@ def test_empty_and_tiny_inputs(tmp_path):
     util.write_matrix("20p43g.matrix", m)
     want, _ = util.run_oracle(q, s, m, minscore=100)
     got, _ = engine.search_files(q, s, m, minscore=100)
-    assert len(want) == 1
+    assert len(want) >= 1 and all(h['qname'] == 'one' and h['sname'] == 'same' for h in want)
     assert_same_hits(got, want)
 
 
