@@ -418,8 +418,8 @@ static void origin_pass(const unsigned char *q, int Q, const unsigned char *s, i
 /* ------------------------------------------------------------------------------------------ */
 /* Banded global traceback between origin and end cell                                         */
 /*   local coordinates u=1..n (query), v=1..mlen (subject); band = diagonals d=u-v in           */
-/*   [min(0,n-m)-W, max(0,n-m)+W]; W = max(bandwidth,1) * 2^k, first k whose banded score       */
-/*   equals the hit's raw score (or whose band covers the whole rectangle).                    */
+/*   [min(0,n-m)-W, max(0,n-m)+W]; W = (max(bandwidth,1) + max(n,m)/32) * 2^k, first k whose     */
+/*   banded score equals the hit's raw score (or whose band covers the whole rectangle).       */
 /* ------------------------------------------------------------------------------------------ */
 
 static int banded_traceback(const unsigned char *q, int n, const unsigned char *s, int mlen, const ora_matrix *m,
@@ -579,8 +579,8 @@ static int banded_traceback(const unsigned char *q, int n, const unsigned char *
 int ora_global_traceback(const unsigned char *q, int n, const unsigned char *s, int mlen, const ora_matrix *m,
                          const ora_params *p, int want_score, char *qaln, char *saln, const char *qlet,
                          const char *slet) {
-  int W = p->bandwidth > 0 ? p->bandwidth : 1;
   int full = n > mlen ? n : mlen;
+  int W = (p->bandwidth > 0 ? p->bandwidth : 1) + full / 32; /* W0 = max(bandwidth,1) + max(n,m)/32, then doubling */
   for (;;) {
     int sc = NEG;
     int len = banded_traceback(q, n, s, mlen, m, p, W, &sc, qaln, saln, qlet, slet);

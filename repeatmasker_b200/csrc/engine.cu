@@ -539,11 +539,20 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
 void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands,
                                   std::vector<std::vector<uint8_t>>& ops, rmgpu_stats& st) {
   ops.assign(cands.size(), {});
-  std::vector<int> todo(cands.size()), W(cands.size(), std::max(p.bandwidth, 1));
+  // band schedule: W0 = max(bandwidth,1) + max(n,m)/32, doubled until the banded score reproduces the raw score
+  std::vector<int> todo(cands.size()), W(cands.size());
   std::iota(todo.begin(), todo.end(), 0);
+  for (size_t i = 0; i < cands.size(); i++)
+    W[i] = std::max(p.bandwidth, 1) + std::max(cands[i].i1 - cands[i].i0 + 1, cands[i].j1 - cands[i].j0 + 1) / 32;
+  auto band_of = [&](int id) {
+    const Candidate& c = cands[id];
+    return (int64_t)std::abs((c.i1 - c.i0) - (c.j1 - c.j0)) + 2 * (int64_t)W[id] + 1;
+  };
   const int64_t kDirBudget = 4ll << 30;  // direction bytes per launch
   while (!todo.empty()) {
     std::vector<int> next;
+    // narrow bands first (one warp each), then wide bands (one 128-thread block each)
+    std::stable_sort(todo.begin(), todo.end(), [&](int x, int y) { return (band_of(x) > 64) < (band_of(y) > 64); });
     size_t at = 0;
     while (at < todo.size()) {
       std::vector<TraceCand> tc;
@@ -554,7 +563,7 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
         int n = c.i1 - c.i0 + 1, m = c.j1 - c.j0 + 1, w = W[todo[at]];
         int64_t bw = (int64_t)std::abs(n - m) + 2 * (int64_t)w + 1;
         int64_t dirBytes = (int64_t)(n + 1) * bw;
-        if (!tc.empty() && dirTot + dirBytes > kDirBudget) break;
+        if (!tc.empty() && (dirTot + dirBytes > kDirBudget || (band_of(ids[0]) > 64) != (bw > 64))) break;
         TraceCand t;
         t.q = c.q;
         t.strand = c.strand;
@@ -596,7 +605,10 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
       a.status = d_status.ensure(tc.size());
       EventTimer tm;
       tm.start(stream);
-      traceback_kernel<<<((int)tc.size() + kTraceWarps - 1) / kTraceWarps, kTraceWarps * 32, 0, stream>>>(a);
+      if (band_of(ids[0]) > 64)
+        traceback_kernel<true><<<(int)tc.size(), kTraceWarps * 32, 0, stream>>>(a);
+      else
+        traceback_kernel<false><<<((int)tc.size() + kTraceWarps - 1) / kTraceWarps, kTraceWarps * 32, 0, stream>>>(a);
       tm.stop(stream);
       CUDA_CHECK(cudaGetLastError());
       std::vector<uint8_t> hops((size_t)opsTot);

@@ -577,21 +577,33 @@ struct TraceArgs {
   int32_t* status;   // [nCand]
 };
 
-// One warp per candidate.  Band cell (u, k) (k = d - dlo, v = u - dlo - k) depends on (u-1, k-1) [E], (u-1, k) [D]
-// and (u, k+1) [F]; all cells with the same w = 2u - k are independent, so the warp sweeps waves w, lane l owning
-// k = l, l+32, ... of the right parity.  H/E/F live in place in shared memory (global scratch when the band is wider
-// than kTraceSmemBand); entries of parity w hold wave w-2 (the diagonal source), the others wave w-1.
-constexpr int kTraceSmemBand = 384;
+// Band cell (u, k) (k = d - dlo, v = u - dlo - k) depends on (u-1, k-1) [E], (u-1, k) [D] and (u, k+1) [F]; all
+// cells with the same w = 2u - k are independent, so a team of T threads (one warp for narrow bands, a 128-thread
+// block for wide ones) sweeps waves w, thread l owning k = 2l (+parity), 2l + 2T, ...  H/E/F live in place in
+// shared memory (global scratch when the band is wider than the shared buffer); entries of parity w hold wave w-2
+// (the diagonal source), the others wave w-1.
+constexpr int kTraceWarpBand = 256;    // ints per array per warp in warp mode
 constexpr int kTraceWarps = 4;
+constexpr int kTraceBlockBand = 3072;  // ints per array in block mode
 
+template <bool BLOCK>
 __global__ void __launch_bounds__(kTraceWarps * 32) traceback_kernel(TraceArgs a) {
+  constexpr int T = BLOCK ? kTraceWarps * 32 : 32;
+  constexpr int SB = BLOCK ? kTraceBlockBand : kTraceWarpBand;
   __shared__ int32_t smat[16 * 16];
-  __shared__ int32_t sband[kTraceWarps][3][kTraceSmemBand];
+  __shared__ int32_t sband[BLOCK ? 1 : kTraceWarps][3][SB];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
   __syncthreads();
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int c = blockIdx.x * kTraceWarps + wib;
+  const int tid = BLOCK ? threadIdx.x : (threadIdx.x & 31);
+  const int wib = BLOCK ? 0 : (threadIdx.x >> 5);
+  const int c = BLOCK ? blockIdx.x : blockIdx.x * kTraceWarps + wib;
   if (c >= a.nCand) return;
+  auto team_sync = [&]() {
+    if (BLOCK)
+      __syncthreads();
+    else
+      __syncwarp();
+  };
   const TraceCand tc = a.cand[c];
   const int NEGI = -(1 << 28);
   const int n = tc.i1 - tc.i0 + 1, m = tc.j1 - tc.j0 + 1;
@@ -601,7 +613,7 @@ __global__ void __launch_bounds__(kTraceWarps * 32) traceback_kernel(TraceArgs a
   const int bw = dhi - dlo + 1;
   uint8_t* dir = a.dir + tc.dirOff;
   int32_t *Hb, *Eb, *Fb;
-  if (bw <= kTraceSmemBand) {
+  if (bw <= SB) {
     Hb = sband[wib][0];
     Eb = sband[wib][1];
     Fb = sband[wib][2];
@@ -611,19 +623,19 @@ __global__ void __launch_bounds__(kTraceWarps * 32) traceback_kernel(TraceArgs a
     Fb = Eb + bw;
   }
   // row u = 0: only (0,0) (d = 0) is reachable
-  for (int k = lane; k < bw; k += 32) {
+  for (int k = tid; k < bw; k += T) {
     Hb[k] = (k == -dlo) ? 0 : NEGI;
     Eb[k] = NEGI;
     Fb[k] = NEGI;
   }
-  __syncwarp();
-  // waves: u >= 1, 0 <= k < bw  ->  w = 2u - k in [2 - (bw-1), 2n]
+  team_sync();
+  // waves: u >= 1, 0 <= k < bw  ->  w = 2u - k in [3 - bw, 2n]
   for (int w = 3 - bw; w <= 2 * n; w++) {
-    for (int k0 = 0; k0 < bw; k0 += 64) {
-      // lane's k with k == w (mod 2)
-      const int k = k0 + 2 * lane + ((w ^ k0) & 1);
-      const int u2 = w + k;  // = 2u
-      const int u = u2 >> 1;
+    // only k with 1 <= (w + k) / 2 <= n matter: k in [2 - w, 2n - w]
+    const int klo = max(0, 2 - w), khi = min(bw - 1, 2 * n - w);
+    for (int k0 = klo & ~1; k0 <= khi; k0 += 2 * T) {
+      const int k = k0 + 2 * tid + (w & 1);
+      const int u = (w + k) >> 1;
       const int v = u - dlo - k;
       const bool inBand = k < bw && u >= 1 && u <= n;
       int hnew = NEGI, enew = NEGI, fnew = NEGI;
@@ -670,12 +682,12 @@ __global__ void __launch_bounds__(kTraceWarps * 32) traceback_kernel(TraceArgs a
         Fb[k] = fnew;
       }
     }
-    __syncwarp();
+    team_sync();
   }
-  // after the last wave: H(n, k) sits in Hb[k] for every k (each k's last in-range wave is row n)
+  // after the last wave H(n, k) sits in Hb[k] for every k (each k's last in-range wave is row n)
   const int kend = (n - m) - dlo;
   int len = -1;
-  if (lane == 0) {
+  if (tid == 0) {
     if (Hb[kend] == tc.raw && (dir[(int64_t)n * bw + kend] & 3) == 3) {
       uint8_t* ops = a.ops + tc.opsOff;
       int uu = n, vv = m, state = 0, pos = 0;
