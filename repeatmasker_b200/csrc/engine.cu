@@ -101,7 +101,7 @@ struct rmgpu_session {
   int device = 0;
   int numSMs = 0;
   cudaStream_t stream = nullptr;
-  static constexpr int R = 8;  // subject rows per lane in K1
+  static constexpr int R = 16;  // subject rows per lane in K1
 
   ScoreMatrix matrix;
   bool haveMatrix = false;
@@ -113,7 +113,8 @@ struct rmgpu_session {
   std::vector<int32_t> h_gsubject;
   DevBuf<uint8_t> d_rowcode, d_gflags, d_sflags, d_scodes;
   DevBuf<uint2> d_prof;
-  DevBuf<int32_t> d_gsubject, d_slen;
+  DevBuf<int32_t> d_gsubject, d_slen, d_order, d_prodPos, d_consPos;
+  int orderGroup = 0;  // max ticket distance between a stripe and the stripe below it
   DevBuf<int64_t> d_soff;
   std::vector<int64_t> h_soff;
   bool profileValid = false;
@@ -136,7 +137,12 @@ struct rmgpu_session {
 
   // ---- scratch
   DevBuf<int32_t> d_pairbest;
-  DevBuf<uint2> d_bnd1;
+  DevBuf<unsigned long long> d_bnd1, d_hotmask;
+  DevBuf<int32_t> d_hotShift;
+  DevBuf<unsigned long long> d_dbg;
+  DevBuf<int> d_abort;
+  void check_abort(const char* what);
+  std::vector<int32_t> h_hotShift;
   DevBuf<OriginBoundary> d_bnd2;
   DevBuf<int> d_progress, d_finished, d_ticket, d_overflow;
   DevBuf<unsigned long long> d_keys, d_vals;
@@ -149,7 +155,8 @@ struct rmgpu_session {
   void set_library(SeqSet s);
   void set_queries(SeqSet s);
   void build_classes_and_profile();
-  void run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest, double& ms, int& launches);
+  void run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest, std::vector<unsigned long long>& hotmask,
+                 double& ms, int& launches);
   void run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest, std::vector<Candidate>& cands,
                   rmgpu_stats& st);
   void run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands, std::vector<std::vector<uint8_t>>& ops,
@@ -226,6 +233,53 @@ void rmgpu_session::set_library(SeqSet s) {
       sflags[k - 1] |= 2;
     }
   }
+  // Ticket order of the stripes (same for every query).  Chains (a subject spanning several stripes) are dealt
+  // round-robin into groups of about kGroupStripes stripes; inside a group the tickets go level by level (all first
+  // stripes, then all second stripes, ...), longest chains first.  A consumer stripe is therefore claimed well
+  // after its producer started (no polling in steady state) while the producer->consumer ticket distance stays
+  // bounded by the group size, which bounds the boundary ring.
+  {
+    struct Chain {
+      int first, len;
+    };
+    std::vector<Chain> chains;
+    for (int k = 0; k < nStripes; k++) {
+      if (sflags[k] & 1)
+        chains.back().len++;
+      else
+        chains.push_back({k, 1});
+    }
+    std::stable_sort(chains.begin(), chains.end(), [](const Chain& a, const Chain& b) { return a.len > b.len; });
+    const int kGroupStripes = 2 * numSMs * 24 + 64;
+    const int nGroupsT = std::max(1, (nStripes + kGroupStripes - 1) / kGroupStripes);
+    std::vector<std::vector<Chain>> grp(nGroupsT);
+    for (size_t c = 0; c < chains.size(); c++) grp[c % nGroupsT].push_back(chains[c]);
+    std::vector<int32_t> order, posOf(nStripes, -1);
+    orderGroup = 0;
+    for (auto& gchains : grp) {
+      int tot = 0, maxLen = 0;
+      for (auto& c : gchains) {
+        tot += c.len;
+        maxLen = std::max(maxLen, c.len);
+      }
+      orderGroup = std::max(orderGroup, tot);
+      for (int level = 0; level < maxLen; level++)
+        for (auto& c : gchains)
+          if (level < c.len) {
+            posOf[c.first + level] = (int32_t)order.size();
+            order.push_back(c.first + level);
+          }
+    }
+    std::vector<int32_t> prodPos(nStripes, -1), consPos(nStripes, -1);
+    for (int pos = 0; pos < nStripes; pos++) {
+      int k = order[pos];
+      if (sflags[k] & 1) prodPos[pos] = posOf[k - 1];
+      if (sflags[k] & 2) consPos[pos] = posOf[k + 1];
+    }
+    d_order.upload(order, stream);
+    d_prodPos.upload(prodPos, stream);
+    d_consPos.upload(consPos, stream);
+  }
   // unpacked subject codes for K2 / K3
   h_soff.assign(n + 1, 0);
   std::vector<int32_t> slen(n);
@@ -257,6 +311,7 @@ void rmgpu_session::set_queries(SeqSet s) {
   h_selOff.assign(n + 1, 0);
   h_qlen.resize(n);
   h_selLen.resize(n);
+  h_hotShift.clear();
   maxQ = 0;
   for (int i = 0; i < n; i++) {
     int64_t Q = (int64_t)queries.seqs[i].size();
@@ -266,6 +321,9 @@ void rmgpu_session::set_queries(SeqSet s) {
     h_qoff[i + 1] = h_qoff[i] + ((Q + 1) & ~1ll);  // even nibble offsets
     h_selOff[i + 1] = h_selOff[i] + h_selLen[i];
     maxQ = std::max<int>(maxQ, (int)Q);
+    int sh = 0;
+    while ((((Q + 31) >> 5) + 1) >> sh > 63) sh++;  // at most 64 column blocks per query for the hot mask
+    h_hotShift.push_back(sh);
   }
   selTotal = h_selOff[n];
   std::vector<uint8_t> packed((size_t)(h_qoff[n] / 2 + 1), 0);
@@ -318,6 +376,7 @@ void rmgpu_session::set_queries(SeqSet s) {
   d_qlen.upload(h_qlen, stream);
   d_selOff.upload(h_selOff, stream);
   d_selLen.upload(h_selLen, stream);
+  d_hotShift.upload(h_hotShift, stream);
   d_sel.ensure((size_t)std::max<int64_t>(selTotal, 1));
   d_codes_fwd.ensure((size_t)std::max<int64_t>(h_qoff[n], 1));
   d_codes_rc.ensure((size_t)std::max<int64_t>(h_qoff[n], 1));
@@ -358,58 +417,92 @@ void rmgpu_session::build_classes_and_profile() {
 
 static uint32_t pack2(int v) { return ((uint32_t)(uint16_t)(int16_t)v) | ((uint32_t)(uint16_t)(int16_t)v << 16); }
 
+void rmgpu_session::check_abort(const char* what) {
+  int f = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&f, d_abort.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (f) throw Error(std::string(what) + ": stripe pipeline watchdog fired (a producer/consumer wait exceeded its bound)");
+}
+
 // K1 over the resident batch x library.
-void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest, double& ms, int& launches) {
+void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest,
+                              std::vector<unsigned long long>& hotmask, double& ms, int& launches) {
   const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
   pairbest.assign((size_t)nQ * nS * 2, 0);
+  hotmask.assign((size_t)nQ * nS * 2, 0);
   ms = 0;
   if (nQ == 0 || nS == 0) return;
   if (p.gap_init >= 0 || p.ins_gap_ext > 0 || p.del_gap_ext > 0 || p.gap_init < -20000)
     throw Error("gap penalties must be negative");
   build_classes_and_profile();
   int blocksPerSM = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R>, 256, 0));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R>, kScoreWarps * 32, 0));
   if (blocksPerSM < 1) throw Error("K1 does not fit on an SM");
   const int64_t nTickets = (int64_t)nQ * nStripes;
   if (nTickets >= (1ll << 31)) throw Error("too many stripe tasks in one batch");
-  int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, (nTickets + 7) / 8);
-  const int warps = grid * 8;
-  const int nslot = (int)std::min<int64_t>(nTickets, 2 * (int64_t)warps + 2);
+  int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, (nTickets + kScoreWarps - 1) / kScoreWarps);
+  const int warps = grid * kScoreWarps;
+  // ring slots: a slot is rewritten nslot tickets later; its reader is at most orderGroup tickets after its writer
+  const int nslot = (int)std::min<int64_t>(nTickets, std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)orderGroup + 2));
   const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
   ScoreArgs a;
   a.prof = d_prof.p;
   a.gflags = d_gflags.p;
   a.gsubject = d_gsubject.p;
   a.sflags = d_sflags.p;
+  a.order = d_order.p;
+  a.prodPos = d_prodPos.p;
+  a.consPos = d_consPos.p;
   a.sel = d_sel.p;
   a.selOff = d_selOff.p;
   a.qlen = d_qlen.p;
+  a.hotShift = d_hotShift.p;
   a.nQueries = nQ;
   a.nStripes = nStripes;
   a.nSubjects = nS;
   a.pairbest = d_pairbest.ensure(pairbest.size());
+  a.hotmask = d_hotmask.ensure(hotmask.size());
   a.bnd = d_bnd1.ensure((size_t)nslot * bndStride);
   a.bndStride = bndStride;
   a.nslot = nslot;
-  a.progress = d_progress.ensure((size_t)nTickets);
   a.finished = d_finished.ensure((size_t)nTickets);
   a.ticket = d_ticket.ensure(1);
   a.gi2 = pack2(p.gap_init);
   a.ie2 = pack2(p.ins_gap_ext);
-  a.de2 = pack2(p.del_gap_ext);
+  a.df2 = pack2(std::max(p.del_gap_ext, p.gap_init));
+  a.minscore = std::min(p.minscore, 32000);
+  a.abort_flag = d_abort.ensure(1);
+  a.dbgMode = getenv("RMGPU_K1_MODE") ? atoi(getenv("RMGPU_K1_MODE")) : 0;
+  CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream));
+  static const bool dbgOn = getenv("RMGPU_DEBUG_K1") != nullptr;
+  a.dbg = nullptr;
+  if (dbgOn) {
+    a.dbg = d_dbg.ensure(4);
+    CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 32, stream));
+  }
   CUDA_CHECK(cudaMemsetAsync(a.pairbest, 0, pairbest.size() * sizeof(int32_t), stream));
-  CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream));
+  CUDA_CHECK(cudaMemsetAsync(a.hotmask, 0, hotmask.size() * sizeof(unsigned long long), stream));
   CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream));
   CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), stream));
   EventTimer tm;
   tm.start(stream);
-  swg_score_kernel<R><<<grid, 256, 0, stream>>>(a);
+  // tag 0 = "never written": the boundary ring must not hold tags of an earlier launch
+  CUDA_CHECK(cudaMemsetAsync(a.bnd, 0, (size_t)nslot * bndStride * sizeof(unsigned long long), stream));
+  swg_score_kernel<R><<<grid, kScoreWarps * 32, 0, stream>>>(a);
   tm.stop(stream);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpyAsync(pairbest.data(), a.pairbest, pairbest.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  CUDA_CHECK(cudaMemcpyAsync(hotmask.data(), a.hotmask, hotmask.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
   CUDA_CHECK(cudaStreamSynchronize(stream));
+  check_abort("K1");
   ms = tm.ms();
-  launches += 1;
+  launches += 2;
+  if (dbgOn) {
+    unsigned long long d[4];
+    CUDA_CHECK(cudaMemcpy(d, a.dbg, 32, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[K1 dbg] tasks %llu  producer-wait %.1f%% of task cycles  slot-wait %.2e cyc  mean task %.0f cyc  grid %d nslot %d\n", d[2],
+            100.0 * (double)d[0] / (double)std::max(d[3], 1ull), (double)d[1], (double)d[3] / (double)std::max(d[2], 1ull), grid, nslot);
+  }
 }
 
 // K2 over every (query, strand, subject) whose K1 best reached minscore.
@@ -421,7 +514,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   for (int q = 0; q < nQ; q++)
     for (int s = 0; s < nS; s++)
       for (int strand = 0; strand < 2; strand++)
-        if (pairbest[((size_t)q * nS + s) * 2 + strand] >= p.minscore) {
+        if (pairbest[((size_t)q * nS + s) * 2 + strand] >= std::min(p.minscore, 32000)) {
           int64_t Q = h_qlen[q], L = (int64_t)lib.seqs[s].size();
           if ((Q + 1) * (L + 1) >= (1ll << 32))
             throw Error("query x subject too large for one origin pass (" + queries.names[q] + " x " + lib.names[s] +
@@ -479,6 +572,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     a.vals = d_vals.ensure(tableSize);
     a.tableMask = (uint32_t)tableSize - 1;
     a.overflow = d_overflow.ensure(1);
+    a.abort_flag = d_abort.ensure(1);
+    CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream));
     CUDA_CHECK(cudaMemsetAsync(a.keys, 0xFF, tableSize * 8, stream));
     CUDA_CHECK(cudaMemsetAsync(a.vals, 0, tableSize * 8, stream));
     CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream));
@@ -496,6 +591,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     CUDA_CHECK(cudaMemcpyAsync(keys.data(), a.keys, tableSize * 8, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaMemcpyAsync(vals.data(), a.vals, tableSize * 8, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
+    check_abort("K2");
     st.ms_origin += tm.ms();
     st.launches += 1;
     st.d2h_bytes += (int64_t)tableSize * 16;
@@ -699,9 +795,10 @@ rmgpu_result* rmgpu_session::search(const rmgpu_params& p) {
     for (int s = 0; s < nS; s++) st.cells += 2.0 * (double)queries.seqs[q].size() * (double)lib.seqs[s].size();
 
   std::vector<int32_t> pairbest;
-  run_score(p, pairbest, st.ms_score, st.launches);
+  std::vector<unsigned long long> hotmask;
+  run_score(p, pairbest, hotmask, st.ms_score, st.launches);
   st.score_launches = 1;
-  st.d2h_bytes += (int64_t)pairbest.size() * 4;
+  st.d2h_bytes += (int64_t)pairbest.size() * 12;
   std::vector<Candidate> cands;
   run_origin(p, pairbest, cands, st);
   std::vector<std::vector<uint8_t>> ops;
@@ -986,9 +1083,10 @@ int rmgpu_session_score_only(rmgpu_session* s, const rmgpu_params* p, int32_t* b
     CUDA_CHECK(cudaSetDevice(s->device));
     if (!s->haveMatrix || !s->haveLib || !s->haveQueries) throw Error("matrix, library and queries must be set");
     std::vector<int32_t> pb;
+    std::vector<unsigned long long> hm;
     double t = 0;
     int launches = 0;
-    s->run_score(*p, pb, t, launches);
+    s->run_score(*p, pb, hm, t, launches);
     if (best) memcpy(best, pb.data(), pb.size() * sizeof(int32_t));
     if (ms) *ms = t;
   });

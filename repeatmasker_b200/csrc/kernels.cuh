@@ -11,12 +11,14 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace rmgpu {
 
 constexpr int kPadClass = 7;            // residue class whose score is very negative: columns outside the query
 constexpr uint32_t kPadSel = 0xF7F7u;   // PRMT selector picking class 7 for both strands (sign-replicated)
 constexpr int kWarp = 32;
+constexpr int kLag = 4;                 // blocks of slack a consumer stripe rebuilds whenever it catches its producer
 
 // ---------------------------------------------------------------------------------------------------------------
 // Inter-warp systolic pipeline through global memory.
@@ -40,12 +42,21 @@ __device__ __forceinline__ uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t sel)
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
   return d;
 }
-__device__ __forceinline__ void wait_ge(const int* p, int want) {
+// Every wait in the stripe pipeline is bounded: a wait longer than ~4 s of SM clock can only be a protocol bug, so
+// it raises *abort_flag (the host turns that into an error) instead of hanging the GPU.
+constexpr long long kWatchdogCycles = 8000000000ll;
+__device__ __forceinline__ bool wait_ge(const int* p, int want, int* abort_flag) {
   unsigned ns = 32;
+  const long long t0 = clock64();
   while (ld_acquire(p) < want) {
     __nanosleep(ns);
     if (ns < 1024) ns <<= 1;
+    if (clock64() - t0 > kWatchdogCycles || ld_acquire(abort_flag) != 0) {
+      if (atomicExch(abort_flag, 1) == 0) printf("[watchdog] wait_ge(%p) want %d have %d\n", (const void*)p, want, ld_acquire(p));
+      return false;
+    }
   }
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -117,9 +128,12 @@ __global__ void build_profile_kernel(ProfileArgs a) {
 // K1: score pass.  Each lane owns R consecutive subject rows (a "group"); the two 16-bit halves of every register
 // are the forward and the reverse-complement strand of the same query (identical dimensions, so they pair
 // perfectly).  With E' = E - gap_init and F' = F - gap_init every state value is >= 0:
-//     E'[i][j] = max(E'[i-1][j] + ins_ext, H[i-1][j])                  VIADDMNMX.S16x2
-//     F'[i][j] = max(F'[i][j-1] + del_ext, H[i][j-1])                  VIADDMNMX.S16x2
-//     H[i][j]  = max(0, H[i-1][j-1] + s, max(E',F') + gap_init)        PRMT, VIADD.16x2, VIMNMX.S16x2, VIADDMNMX.S16x2.RELU
+//     E'[i][j]  = max(E'[i-1][j] + ins_ext, H[i-1][j])                 VIADDMNMX.S16x2
+//     T[i][j]   = max(0, H[i-1][j-1] + s, E'[i][j] + gap_init)         PRMT, VIADD.16x2, VIADDMNMX.S16x2.RELU
+//     H[i][j]   = max(T[i][j], F'[i][j] + gap_init)                    VIADDMNMX.S16x2
+//     F'[i][j+1]= max(F'[i][j] + max(del_ext, gap_init), T[i][j])      VIADDMNMX.S16x2
+// (the last line is F'[j+1] = max(F'[j]+del_ext, H[j]) with H expanded; it makes the F' recurrence the ONLY serial
+// dependency down a column -- one instruction per row -- so a single warp keeps the DPX pipe busy)
 // Lane t works on column (step - t): an anti-diagonal wavefront; the last row's (H, F') and the column's selector
 // move one lane down per step by warp shuffle.  int16 overflow: a pair whose best reaches 32000 is re-done by K2 in
 // int32 like every pair with best >= minscore, so wrapped values never reach a result.
@@ -129,30 +143,62 @@ struct ScoreArgs {
   const uint8_t* gflags;      // [nGroups] bit0: group starts a subject
   const int32_t* gsubject;    // [nGroups] subject id or -1 (unused lanes)
   const uint8_t* sflags;      // [nStripes] bit0 has_prev, bit1 has_next
+  const int32_t* order;       // [nStripes] ticket position -> stripe (level order inside groups, see engine.cu)
+  const int32_t* prodPos;     // [nStripes] position of the stripe above (producer), -1 if none
+  const int32_t* consPos;     // [nStripes] position of the stripe below (consumer), -1 if none
   const uint16_t* sel;
   const int64_t* selOff;
   const int32_t* qlen;
+  const int32_t* hotShift;    // [nQueries] 32-column blocks per hot-mask bit (power of two exponent)
   int nQueries, nStripes, nSubjects;
   int32_t* pairbest;          // [nQueries * nSubjects * 2] raw best per strand (atomicMax)
-  uint2* bnd;                 // [nslot * bndStride] (H, F') of the stripe's last row per column
+  unsigned long long* hotmask;  // [nQueries * nSubjects * 2] bit c: some cell of column block c reached minscore
+  unsigned long long* bnd;    // [nslot * bndStride] tagged (H, F') of the stripe's last row per column
   int64_t bndStride;
   int nslot;
-  int* progress;              // [nTickets] completed 32-column blocks of the boundary
   int* finished;              // [nTickets]
   int* ticket;                // global ticket counter
-  uint32_t gi2, ie2, de2;     // penalties replicated in both halves
+  uint32_t gi2, ie2, df2;     // gap_init, ins_gap_ext, max(del_gap_ext, gap_init), replicated in both halves
+  int minscore;
+  int* abort_flag;            // set by the watchdog
+  int dbgMode;                // bit0: no hysteresis, bit1: no prefetch (debug)
+  unsigned long long* dbg;    // optional [4]: cycles waiting on the producer, cycles waiting on a slot, tasks, task cycles
 };
 
+// Boundary elements are single 64-bit words {H | F' << 32}; every 16-bit half is < 32768, so bit 15 of each half is
+// free and carries a 4-bit generation tag: a consumer simply re-reads an element until the tag is the one its
+// producer writes (64-bit scalar accesses are single-copy atomic), so no fence, flag or progress counter is needed.
+// The ring is cleared (tag 0 = never valid) before every launch.
+constexpr unsigned long long kTagMask = 0x8000800080008000ull;
+__device__ __forceinline__ unsigned long long tag_bits(int ticket, int nslot) {
+  const unsigned tag = (unsigned)((ticket / nslot) % 15) + 1u;
+  return ((unsigned long long)(tag & 1u) << 15) | ((unsigned long long)((tag >> 1) & 1u) << 31) |
+         ((unsigned long long)((tag >> 2) & 1u) << 47) | ((unsigned long long)((tag >> 3) & 1u) << 63);
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr int kScoreWarps = 8;
+
 template <int R>
-__global__ void __launch_bounds__(256) swg_score_kernel(ScoreArgs a) {
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArgs a) {
+  __shared__ uint4 s_feed[kScoreWarps][32];  // (selector, H above, F' above) for the 32 columns of the current block
+  __shared__ uint2 s_out[kScoreWarps][32];   // last row's (H, F') of the last 32 columns lane 31 finished
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nTickets = a.nQueries * a.nStripes;
   for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(a.ticket, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= nTickets) break;
-    const int q = t / a.nStripes, k = t - q * a.nStripes;
+    const int q = t / a.nStripes, pos = t - q * a.nStripes;
+    const int k = a.order[pos];
     const int g = k * 32 + lane;
     const int Q = a.qlen[q];
     const uint8_t sf = a.sflags[k];
@@ -170,78 +216,138 @@ __global__ void __launch_bounds__(256) swg_score_kernel(ScoreArgs a) {
     }
     const int qBlocks = (Q + 31) >> 5;
     const int nBlocks = qBlocks + 1;  // lane 31 reaches column qBlocks*32 >= Q
-    const uint2* bndIn = a.bnd + (int64_t)((t - 1 + a.nslot) % a.nslot) * a.bndStride;
-    uint2* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
-    if (hasNext && t >= a.nslot) {  // the slot's previous reader must be done
-      if (lane == 0) wait_ge(&a.finished[t - a.nslot + 1], 1);
-      __syncwarp();
+    const int tProd = hasPrev ? q * a.nStripes + a.prodPos[pos] : 0;  // ticket of the stripe above (always older)
+    const unsigned long long* bndIn = a.bnd + (int64_t)(tProd % a.nslot) * a.bndStride;
+    unsigned long long* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
+    const unsigned long long tagIn = tag_bits(tProd, a.nslot), tagOut = tag_bits(t, a.nslot);
+    if (hasNext) {
+      // The slot still holds the boundary of the last ticket that WROTE it (t - nslot, t - 2 nslot, ... skipping
+      // tickets whose stripe has no stripe below): its reader must be done before this ticket overwrites it.
+      for (int tOld = t - a.nslot; tOld >= 0; tOld -= a.nslot) {
+        const int qOld = tOld / a.nStripes;
+        const int cOld = a.consPos[tOld - qOld * a.nStripes];
+        if (cOld < 0) continue;
+        const long long w0 = clock64();
+        if (lane == 0) wait_ge(&a.finished[qOld * a.nStripes + cOld], 1, a.abort_flag);
+        __syncwarp();
+        if (a.dbg && lane == 0) atomicAdd(&a.dbg[1], (unsigned long long)(clock64() - w0));
+        break;
+      }
     }
-    uint32_t best = 0, outH = 0, outF = 0, diag = 0, curSel = kPadSel;
-    uint32_t wbH = 0, wbF = 0;
+    const long long task0 = clock64();
+    long long waitCyc = 0;
+    const int hotShift = a.hotShift[q];
+    const int sj = a.gsubject[g];
+    uint32_t best = 0, bestBlk = 0, outH = 0, outF = 0, diag = 0, curSel = kPadSel;
+    unsigned long long nextRaw = 0;
+    if (hasPrev) nextRaw = ld_relaxed_u64(&bndIn[lane]);
     for (int b = 0; b < nBlocks; b++) {
       uint32_t selv = sel[b * 32 + lane];
-      uint2 bv = make_uint2(0u, 0u);
+      unsigned long long raw = 0;
       if (hasPrev && b < qBlocks) {
-        if (lane == 0) wait_ge(&a.progress[t - 1], b + 1);
-        __syncwarp();
-        bv = __ldcg(&bndIn[b * 32 + lane]);
+        raw = nextRaw;
+        if (!__all_sync(0xffffffffu, (raw & kTagMask) == tagIn)) {
+          // the prefetch was too early: look again before deciding that the producer really is not ahead
+          raw = ld_relaxed_u64(&bndIn[b * 32 + lane]);
+          if (!__all_sync(0xffffffffu, (raw & kTagMask) == tagIn)) {
+            const long long w0 = clock64();
+            // caught up with the producer: sleep until it is kLag blocks ahead (hysteresis), then take block b
+            const int far = (a.dbgMode & 1) ? b : min(b + kLag, qBlocks - 1);
+            unsigned ns = 128;
+            bool dead = false;
+            for (;;) {
+              unsigned long long probe = ld_relaxed_u64(&bndIn[far * 32 + lane]);
+              if (__all_sync(0xffffffffu, (probe & kTagMask) == tagIn)) break;
+              __nanosleep(ns);
+              if (ns < 1024) ns <<= 1;
+              if (clock64() - w0 > kWatchdogCycles || ld_acquire(a.abort_flag) != 0) {
+                dead = true;
+                break;
+              }
+            }
+            dead = __any_sync(0xffffffffu, dead);
+            while (!dead) {
+              raw = ld_relaxed_u64(&bndIn[b * 32 + lane]);
+              if (__all_sync(0xffffffffu, (raw & kTagMask) == tagIn)) break;
+              dead = __any_sync(0xffffffffu, clock64() - w0 > kWatchdogCycles);
+            }
+            if (dead && lane == 0) {
+              if (atomicExch(a.abort_flag, 1) == 0)
+                printf("[K1 watchdog] ticket %d (q %d pos %d stripe %d) block %d/%d waits on producer ticket %d slot %d tagIn %llx raw %llx far %d\n", t, q, pos, k, b, qBlocks, tProd, tProd % a.nslot, tagIn, raw & kTagMask, far);
+            }
+            waitCyc += clock64() - w0;
+          }
+        }
+        raw &= ~kTagMask;
+        if (b + 1 < qBlocks && !(a.dbgMode & 2)) nextRaw = ld_relaxed_u64(&bndIn[(b + 1) * 32 + lane]);  // prefetch, validated next block
       }
-#pragma unroll 4
+      __syncwarp();  // everyone is done reading the previous block's feed
+      s_feed[wib][lane] = make_uint4(selv, (uint32_t)raw, (uint32_t)(raw >> 32), 0u);
+      __syncwarp();
+#pragma unroll 2
       for (int j = 0; j < 32; j++) {
         uint32_t inSel = __shfl_up_sync(0xffffffffu, curSel, 1);
         uint32_t inH = __shfl_up_sync(0xffffffffu, outH, 1);
         uint32_t inF = __shfl_up_sync(0xffffffffu, outF, 1);
-        uint32_t fs = __shfl_sync(0xffffffffu, selv, j);
-        uint32_t fh = __shfl_sync(0xffffffffu, bv.x, j);
-        uint32_t ff = __shfl_sync(0xffffffffu, bv.y, j);
+        const uint4 fd = s_feed[wib][j];  // broadcast read
         if (lane == 0) {
-          inSel = fs;
-          inH = fh;
-          inF = ff;
+          inSel = fd.x;
+          inH = fd.y;
+          inF = fd.z;
         }
         if (startFlag) {
           inH = 0;
           inF = 0;
         }
         curSel = inSel;
-        uint32_t hd = diag, hu = inH, f = inF;
+        uint32_t hd = diag, f = inF, h = 0;
         diag = inH;
 #pragma unroll
         for (int r = 0; r < R; r++) {
-          uint32_t s = prmt(Plo[r], Phi[r], curSel);
-          uint32_t hl = H[r];
-          E[r] = __viaddmax_s16x2(E[r], a.ie2, hl);
-          f = __viaddmax_s16x2(f, a.de2, hu);
-          uint32_t m = __vmaxs2(E[r], f);
-          uint32_t d = __vadd2(hd, s);
-          uint32_t h = __viaddmax_s16x2_relu(m, a.gi2, d);
+          const uint32_t s = prmt(Plo[r], Phi[r], curSel);
+          const uint32_t hl = H[r];
+          E[r] = __viaddmax_s16x2(E[r], a.ie2, hl);                  // E'[i][j]
+          const uint32_t d = __vadd2(hd, s);                         // H[i-1][j-1] + s
+          const uint32_t tt = __viaddmax_s16x2_relu(E[r], a.gi2, d);  // T = max(0, diag, E'+gi): H without F
+          h = __viaddmax_s16x2(f, a.gi2, tt);                        // H = max(T, F'+gi)          (off the chain)
+          f = __viaddmax_s16x2(f, a.df2, tt);                        // F' of the next row         (the only chain)
           hd = hl;
           H[r] = h;
-          hu = h;
-          best = __vmaxs2(best, h);
+          bestBlk = __vmaxs2(bestBlk, h);
         }
-        outH = hu;
+        outH = h;
         outF = f;
         if (hasNext) {
-          // lane 31 has just finished column c = b*32 + j - 31; lane (c & 31) keeps it for a coalesced store
-          uint32_t oh = __shfl_sync(0xffffffffu, outH, 31);
-          uint32_t of = __shfl_sync(0xffffffffu, outF, 31);
-          int c = b * 32 + j - 31;
-          if (lane == (c & 31)) {
-            wbH = oh;
-            wbF = of;
-          }
-          if (c >= 0 && (c & 31) == 31) {  // column block complete
-            bndOut[(c & ~31) + lane] = make_uint2(wbH, wbF);
-            __threadfence();
+          // lane 31 has just finished column c = b*32 + j - 31
+          const int c = b * 32 + j - 31;
+          if (lane == 31) s_out[wib][c & 31] = make_uint2(outH, outF);
+          if (c >= 0 && (c & 31) == 31) {  // column block complete: one coalesced, tagged 64-bit store per lane
             __syncwarp();
-            if (lane == 0) st_release(&a.progress[t], (c >> 5) + 1);
+            const uint2 o = s_out[wib][lane];
+            st_relaxed_u64(&bndOut[(c & ~31) + lane],
+                           ((((unsigned long long)o.y << 32) | o.x) & ~kTagMask) | tagOut);
+            __syncwarp();
           }
         }
       }
+      // column-block bookkeeping for the origin pass: which blocks hold a cell >= minscore
+      if ((((b + 1) >> hotShift) != (b >> hotShift)) || b == nBlocks - 1) {
+        if (sj >= 0) {
+          // per-half compare bestBlk >= minscore
+          const bool hf = (int)(int16_t)(bestBlk & 0xffffu) >= a.minscore;
+          const bool hr = (int)(int16_t)(bestBlk >> 16) >= a.minscore;
+          if (hf | hr) {
+            unsigned long long* hm = a.hotmask + ((int64_t)q * a.nSubjects + sj) * 2;
+            const unsigned long long bit = 1ull << min(b >> hotShift, 63);
+            if (hf) atomicOr(hm, bit);
+            if (hr) atomicOr(hm + 1, bit);
+          }
+        }
+        best = __vmaxs2(best, bestBlk);
+        bestBlk = 0;
+      }
     }
     // per (query, subject, strand) best
-    int sj = a.gsubject[g];
     if (sj >= 0) {
       int f = (int)(int16_t)(best & 0xffffu), rc = (int)(int16_t)(best >> 16);
       // an int16 wrap shows up as a negative or >= 32000 best: report 32767 so the pair goes to the int32 pass
@@ -252,7 +358,14 @@ __global__ void __launch_bounds__(256) swg_score_kernel(ScoreArgs a) {
       if (rc > 0) atomicMax(pb + 1, rc);
     }
     __syncwarp();
-    if (lane == 0) st_release(&a.finished[t], 1);
+    if (lane == 0) {
+      st_release(&a.finished[t], 1);
+      if (a.dbg) {
+        atomicAdd(&a.dbg[0], (unsigned long long)waitCyc);
+        atomicAdd(&a.dbg[2], 1ull);
+        atomicAdd(&a.dbg[3], (unsigned long long)(clock64() - task0));
+      }
+    }
   }
 }
 
@@ -279,10 +392,10 @@ __global__ void dpx_peak_kernel(uint32_t* out, int iters, uint32_t seed) {
       uint32_t s = prmt(Plo[r], Phi[r], sel);
       uint32_t hl = H[r];
       E[r] = __viaddmax_s16x2(E[r], ie2, hl);
-      f = __viaddmax_s16x2(f, de2, hu);
-      uint32_t m = __vmaxs2(E[r], f);
       uint32_t d = __vadd2(hd, s);
-      uint32_t h = __viaddmax_s16x2_relu(m, gi2, d);
+      uint32_t tt = __viaddmax_s16x2_relu(E[r], gi2, d);
+      uint32_t h = __viaddmax_s16x2(f, gi2, tt);
+      f = __viaddmax_s16x2(f, de2, tt);
       hd = hl;
       H[r] = h;
       hu = h;
@@ -347,6 +460,7 @@ struct OriginArgs {
   int* progress;
   int* finished;
   int* ticket;
+  int* abort_flag;
   unsigned long long* keys;    // open-addressing table
   unsigned long long* vals;
   uint32_t tableMask;
@@ -407,7 +521,7 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
     const OriginBoundary* bndIn = a.bnd + (int64_t)((t - 1 + a.nslot) % a.nslot) * a.bndStride;
     OriginBoundary* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
     if (hasNext && t >= a.nslot) {
-      if (lane == 0) wait_ge(&a.finished[t - a.nslot + 1], 1);
+      if (lane == 0) wait_ge(&a.finished[t - a.nslot + 1], 1, a.abort_flag);
       __syncwarp();
     }
     int outH = 0, outF = NEGI, diagH = 0, curQ = -1;
@@ -420,7 +534,8 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
       int qv = (col < Q) ? (int)qc[col] : -1;
       OriginBoundary bv = {0, NEGI, 0, 0};
       if (hasPrev && b < qBlocks) {
-        if (lane == 0) wait_ge(&a.progress[t - 1], b + 1);
+        // hysteresis: when the producer is not ahead, let it get kLag blocks ahead so that later blocks need no sleep
+        if (lane == 0 && ld_acquire(&a.progress[t - 1]) < b + 1) wait_ge(&a.progress[t - 1], min(b + kLag, qBlocks), a.abort_flag);
         __syncwarp();
         const int4 raw = __ldcg(reinterpret_cast<const int4*>(&bndIn[col]));
         bv.h = raw.x;
