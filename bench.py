@@ -261,7 +261,7 @@ def main():
                          "hbm_algorithmic_gbs": (Q / 2 + sum(len(x) for x in sseqs) * 8) / (k1_ms * 1e-3) / 1e9,
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},
             "stage_ms": {k: sum(s[k] for s in st_res) / len(st_res) for k in ("ms_score", "ms_origin", "ms_traceback", "ms_host_post", "ms_total")},
-            "hits": None, "pairs_passed": nS["n_pairs_passed"], "candidates": nS["n_candidates"], "origin_cells": nS["origin_cells"],
+            "hits": None, "pairs_passed": nS["n_pairs_passed"], "candidates": nS["n_candidates"], "origin_cells": nS["origin_cells"], "origin_redo": nS["n_origin_redo"],
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:

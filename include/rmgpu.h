@@ -75,6 +75,8 @@ typedef struct rmgpu_stats {
   int32_t n_pairs_passed; /* (query,strand,subject) triples with K1 best >= minscore                    */
   int32_t n_candidates;   /* origins with raw >= minscore                                               */
   double origin_cells;    /* cells K2 recomputed                                                        */
+  int32_t n_origin_redo;  /* K2 tasks redone with origin propagation over the whole fragment            */
+  int32_t pad_;
 } rmgpu_stats;
 
 typedef struct rmgpu_result {

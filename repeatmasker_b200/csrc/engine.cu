@@ -110,11 +110,16 @@ struct rmgpu_session {
 
   // ---- library layout
   int nGroups = 0, nStripes = 0;
-  std::vector<int32_t> h_gsubject;
+  std::vector<int32_t> h_gsubject, h_subjFirstGroup;
+  DevBuf<uint2> d_ck;
+  bool ckEnabled = false;
   DevBuf<uint8_t> d_rowcode, d_gflags, d_sflags, d_scodes;
   DevBuf<uint2> d_prof;
   DevBuf<int32_t> d_gsubject, d_slen, d_order, d_prodPos, d_consPos;
-  int orderGroup = 0;  // max ticket distance between a stripe and the stripe below it
+  std::vector<uint8_t> h_sflags;
+  int orderGroup = 0;   // max position distance between a stripe and the stripe below it in the ticket order
+  int orderForNQ = -1;  // batch size the order was built for
+  void build_order(int nQ, int warps);
   DevBuf<int64_t> d_soff;
   std::vector<int64_t> h_soff;
   bool profileValid = false;
@@ -140,7 +145,7 @@ struct rmgpu_session {
   DevBuf<unsigned long long> d_bnd1, d_hotmask;
   DevBuf<int32_t> d_hotShift;
   DevBuf<unsigned long long> d_dbg;
-  DevBuf<int> d_abort;
+  DevBuf<int> d_abort, d_leftFlag;
   void check_abort(const char* what);
   std::vector<int32_t> h_hotShift;
   DevBuf<OriginBoundary> d_bnd2;
@@ -157,8 +162,8 @@ struct rmgpu_session {
   void build_classes_and_profile();
   void run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest, std::vector<unsigned long long>& hotmask,
                  double& ms, int& launches);
-  void run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest, std::vector<Candidate>& cands,
-                  rmgpu_stats& st);
+  void run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest,
+                  const std::vector<unsigned long long>& hotmask, std::vector<Candidate>& cands, rmgpu_stats& st);
   void run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands, std::vector<std::vector<uint8_t>>& ops,
                      rmgpu_stats& st);
   rmgpu_result* search(const rmgpu_params& p);
@@ -214,7 +219,9 @@ void rmgpu_session::set_library(SeqSet s) {
   nGroups = nStripes * 32;
   std::vector<uint8_t> rowcode((size_t)nGroups * R, 0xFF), gflags(nGroups, 1), sflags(nStripes, 0);
   h_gsubject.assign(nGroups, -1);
+  h_subjFirstGroup.assign(n, -1);
   for (auto& pl : places) {
+    h_subjFirstGroup[pl.subject] = pl.firstGroup;
     const std::string& sq = lib.seqs[pl.subject];
     for (int gi = 0; gi < groups[pl.subject]; gi++) {
       int g = pl.firstGroup + gi;
@@ -233,53 +240,8 @@ void rmgpu_session::set_library(SeqSet s) {
       sflags[k - 1] |= 2;
     }
   }
-  // Ticket order of the stripes (same for every query).  Chains (a subject spanning several stripes) are dealt
-  // round-robin into groups of about kGroupStripes stripes; inside a group the tickets go level by level (all first
-  // stripes, then all second stripes, ...), longest chains first.  A consumer stripe is therefore claimed well
-  // after its producer started (no polling in steady state) while the producer->consumer ticket distance stays
-  // bounded by the group size, which bounds the boundary ring.
-  {
-    struct Chain {
-      int first, len;
-    };
-    std::vector<Chain> chains;
-    for (int k = 0; k < nStripes; k++) {
-      if (sflags[k] & 1)
-        chains.back().len++;
-      else
-        chains.push_back({k, 1});
-    }
-    std::stable_sort(chains.begin(), chains.end(), [](const Chain& a, const Chain& b) { return a.len > b.len; });
-    const int kGroupStripes = 2 * numSMs * 24 + 64;
-    const int nGroupsT = std::max(1, (nStripes + kGroupStripes - 1) / kGroupStripes);
-    std::vector<std::vector<Chain>> grp(nGroupsT);
-    for (size_t c = 0; c < chains.size(); c++) grp[c % nGroupsT].push_back(chains[c]);
-    std::vector<int32_t> order, posOf(nStripes, -1);
-    orderGroup = 0;
-    for (auto& gchains : grp) {
-      int tot = 0, maxLen = 0;
-      for (auto& c : gchains) {
-        tot += c.len;
-        maxLen = std::max(maxLen, c.len);
-      }
-      orderGroup = std::max(orderGroup, tot);
-      for (int level = 0; level < maxLen; level++)
-        for (auto& c : gchains)
-          if (level < c.len) {
-            posOf[c.first + level] = (int32_t)order.size();
-            order.push_back(c.first + level);
-          }
-    }
-    std::vector<int32_t> prodPos(nStripes, -1), consPos(nStripes, -1);
-    for (int pos = 0; pos < nStripes; pos++) {
-      int k = order[pos];
-      if (sflags[k] & 1) prodPos[pos] = posOf[k - 1];
-      if (sflags[k] & 2) consPos[pos] = posOf[k + 1];
-    }
-    d_order.upload(order, stream);
-    d_prodPos.upload(prodPos, stream);
-    d_consPos.upload(consPos, stream);
-  }
+  h_sflags = sflags;
+  orderForNQ = -1;
   // unpacked subject codes for K2 / K3
   h_soff.assign(n + 1, 0);
   std::vector<int32_t> slen(n);
@@ -417,6 +379,58 @@ void rmgpu_session::build_classes_and_profile() {
 
 static uint32_t pack2(int v) { return ((uint32_t)(uint16_t)(int16_t)v) | ((uint32_t)(uint16_t)(int16_t)v << 16); }
 
+// Ticket order of the stripes.  Ticket t = position * nQ + query: a "level" of the order spans all queries of the
+// batch.  Chains (a subject spanning several stripes) are dealt round-robin into groups; inside a group positions go
+// level by level (all first stripes, then all second stripes, ...).  With group sizes chosen so that one level holds
+// a few times more tickets than there are resident warps, a consumer stripe is claimed long after its producer
+// finished (no polling in steady state), while the producer->consumer distance stays bounded by the group size,
+// which bounds the boundary ring.
+void rmgpu_session::build_order(int nQ, int warps) {
+  if (orderForNQ == nQ) return;
+  struct Chain {
+    int first, len;
+  };
+  std::vector<Chain> chains;
+  for (int k = 0; k < nStripes; k++) {
+    if (h_sflags[k] & 1)
+      chains.back().len++;
+    else
+      chains.push_back({k, 1});
+  }
+  std::stable_sort(chains.begin(), chains.end(), [](const Chain& a, const Chain& b) { return a.len > b.len; });
+  // aim at ~3 x warps tickets per level: chainsPerGroup * nQ ~ 3 * warps
+  const int chainsPerGroup = std::max(8, (3 * warps + nQ - 1) / std::max(nQ, 1));
+  const int nGroupsT = std::max(1, ((int)chains.size() + chainsPerGroup - 1) / chainsPerGroup);
+  std::vector<std::vector<Chain>> grp(nGroupsT);
+  for (size_t c = 0; c < chains.size(); c++) grp[c % nGroupsT].push_back(chains[c]);
+  std::vector<int32_t> order, posOf(nStripes, -1);
+  orderGroup = 0;
+  for (auto& gchains : grp) {
+    int tot = 0, maxLen = 0;
+    for (auto& c : gchains) {
+      tot += c.len;
+      maxLen = std::max(maxLen, c.len);
+    }
+    orderGroup = std::max(orderGroup, tot);
+    for (int level = 0; level < maxLen; level++)
+      for (auto& c : gchains)
+        if (level < c.len) {
+          posOf[c.first + level] = (int32_t)order.size();
+          order.push_back(c.first + level);
+        }
+  }
+  std::vector<int32_t> prodPos(nStripes, -1), consPos(nStripes, -1);
+  for (int pos = 0; pos < nStripes; pos++) {
+    int k = order[pos];
+    if (h_sflags[k] & 1) prodPos[pos] = posOf[k - 1];
+    if (h_sflags[k] & 2) consPos[pos] = posOf[k + 1];
+  }
+  d_order.upload(order, stream);
+  d_prodPos.upload(prodPos, stream);
+  d_consPos.upload(consPos, stream);
+  orderForNQ = nQ;
+}
+
 void rmgpu_session::check_abort(const char* what) {
   int f = 0;
   CUDA_CHECK(cudaMemcpyAsync(&f, d_abort.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -442,8 +456,9 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   if (nTickets >= (1ll << 31)) throw Error("too many stripe tasks in one batch");
   int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, (nTickets + kScoreWarps - 1) / kScoreWarps);
   const int warps = grid * kScoreWarps;
-  // ring slots: a slot is rewritten nslot tickets later; its reader is at most orderGroup tickets after its writer
-  const int nslot = (int)std::min<int64_t>(nTickets, std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)orderGroup + 2));
+  build_order(nQ, warps);
+  // ring slots: a slot is rewritten nslot tickets later; its reader is at most orderGroup * nQ tickets after its writer
+  const int nslot = (int)std::min<int64_t>(nTickets, std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)orderGroup * nQ + 2));
   const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
   ScoreArgs a;
   a.prof = d_prof.p;
@@ -472,7 +487,14 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   a.df2 = pack2(std::max(p.del_gap_ext, p.gap_init));
   a.minscore = std::min(p.minscore, 32000);
   a.abort_flag = d_abort.ensure(1);
-  a.dbgMode = getenv("RMGPU_K1_MODE") ? atoi(getenv("RMGPU_K1_MODE")) : 0;
+  // column checkpoints for the origin pass (64 per query): only when they fit the budget
+  {
+    static const bool noCk = getenv("RMGPU_NO_CHECKPOINTS") != nullptr;
+    const int64_t ckElems = (int64_t)nQ * 64 * nGroups * R;
+    ckEnabled = !noCk && ckElems * (int64_t)sizeof(uint2) <= (24ll << 30);
+    a.ck = ckEnabled ? d_ck.ensure((size_t)ckElems) : nullptr;
+    a.ckRows = (int64_t)nGroups * R;
+  }
   CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream));
   static const bool dbgOn = getenv("RMGPU_DEBUG_K1") != nullptr;
   a.dbg = nullptr;
@@ -505,121 +527,235 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   }
 }
 
-// K2 over every (query, strand, subject) whose K1 best reached minscore.
-void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest, std::vector<Candidate>& cands,
+// K2 over every (query, strand, subject) whose K1 best reached minscore.  Only the column blocks K1 marked hot
+// (dilated by one block each side) are swept with origin propagation; a task whose hits turn out to need origins
+// from outside those blocks is flagged by the kernel and redone with every block in origin mode.
+void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest,
+                               const std::vector<unsigned long long>& hotmask, std::vector<Candidate>& cands,
                                rmgpu_stats& st) {
   const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
+  static const bool fullMode = getenv("RMGPU_K2_FULL") != nullptr;
+  struct Triple {
+    int q, strand, subject;
+  };
+  std::vector<Triple> triples;
   std::vector<OriginTask> tasks;
-  std::vector<int32_t> ticketTask;
+  std::vector<int> taskTriple;
+  auto full_task = [&](int q, int strand, int s, unsigned long long mode) {
+    OriginTask t;
+    memset(&t, 0, sizeof(t));
+    t.q = q;
+    t.strand = strand;
+    t.subject = s;
+    t.nStripes = (int)((lib.seqs[s].size() + kR2 * 32 - 1) / (kR2 * 32));
+    t.mode = mode;
+    t.hotShift = h_hotShift[q];
+    t.c0 = 0;
+    t.c1 = h_qlen[q];
+    t.ckOff = -1;
+    return t;
+  };
   for (int q = 0; q < nQ; q++)
     for (int s = 0; s < nS; s++)
-      for (int strand = 0; strand < 2; strand++)
-        if (pairbest[((size_t)q * nS + s) * 2 + strand] >= std::min(p.minscore, 32000)) {
-          int64_t Q = h_qlen[q], L = (int64_t)lib.seqs[s].size();
-          if ((Q + 1) * (L + 1) >= (1ll << 32))
-            throw Error("query x subject too large for one origin pass (" + queries.names[q] + " x " + lib.names[s] +
-                        "): fragment the query as SimpleBatcher does");
-          OriginTask t;
-          t.q = q;
-          t.strand = strand;
-          t.subject = s;
-          t.firstTicket = (int)ticketTask.size();
-          t.nStripes = (int)((L + kR2 * 32 - 1) / (kR2 * 32));
-          for (int k = 0; k < t.nStripes; k++) ticketTask.push_back((int32_t)tasks.size());
-          tasks.push_back(t);
+      for (int strand = 0; strand < 2; strand++) {
+        const size_t idx = ((size_t)q * nS + s) * 2 + strand;
+        if (pairbest[idx] < std::min(p.minscore, 32000)) continue;
+        const int64_t Q = h_qlen[q], L = (int64_t)lib.seqs[s].size();
+        if ((Q + 1) * (L + 1) >= (1ll << 32))
+          throw Error("query x subject too large for one origin pass (" + queries.names[q] + " x " + lib.names[s] +
+                      "): fragment the query as SimpleBatcher does");
+        const int tr = (int)triples.size();
+        triples.push_back({q, strand, s});
+        const unsigned long long m = hotmask[idx];
+        const unsigned long long dil = m | (m << 1) | (m >> 1);
+        const bool overflowed = pairbest[idx] >= 32000;
+        if (overflowed || fullMode || dil == 0) {
+          tasks.push_back(full_task(q, strand, s, ~0ull));
+          taskTriple.push_back(tr);
           st.origin_cells += (double)Q * (double)L;
+        } else if (!ckEnabled) {
+          tasks.push_back(full_task(q, strand, s, dil));
+          taskTriple.push_back(tr);
+          st.origin_cells += (double)Q * (double)L;
+        } else {
+          // one task per run of hot column blocks, started from K1's checkpoint before the run
+          const int64_t CB = 32ll << h_hotShift[q];
+          for (int c = 0; c < 64;) {
+            if (!((dil >> c) & 1ull)) {
+              c++;
+              continue;
+            }
+            int e = c;
+            while (e + 1 < 64 && ((dil >> (e + 1)) & 1ull)) e++;
+            OriginTask t = full_task(q, strand, s, ~0ull);
+            t.c0 = (int)std::min<int64_t>(Q, c * CB);
+            t.c1 = (e == 63) ? (int)Q : (int)std::min<int64_t>(Q, (e + 1) * CB);
+            if (t.c0 > 0) t.ckOff = ((int64_t)q * 64 + c) * ((int64_t)nGroups * R) + (int64_t)h_subjFirstGroup[s] * R;
+            if (t.c1 > t.c0) {
+              tasks.push_back(t);
+              taskTriple.push_back(tr);
+              st.origin_cells += (double)(t.c1 - t.c0) * (double)L;
+            }
+            c = e + 1;
+          }
         }
-  st.n_pairs_passed = (int)tasks.size();
+      }
+  st.n_pairs_passed = (int)triples.size();
   cands.clear();
   if (tasks.empty()) return;
-  const int nTickets = (int)ticketTask.size();
   int blocksPerSM = 0;
   CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_origin_kernel, 128, 0));
   if (blocksPerSM < 1) throw Error("K2 does not fit on an SM");
   blocksPerSM = std::min(blocksPerSM, 4);
-  int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, ((int64_t)nTickets + 3) / 4);
-  const int warps = grid * 4;
-  const int nslot = std::min(nTickets, 2 * warps + 2);
   const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
-  size_t tableSize = 1u << 18;
-  for (;;) {
-    OriginArgs a;
-    d_tasks.upload(tasks, stream);
-    d_ticketTask.upload(ticketTask, stream);
-    a.tasks = d_tasks.p;
-    a.ticketTask = d_ticketTask.p;
-    a.nTickets = nTickets;
-    a.codes_fwd = d_codes_fwd.p;
-    a.codes_rc = d_codes_rc.p;
-    a.qoff = d_qoff.p;
-    a.qlen = d_qlen.p;
-    a.scodes = d_scodes.p;
-    a.soff = d_soff.p;
-    a.slen = d_slen.p;
-    for (int i = 0; i < 16; i++)
-      for (int j = 0; j < 16; j++) a.mat[i][j] = (i < matrix.n && j < matrix.n) ? matrix.score[i][j] : -128;
-    a.gap_init = p.gap_init;
-    a.ins_ext = p.ins_gap_ext;
-    a.del_ext = p.del_gap_ext;
-    a.minscore = p.minscore;
-    a.bnd = d_bnd2.ensure((size_t)nslot * bndStride);
-    a.bndStride = bndStride;
-    a.nslot = nslot;
-    a.progress = d_progress.ensure((size_t)nTickets);
-    a.finished = d_finished.ensure((size_t)nTickets);
-    a.ticket = d_ticket.ensure(1);
-    a.keys = d_keys.ensure(tableSize);
-    a.vals = d_vals.ensure(tableSize);
-    a.tableMask = (uint32_t)tableSize - 1;
-    a.overflow = d_overflow.ensure(1);
-    a.abort_flag = d_abort.ensure(1);
-    CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream));
-    CUDA_CHECK(cudaMemsetAsync(a.keys, 0xFF, tableSize * 8, stream));
-    CUDA_CHECK(cudaMemsetAsync(a.vals, 0, tableSize * 8, stream));
-    CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream));
-    CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream));
-    CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), stream));
-    CUDA_CHECK(cudaMemsetAsync(a.overflow, 0, sizeof(int), stream));
-    EventTimer tm;
-    tm.start(stream);
-    swg_origin_kernel<<<grid, 128, 0, stream>>>(a);
-    tm.stop(stream);
-    CUDA_CHECK(cudaGetLastError());
-    std::vector<unsigned long long> keys(tableSize), vals(tableSize);
-    int overflow = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaMemcpyAsync(keys.data(), a.keys, tableSize * 8, cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaMemcpyAsync(vals.data(), a.vals, tableSize * 8, cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
-    check_abort("K2");
-    st.ms_origin += tm.ms();
-    st.launches += 1;
-    st.d2h_bytes += (int64_t)tableSize * 16;
-    size_t used = 0;
-    for (size_t i = 0; i < tableSize; i++) used += keys[i] != kEmptyKey;
-    if (overflow || used * 2 > tableSize) {  // keep the table sparse; rerun bigger
-      tableSize *= 4;
-      if (tableSize > (1u << 28)) throw Error("candidate table overflow");
-      if (overflow) continue;
+  std::vector<char> tripleRedo(triples.size(), 0);
+  std::vector<std::pair<int, Candidate>> found;  // (triple, candidate)
+  for (int round = 0; round < 2 && !tasks.empty(); round++) {
+    std::vector<int32_t> ticketTask;
+    for (size_t i = 0; i < tasks.size(); i++) {
+      tasks[i].firstTicket = (int)ticketTask.size();
+      for (int k = 0; k < tasks[i].nStripes; k++) ticketTask.push_back((int32_t)i);
     }
-    for (size_t i = 0; i < tableSize && i < keys.size(); i++) {
-      if (keys[i] == kEmptyKey) continue;
-      int ti = (int)(keys[i] >> 32);
-      uint32_t origin = (uint32_t)keys[i];
-      const OriginTask& t = tasks[ti];
-      Candidate c;
-      c.q = t.q;
-      c.strand = t.strand;
-      c.subject = t.subject;
-      const uint32_t Lp1 = (uint32_t)lib.seqs[t.subject].size() + 1u;
-      c.i0 = (int)(origin / Lp1);
-      c.j0 = (int)(origin % Lp1);
-      c.raw = (int)(vals[i] >> 40);
-      c.i1 = (int)(0xFFFFFu - (uint32_t)((vals[i] >> 20) & 0xFFFFFu));
-      c.j1 = (int)(0xFFFFFu - (uint32_t)(vals[i] & 0xFFFFFu));
-      cands.push_back(c);
+    const int nTickets = (int)ticketTask.size();
+    int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, ((int64_t)nTickets + 3) / 4);
+    const int warps = grid * 4;
+    const int nslot = std::min(nTickets, 2 * warps + 2);
+    std::vector<int> leftFlag(tasks.size(), 0);
+    size_t tableSize = 1u << 18;
+    for (;;) {
+      OriginArgs a;
+      d_tasks.upload(tasks, stream);
+      d_ticketTask.upload(ticketTask, stream);
+      a.tasks = d_tasks.p;
+      a.ticketTask = d_ticketTask.p;
+      a.nTickets = nTickets;
+      a.codes_fwd = d_codes_fwd.p;
+      a.codes_rc = d_codes_rc.p;
+      a.qoff = d_qoff.p;
+      a.qlen = d_qlen.p;
+      a.scodes = d_scodes.p;
+      a.soff = d_soff.p;
+      a.slen = d_slen.p;
+      for (int i = 0; i < 16; i++)
+        for (int j = 0; j < 16; j++) a.mat[i][j] = (i < matrix.n && j < matrix.n) ? matrix.score[i][j] : -128;
+      a.gap_init = p.gap_init;
+      a.ins_ext = p.ins_gap_ext;
+      a.del_ext = p.del_gap_ext;
+      a.minscore = p.minscore;
+      a.bnd = d_bnd2.ensure((size_t)nslot * bndStride);
+      a.bndStride = bndStride;
+      a.nslot = nslot;
+      a.progress = d_progress.ensure((size_t)nTickets);
+      a.finished = d_finished.ensure((size_t)nTickets);
+      a.ticket = d_ticket.ensure(1);
+      a.keys = d_keys.ensure(tableSize);
+      a.vals = d_vals.ensure(tableSize);
+      a.tableMask = (uint32_t)tableSize - 1;
+      a.overflow = d_overflow.ensure(1);
+      a.abort_flag = d_abort.ensure(1);
+      static const bool dbgOn2 = getenv("RMGPU_DEBUG_K2") != nullptr;
+      a.dbg = nullptr;
+      if (dbgOn2) {
+        a.dbg = d_dbg.ensure(4);
+        CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 32, stream));
+      }
+      a.ck = d_ck.p;
+      a.leftFlag = d_leftFlag.ensure(tasks.size());
+      CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream));
+      CUDA_CHECK(cudaMemsetAsync(a.leftFlag, 0, tasks.size() * sizeof(int), stream));
+      CUDA_CHECK(cudaMemsetAsync(a.keys, 0xFF, tableSize * 8, stream));
+      CUDA_CHECK(cudaMemsetAsync(a.vals, 0, tableSize * 8, stream));
+      CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream));
+      CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream));
+      CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), stream));
+      CUDA_CHECK(cudaMemsetAsync(a.overflow, 0, sizeof(int), stream));
+      EventTimer tm;
+      tm.start(stream);
+      swg_origin_kernel<<<grid, 128, 0, stream>>>(a);
+      tm.stop(stream);
+      CUDA_CHECK(cudaGetLastError());
+      std::vector<unsigned long long> keys(tableSize), vals(tableSize);
+      int overflow = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaMemcpyAsync(leftFlag.data(), a.leftFlag, tasks.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaMemcpyAsync(keys.data(), a.keys, tableSize * 8, cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaMemcpyAsync(vals.data(), a.vals, tableSize * 8, cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaStreamSynchronize(stream));
+      check_abort("K2");
+      if (dbgOn2) {
+        unsigned long long d[4];
+        CUDA_CHECK(cudaMemcpy(d, a.dbg, 32, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[K2 dbg] %.2f ms tasks %zu tickets %llu grid %d: guard-wait %.1f%% producer-wait %.1f%% of ticket cycles, mean ticket %.0f cyc\n", tm.ms(),
+                tasks.size(), d[2], grid, 100.0 * d[0] / std::max(d[3], 1ull), 100.0 * d[1] / std::max(d[3], 1ull), (double)d[3] / std::max(d[2], 1ull));
+      }
+      st.ms_origin += tm.ms();
+      st.launches += 1;
+      st.d2h_bytes += (int64_t)tableSize * 16;
+      size_t used = 0;
+      for (size_t i = 0; i < tableSize; i++) used += keys[i] != kEmptyKey;
+      if (overflow || used * 2 > tableSize) {  // keep the table sparse; rerun bigger
+        tableSize *= 4;
+        if (tableSize > (1u << 28)) throw Error("candidate table overflow");
+        if (overflow) continue;
+      }
+      for (size_t i = 0; i < tasks.size(); i++)
+        if (leftFlag[i]) {
+          if (round > 0) throw Error("origin pass: a fully swept task still reports a left origin");
+          tripleRedo[taskTriple[i]] = 1;
+        }
+      for (size_t i = 0; i < keys.size(); i++) {
+        if (keys[i] == kEmptyKey) continue;
+        int ti = (int)(keys[i] >> 32);
+        uint32_t origin = (uint32_t)keys[i];
+        const OriginTask& t = tasks[ti];
+        Candidate c;
+        c.q = t.q;
+        c.strand = t.strand;
+        c.subject = t.subject;
+        const uint32_t Lp1 = (uint32_t)lib.seqs[t.subject].size() + 1u;
+        c.i0 = (int)(origin / Lp1);
+        c.j0 = (int)(origin % Lp1);
+        c.raw = (int)(vals[i] >> 40);
+        c.i1 = (int)(0xFFFFFu - (uint32_t)((vals[i] >> 20) & 0xFFFFFu));
+        c.j1 = (int)(0xFFFFFu - (uint32_t)(vals[i] & 0xFFFFFu));
+        found.push_back({taskTriple[ti], c});
+      }
+      break;
     }
-    break;
+    // triples whose hits need origins from outside their windows are redone with one full sweep
+    std::vector<OriginTask> redo;
+    std::vector<int> redoTriple;
+    if (round == 0) {
+      for (size_t tr = 0; tr < triples.size(); tr++)
+        if (tripleRedo[tr]) {
+          redo.push_back(full_task(triples[tr].q, triples[tr].strand, triples[tr].subject, ~0ull));
+          redoTriple.push_back((int)tr);
+          st.origin_cells += (double)h_qlen[triples[tr].q] * (double)lib.seqs[triples[tr].subject].size();
+        }
+      // drop what the windowed tasks of those triples found: the full sweep finds all of it again
+      std::vector<std::pair<int, Candidate>> keep;
+      for (auto& f : found)
+        if (!tripleRedo[f.first]) keep.push_back(f);
+      found.swap(keep);
+    }
+    st.n_origin_redo += (int)redo.size();
+    tasks.swap(redo);
+    taskTriple.swap(redoTriple);
+  }
+  // an alignment that crosses two windows of one triple is seen by both with the same origin: keep the better end
+  std::sort(found.begin(), found.end(), [](const std::pair<int, Candidate>& x, const std::pair<int, Candidate>& y) {
+    if (x.first != y.first) return x.first < y.first;
+    if (x.second.i0 != y.second.i0) return x.second.i0 < y.second.i0;
+    if (x.second.j0 != y.second.j0) return x.second.j0 < y.second.j0;
+    if (x.second.raw != y.second.raw) return x.second.raw > y.second.raw;
+    if (x.second.i1 != y.second.i1) return x.second.i1 < y.second.i1;
+    return x.second.j1 < y.second.j1;
+  });
+  for (size_t i = 0; i < found.size(); i++) {
+    if (i > 0 && found[i].first == found[i - 1].first && found[i].second.i0 == found[i - 1].second.i0 &&
+        found[i].second.j0 == found[i - 1].second.j0)
+      continue;
+    cands.push_back(found[i].second);
   }
   std::sort(cands.begin(), cands.end(), [](const Candidate& x, const Candidate& y) {
     if (x.q != y.q) return x.q < y.q;
@@ -800,7 +936,7 @@ rmgpu_result* rmgpu_session::search(const rmgpu_params& p) {
   st.score_launches = 1;
   st.d2h_bytes += (int64_t)pairbest.size() * 12;
   std::vector<Candidate> cands;
-  run_origin(p, pairbest, cands, st);
+  run_origin(p, pairbest, hotmask, cands, st);
   std::vector<std::vector<uint8_t>> ops;
   run_traceback(p, cands, ops, st);
 

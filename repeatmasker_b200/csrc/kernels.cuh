@@ -161,7 +161,8 @@ struct ScoreArgs {
   uint32_t gi2, ie2, df2;     // gap_init, ins_gap_ext, max(del_gap_ext, gap_init), replicated in both halves
   int minscore;
   int* abort_flag;            // set by the watchdog
-  int dbgMode;                // bit0: no hysteresis, bit1: no prefetch (debug)
+  uint2* ck;                  // optional column checkpoints [(q*64 + cb) * ckRows + g*R + r] = (H, E') before column cb*CB
+  int64_t ckRows;             // nGroups * R
   unsigned long long* dbg;    // optional [4]: cycles waiting on the producer, cycles waiting on a slot, tasks, task cycles
 };
 
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     if (lane == 0) t = atomicAdd(a.ticket, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= nTickets) break;
-    const int q = t / a.nStripes, pos = t - q * a.nStripes;
+    const int pos = t / a.nQueries, q = t - pos * a.nQueries;  // query fastest: a level of the order spans all queries
     const int k = a.order[pos];
     const int g = k * 32 + lane;
     const int Q = a.qlen[q];
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     }
     const int qBlocks = (Q + 31) >> 5;
     const int nBlocks = qBlocks + 1;  // lane 31 reaches column qBlocks*32 >= Q
-    const int tProd = hasPrev ? q * a.nStripes + a.prodPos[pos] : 0;  // ticket of the stripe above (always older)
+    const int tProd = hasPrev ? a.prodPos[pos] * a.nQueries + q : 0;  // ticket of the stripe above (always older)
     const unsigned long long* bndIn = a.bnd + (int64_t)(tProd % a.nslot) * a.bndStride;
     unsigned long long* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
     const unsigned long long tagIn = tag_bits(tProd, a.nslot), tagOut = tag_bits(t, a.nslot);
@@ -224,11 +225,11 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
       // The slot still holds the boundary of the last ticket that WROTE it (t - nslot, t - 2 nslot, ... skipping
       // tickets whose stripe has no stripe below): its reader must be done before this ticket overwrites it.
       for (int tOld = t - a.nslot; tOld >= 0; tOld -= a.nslot) {
-        const int qOld = tOld / a.nStripes;
-        const int cOld = a.consPos[tOld - qOld * a.nStripes];
+        const int pOld = tOld / a.nQueries;
+        const int cOld = a.consPos[pOld];
         if (cOld < 0) continue;
         const long long w0 = clock64();
-        if (lane == 0) wait_ge(&a.finished[qOld * a.nStripes + cOld], 1, a.abort_flag);
+        if (lane == 0) wait_ge(&a.finished[cOld * a.nQueries + (tOld - pOld * a.nQueries)], 1, a.abort_flag);
         __syncwarp();
         if (a.dbg && lane == 0) atomicAdd(&a.dbg[1], (unsigned long long)(clock64() - w0));
         break;
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     const long long task0 = clock64();
     long long waitCyc = 0;
     const int hotShift = a.hotShift[q];
+    const int ckBlkMask = (1 << hotShift) - 1;
     const int sj = a.gsubject[g];
     uint32_t best = 0, bestBlk = 0, outH = 0, outF = 0, diag = 0, curSel = kPadSel;
     unsigned long long nextRaw = 0;
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           if (!__all_sync(0xffffffffu, (raw & kTagMask) == tagIn)) {
             const long long w0 = clock64();
             // caught up with the producer: sleep until it is kLag blocks ahead (hysteresis), then take block b
-            const int far = (a.dbgMode & 1) ? b : min(b + kLag, qBlocks - 1);
+            const int far = min(b + kLag, qBlocks - 1);
             unsigned ns = 128;
             bool dead = false;
             for (;;) {
@@ -279,8 +281,10 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           }
         }
         raw &= ~kTagMask;
-        if (b + 1 < qBlocks && !(a.dbgMode & 2)) nextRaw = ld_relaxed_u64(&bndIn[(b + 1) * 32 + lane]);  // prefetch, validated next block
+        if (b + 1 < qBlocks) nextRaw = ld_relaxed_u64(&bndIn[(b + 1) * 32 + lane]);  // prefetch, validated next block
       }
+      // lane l reaches column b*32 at step j == l; that column starts a checkpointed block iff b is a multiple of CB/32
+      const bool ckBlock = a.ck != nullptr && b > 0 && (b & ckBlkMask) == 0 && b * 32 < Q;
       __syncwarp();  // everyone is done reading the previous block's feed
       s_feed[wib][lane] = make_uint4(selv, (uint32_t)raw, (uint32_t)(raw >> 32), 0u);
       __syncwarp();
@@ -300,6 +304,12 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           inF = 0;
         }
         curSel = inSel;
+        if (ckBlock && j == lane) {
+          // column checkpoint for the origin pass: the (H, E') this lane holds before it starts column b*32 = cb*CB
+          uint2* dst = a.ck + ((int64_t)q * 64 + (b >> hotShift)) * a.ckRows + (int64_t)g * R;
+#pragma unroll
+          for (int r = 0; r < R; r++) dst[r] = make_uint2(H[r], E[r]);
+        }
         uint32_t hd = diag, f = inF, h = 0;
         diag = inH;
 #pragma unroll
@@ -428,12 +438,18 @@ __global__ void dpx_instr_kernel(uint32_t* out, int iters) {
 // H >= minscore is a candidate end: per (task, origin) the table keeps max score, then min i, then min j.
 // Same stripe pipeline as K1 with R2 rows per lane.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kR2 = 4;
+constexpr int kR2 = 8;
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kOriginLeft = 0xFFFFFFFFu;  // "the origin lies in a part of the matrix swept without origins"
 
 struct OriginTask {
   int32_t q, strand, subject;
   int32_t firstTicket, nStripes;  // stripes of kR2*32 rows
+  unsigned long long mode;        // bit c: sweep column block c with origin propagation (else score only)
+  int32_t hotShift;               // column block c = ((column >> 5) >> hotShift), capped at 63
+  int32_t c0, c1;                 // query columns [c0, c1) swept by this task (0-based)
+  int32_t pad_;
+  int64_t ckOff;                  // offset of the subject's first row in the K1 checkpoint taken before column c0, or -1
 };
 
 struct OriginBoundary {  // per column, last row of the stripe above
@@ -461,6 +477,9 @@ struct OriginArgs {
   int* finished;
   int* ticket;
   int* abort_flag;
+  const uint2* ck;             // K1 column checkpoints (H, E' both strands), see ScoreArgs
+  unsigned long long* dbg;     // optional [4]: guard-wait cycles, producer-wait cycles, tickets, ticket cycles
+  int* leftFlag;               // [nTasks] set when a hit needs origins from a score-only region: redo that task fully
   unsigned long long* keys;    // open-addressing table
   unsigned long long* vals;
   uint32_t tableMask;
@@ -469,9 +488,13 @@ struct OriginArgs {
 
 // An origin (i0, j0) is carried as one 32-bit word i0 * (L + 1) + j0 (L = subject length); the host checks
 // (Q + 1) * (L + 1) < 2^32 per task (any SimpleBatcher fragment, <= 75 kbp, against subjects up to 57 kbp).
-__device__ __forceinline__ void origin_emit(const OriginArgs& a, int task, uint32_t origin, int h, int i, int j) {
+// value of a candidate end: larger = better score, then smaller i, then smaller j
+__device__ __forceinline__ unsigned long long cand_val(int h, int i, int j) {
+  return ((unsigned long long)(uint32_t)h << 40) | ((unsigned long long)(0xFFFFFu - (uint32_t)i) << 20) |
+         (unsigned long long)(0xFFFFFu - (uint32_t)j);
+}
+__device__ __forceinline__ void origin_emit(const OriginArgs& a, int task, uint32_t origin, unsigned long long val) {
   uint64_t key = ((uint64_t)(uint32_t)task << 32) | origin;
-  uint64_t val = ((uint64_t)(uint32_t)h << 40) | ((uint64_t)(0xFFFFFu - (uint32_t)i) << 20) | (uint64_t)(0xFFFFFu - (uint32_t)j);
   uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & a.tableMask;
   for (uint32_t probe = 0; probe <= a.tableMask; probe++) {
     unsigned long long old = atomicCAS(&a.keys[slot], kEmptyKey, key);
@@ -484,6 +507,10 @@ __device__ __forceinline__ void origin_emit(const OriginArgs& a, int task, uint3
   atomicExch(a.overflow, 1);
 }
 
+// Column blocks that K1 saw reach minscore (dilated by one block on either side by the host) are swept with origin
+// propagation; all other columns with the plain int32 recurrence (same H/E/F values, about a quarter of the
+// instructions).  Entering an origin block, every live path gets the origin kOriginLeft; a candidate carrying it,
+// or any cell >= minscore met in score-only mode, flags the task and the host redoes it with mode = all ones.
 __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
   __shared__ int32_t smat[16 * 16];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
@@ -517,32 +544,68 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
       oH[r] = 0;
       oE[r] = 0;
     }
-    const int qBlocks = (Q + 31) >> 5, nBlocks = qBlocks + 1;
+    const long long k2t0 = clock64();
+    long long k2wait = 0;
+    const int W = tk.c1 - tk.c0;  // columns of this task's window
+    const int qBlocks = (W + 31) >> 5, nBlocks = qBlocks + 1;
     const OriginBoundary* bndIn = a.bnd + (int64_t)((t - 1 + a.nslot) % a.nslot) * a.bndStride;
     OriginBoundary* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
-    if (hasNext && t >= a.nslot) {
-      if (lane == 0) wait_ge(&a.finished[t - a.nslot + 1], 1, a.abort_flag);
-      __syncwarp();
+    if (hasNext) {
+      // the reader (ticket + 1) of the last ticket that wrote this ring slot must be done
+      for (int tOld = t - a.nslot; tOld >= 0; tOld -= a.nslot) {
+        const OriginTask& ot = a.tasks[a.ticketTask[tOld]];
+        if (tOld - ot.firstTicket + 1 >= ot.nStripes) continue;  // that ticket had no stripe below: it wrote nothing
+        const long long g0 = clock64();
+        if (lane == 0) wait_ge(&a.finished[tOld + 1], 1, a.abort_flag);
+        __syncwarp();
+        if (a.dbg && lane == 0) atomicAdd(&a.dbg[0], (unsigned long long)(clock64() - g0));
+        break;
+      }
     }
     int outH = 0, outF = NEGI, diagH = 0, curQ = -1;
     uint32_t outOH = 0, outOF = 0, diagO = 0;
     OriginBoundary wb = {0, NEGI, 0, 0};
-    uint32_t lastOrigin = 0xFFFFFFFFu;
-    int lastBest = 0;
+    uint32_t lastOrigin = kOriginLeft;  // nothing cached
+    unsigned long long lastVal = 0;
+    bool prevMode = false, needFull = false;
+    if (tk.ckOff >= 0) {
+      // start from K1's exact column state before column c0; every live path gets the "left" origin
+      const uint2* ck = a.ck + tk.ckOff;
+      const int sh = tk.strand ? 16 : 0;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (row0 + r < L) {
+          const uint2 v = ck[row0 + r];
+          H[r] = (int)((v.x >> sh) & 0xffffu);
+          E[r] = (int)((v.y >> sh) & 0xffffu) + a.gap_init;
+        }
+        oH[r] = kOriginLeft;
+        oE[r] = kOriginLeft;
+      }
+      if (row0 > 0 && row0 - 1 < L) diagH = (int)((ck[row0 - 1].x >> sh) & 0xffffu);
+      diagO = kOriginLeft;
+      prevMode = true;
+    }
     for (int b = 0; b < nBlocks; b++) {
-      int col = b * 32 + lane;
-      int qv = (col < Q) ? (int)qc[col] : -1;
+      int col = b * 32 + lane;  // column offset inside the window
+      int qv = (col < W) ? (int)qc[tk.c0 + col] : -1;
       OriginBoundary bv = {0, NEGI, 0, 0};
       if (hasPrev && b < qBlocks) {
         // hysteresis: when the producer is not ahead, let it get kLag blocks ahead so that later blocks need no sleep
+        const long long w0 = clock64();
         if (lane == 0 && ld_acquire(&a.progress[t - 1]) < b + 1) wait_ge(&a.progress[t - 1], min(b + kLag, qBlocks), a.abort_flag);
         __syncwarp();
+        k2wait += clock64() - w0;
         const int4 raw = __ldcg(reinterpret_cast<const int4*>(&bndIn[col]));
         bv.h = raw.x;
         bv.f = raw.y;
         bv.oh = (uint32_t)raw.z;
         bv.of = (uint32_t)raw.w;
       }
+      // mode of this lane's column: lanes lag the block by `lane` columns, so two 32-column blocks are involved
+      const int b0 = tk.c0 >> 5;  // windows start on 32-column boundaries
+      const bool modeCur = (tk.mode >> min((b0 + b) >> tk.hotShift, 63)) & 1ull;
+      const bool modeOld = b > 0 ? (bool)((tk.mode >> min((b0 + b - 1) >> tk.hotShift, 63)) & 1ull) : modeCur;
       for (int j = 0; j < 32; j++) {
         int inQ = __shfl_up_sync(0xffffffffu, curQ, 1);
         int inH = __shfl_up_sync(0xffffffffu, outH, 1);
@@ -562,76 +625,119 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
           inOF = fof;
         }
         curQ = inQ;
-        const int i1 = b * 32 + j - lane + 1;  // 1-based query column of this lane at this step
+        const int i1 = tk.c0 + b * 32 + j - lane + 1;  // 1-based query column of this lane at this step
+        const bool mode = (j >= lane) ? modeCur : modeOld;
         int hd = diagH, hu = inH, f = inF;
-        uint32_t od = diagO, ou = inOH, of = inOF;
         diagH = inH;
-        diagO = inOH;
         const bool active = curQ >= 0;
+        if (!mode) {
+          // ---- score-only sweep: identical H/E/F values, no origins
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          int hl = H[r];
-          uint32_t ol = oH[r];
-          int hnew = 0;
-          uint32_t onew = 0;
-          if (active && srow[r] >= 0) {
-            int e_ext = E[r] + a.ins_ext, e_open = hl + a.gap_init;
-            if (e_ext >= e_open) {
-              E[r] = e_ext;
+          for (int r = 0; r < R; r++) {
+            const int hl = H[r];
+            int hnew = 0;
+            if (active && srow[r] >= 0) {
+              const int e = max(E[r] + a.ins_ext, hl + a.gap_init);
+              f = max(f + a.del_ext, hu + a.gap_init);
+              const int d = hd + smat[srow[r] + curQ];
+              hnew = max(max(e, f), max(d, 0));
+              E[r] = e;
+              needFull |= hnew >= a.minscore;
             } else {
-              E[r] = e_open;
-              oE[r] = ol;
+              E[r] = NEGI;
+              f = NEGI;
             }
-            int f_ext = f + a.del_ext, f_open = hu + a.gap_init;
-            if (f_ext >= f_open) {
-              f = f_ext;
-            } else {
-              f = f_open;
-              of = ou;
-            }
-            int s = smat[srow[r] + curQ];
-            int d = hd + s;
-            uint32_t odd = hd > 0 ? od : ((uint32_t)i1 * Lp1 + (uint32_t)(row0 + r + 1));
-            hnew = E[r];
-            onew = oE[r];
-            bool viaDiag = false;
-            if (f > hnew) {
-              hnew = f;
-              onew = of;
-            }
-            if (d > hnew) {
-              hnew = d;
-              onew = odd;
-              viaDiag = true;
-            }
-            if (hnew <= 0) {
-              hnew = 0;
-              onew = 0;
-              viaDiag = false;
-            }
-            if (viaDiag && hnew >= a.minscore) {
-              if (onew != lastOrigin || hnew > lastBest) {
-                origin_emit(a, ti, onew, hnew, i1, row0 + r + 1);
-                lastOrigin = onew;
-                lastBest = hnew;
-              }
-            }
-          } else {
-            // outside the matrix: keep a clean zero boundary
-            E[r] = NEGI;
-            f = NEGI;
+            hd = hl;
+            H[r] = hnew;
+            hu = hnew;
           }
-          hd = hl;
-          od = ol;
-          H[r] = hnew;
-          oH[r] = onew;
-          hu = hnew;
-          ou = onew;
+          diagO = kOriginLeft;
+          outOH = kOriginLeft;
+          outOF = kOriginLeft;
+        } else {
+          if (!prevMode) {  // entering an origin block: everything alive comes from the left
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              oH[r] = kOriginLeft;
+              oE[r] = kOriginLeft;
+            }
+          }
+          uint32_t od = diagO, ou = inOH, of = inOF;
+          diagO = inOH;
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            int hl = H[r];
+            uint32_t ol = oH[r];
+            int hnew = 0;
+            uint32_t onew = 0;
+            if (active && srow[r] >= 0) {
+              int e_ext = E[r] + a.ins_ext, e_open = hl + a.gap_init;
+              if (e_ext >= e_open) {
+                E[r] = e_ext;
+              } else {
+                E[r] = e_open;
+                oE[r] = ol;
+              }
+              int f_ext = f + a.del_ext, f_open = hu + a.gap_init;
+              if (f_ext >= f_open) {
+                f = f_ext;
+              } else {
+                f = f_open;
+                of = ou;
+              }
+              int s = smat[srow[r] + curQ];
+              int d = hd + s;
+              uint32_t odd = hd > 0 ? od : ((uint32_t)i1 * Lp1 + (uint32_t)(row0 + r + 1));
+              hnew = E[r];
+              onew = oE[r];
+              bool viaDiag = false;
+              if (f > hnew) {
+                hnew = f;
+                onew = of;
+              }
+              if (d > hnew) {
+                hnew = d;
+                onew = odd;
+                viaDiag = true;
+              }
+              if (hnew <= 0) {
+                hnew = 0;
+                onew = 0;
+                viaDiag = false;
+              }
+              if (viaDiag && hnew >= a.minscore) {
+                if (onew == kOriginLeft) {
+                  needFull = true;
+                } else {
+                  // per-thread cache: one table update per (origin, lane crossing) instead of one per cell
+                  const unsigned long long val = cand_val(hnew, i1, row0 + r + 1);
+                  if (onew == lastOrigin) {
+                    lastVal = val > lastVal ? val : lastVal;
+                  } else {
+                    if (lastOrigin != kOriginLeft) origin_emit(a, ti, lastOrigin, lastVal);
+                    lastOrigin = onew;
+                    lastVal = val;
+                  }
+                }
+              }
+            } else {
+              // outside the matrix: keep a clean zero boundary
+              E[r] = NEGI;
+              f = NEGI;
+            }
+            hd = hl;
+            od = ol;
+            H[r] = hnew;
+            oH[r] = onew;
+            hu = hnew;
+            ou = onew;
+          }
+          outOH = ou;
+          outOF = of;
         }
+        prevMode = mode;
         outH = hu;
         outF = f;
-        outOH = ou;
-        outOF = of;
         if (hasNext) {
           int oh = __shfl_sync(0xffffffffu, outH, 31);
           int of2 = __shfl_sync(0xffffffffu, outF, 31);
@@ -653,8 +759,17 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
         }
       }
     }
+    if (lastOrigin != kOriginLeft) origin_emit(a, ti, lastOrigin, lastVal);
+    if (__any_sync(0xffffffffu, needFull) && lane == 0) atomicExch(&a.leftFlag[ti], 1);
     __syncwarp();
-    if (lane == 0) st_release(&a.finished[t], 1);
+    if (lane == 0) {
+      st_release(&a.finished[t], 1);
+      if (a.dbg) {
+        atomicAdd(&a.dbg[1], (unsigned long long)k2wait);
+        atomicAdd(&a.dbg[2], 1ull);
+        atomicAdd(&a.dbg[3], (unsigned long long)(clock64() - k2t0));
+      }
+    }
   }
 }
 

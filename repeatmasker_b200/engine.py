@@ -39,7 +39,8 @@ class Stats(C.Structure):
                 ("ms_score", C.c_double), ("ms_origin", C.c_double), ("ms_traceback", C.c_double),
                 ("ms_host_post", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("launches", C.c_int32), ("score_launches", C.c_int32), ("n_pairs_passed", C.c_int32),
-                ("n_candidates", C.c_int32), ("origin_cells", C.c_double)]
+                ("n_candidates", C.c_int32), ("origin_cells", C.c_double), ("n_origin_redo", C.c_int32),
+                ("pad_", C.c_int32)]
 
 
 class Result(C.Structure):
