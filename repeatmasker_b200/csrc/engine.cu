@@ -12,7 +12,9 @@
 #include <memory>
 #include <numeric>
 #include <set>
+#include <exception>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rmgpu.h"
@@ -146,7 +148,19 @@ struct rmgpu_session {
   DevBuf<int32_t> d_hotShift;
   DevBuf<unsigned long long> d_dbg;
   DevBuf<int> d_abort, d_leftFlag;
+  // second stream + scratch of the stripe-pipeline fallback, which runs concurrently with the block-parallel path
+  cudaStream_t stream2 = nullptr;
+  DevBuf<OriginTask> d_tasksC;
+  DevBuf<int32_t> d_ticketTaskC;
+  DevBuf<OriginBoundary> d_bndC;
+  DevBuf<int> d_progressC, d_finishedC, d_ticketC, d_overflowC, d_abortC, d_leftFlagC;
+  DevBuf<unsigned long long> d_keysC, d_valsC;
+  DevBuf<BlockTask> d_btasks;
+  DevBuf<uint32_t> d_snap;
+  DevBuf<unsigned long long> d_fkeys, d_fvals;
+  int32_t h_mat[16][16];
   void check_abort(const char* what);
+  void check_abort_on(const char* what, int* flag, cudaStream_t st);
   std::vector<int32_t> h_hotShift;
   DevBuf<OriginBoundary> d_bnd2;
   DevBuf<int> d_progress, d_finished, d_ticket, d_overflow;
@@ -431,10 +445,12 @@ void rmgpu_session::build_order(int nQ, int warps) {
   orderForNQ = nQ;
 }
 
-void rmgpu_session::check_abort(const char* what) {
+void rmgpu_session::check_abort(const char* what) { check_abort_on(what, d_abort.p, stream); }
+
+void rmgpu_session::check_abort_on(const char* what, int* flag, cudaStream_t stq) {
   int f = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&f, d_abort.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  CUDA_CHECK(cudaStreamSynchronize(stream));
+  CUDA_CHECK(cudaMemcpyAsync(&f, flag, sizeof(int), cudaMemcpyDeviceToHost, stq));
+  CUDA_CHECK(cudaStreamSynchronize(stq));
   if (f) throw Error(std::string(what) + ": stripe pipeline watchdog fired (a producer/consumer wait exceeded its bound)");
 }
 
@@ -527,9 +543,12 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   }
 }
 
-// K2 over every (query, strand, subject) whose K1 best reached minscore.  Only the column blocks K1 marked hot
-// (dilated by one block each side) are swept with origin propagation; a task whose hits turn out to need origins
-// from outside those blocks is flagged by the kernel and redone with every block in origin mode.
+// K2 over every (query, strand, subject) triple whose K1 best reached minscore.
+//   common path  (run_blocks): one task per hot column block, started from K1's column checkpoint, all blocks in
+//                parallel, pseudo origins resolved through per-block snapshots (swg_origin_block_kernel);
+//   fallback     (run_chain):  one sweep from column 0 with the stripe pipeline (swg_origin_kernel) for triples whose
+//                K1 values wrapped (int16), that are too large for the 31-bit relative origin, or when checkpoints
+//                are disabled.
 void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest,
                                const std::vector<unsigned long long>& hotmask, std::vector<Candidate>& cands,
                                rmgpu_stats& st) {
@@ -537,24 +556,10 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   static const bool fullMode = getenv("RMGPU_K2_FULL") != nullptr;
   struct Triple {
     int q, strand, subject;
+    unsigned long long dil;
+    bool chain;
   };
   std::vector<Triple> triples;
-  std::vector<OriginTask> tasks;
-  std::vector<int> taskTriple;
-  auto full_task = [&](int q, int strand, int s, unsigned long long mode) {
-    OriginTask t;
-    memset(&t, 0, sizeof(t));
-    t.q = q;
-    t.strand = strand;
-    t.subject = s;
-    t.nStripes = (int)((lib.seqs[s].size() + kR2 * 32 - 1) / (kR2 * 32));
-    t.mode = mode;
-    t.hotShift = h_hotShift[q];
-    t.c0 = 0;
-    t.c1 = h_qlen[q];
-    t.ckOff = -1;
-    return t;
-  };
   for (int q = 0; q < nQ; q++)
     for (int s = 0; s < nS; s++)
       for (int strand = 0; strand < 2; strand++) {
@@ -564,185 +569,377 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         if ((Q + 1) * (L + 1) >= (1ll << 32))
           throw Error("query x subject too large for one origin pass (" + queries.names[q] + " x " + lib.names[s] +
                       "): fragment the query as SimpleBatcher does");
-        const int tr = (int)triples.size();
-        triples.push_back({q, strand, s});
         const unsigned long long m = hotmask[idx];
-        const unsigned long long dil = m | (m << 1) | (m >> 1);
-        const bool overflowed = pairbest[idx] >= 32000;
-        if (overflowed || fullMode || dil == 0) {
-          tasks.push_back(full_task(q, strand, s, ~0ull));
-          taskTriple.push_back(tr);
-          st.origin_cells += (double)Q * (double)L;
-        } else if (!ckEnabled) {
-          tasks.push_back(full_task(q, strand, s, dil));
-          taskTriple.push_back(tr);
-          st.origin_cells += (double)Q * (double)L;
-        } else {
-          // one task per run of hot column blocks, started from K1's checkpoint before the run
-          const int64_t CB = 32ll << h_hotShift[q];
-          for (int c = 0; c < 64;) {
-            if (!((dil >> c) & 1ull)) {
-              c++;
-              continue;
-            }
-            int e = c;
-            while (e + 1 < 64 && ((dil >> (e + 1)) & 1ull)) e++;
-            OriginTask t = full_task(q, strand, s, ~0ull);
-            t.c0 = (int)std::min<int64_t>(Q, c * CB);
-            t.c1 = (e == 63) ? (int)Q : (int)std::min<int64_t>(Q, (e + 1) * CB);
-            if (t.c0 > 0) t.ckOff = ((int64_t)q * 64 + c) * ((int64_t)nGroups * R) + (int64_t)h_subjFirstGroup[s] * R;
-            if (t.c1 > t.c0) {
-              tasks.push_back(t);
-              taskTriple.push_back(tr);
-              st.origin_cells += (double)(t.c1 - t.c0) * (double)L;
-            }
-            c = e + 1;
-          }
-        }
+        Triple t;
+        t.q = q;
+        t.strand = strand;
+        t.subject = s;
+        t.dil = m | (m << 1) | (m >> 1);
+        const int64_t CB = 32ll << h_hotShift[q];
+        // checkpoints are exact only when K1 is (no merged residue class, no int16 wrap)
+        t.chain = pairbest[idx] >= 32000 || fullMode || !ckEnabled || !classesExact || t.dil == 0 ||
+                  (CB + 2) * (L + 1) >= (1ll << 31);
+        triples.push_back(t);
       }
   st.n_pairs_passed = (int)triples.size();
   cands.clear();
-  if (tasks.empty()) return;
-  int blocksPerSM = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_origin_kernel, 128, 0));
-  if (blocksPerSM < 1) throw Error("K2 does not fit on an SM");
-  blocksPerSM = std::min(blocksPerSM, 4);
-  const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
-  std::vector<char> tripleRedo(triples.size(), 0);
+  if (triples.empty()) return;
   std::vector<std::pair<int, Candidate>> found;  // (triple, candidate)
-  for (int round = 0; round < 2 && !tasks.empty(); round++) {
+  auto decode_val = [](unsigned long long v, Candidate& c) {
+    c.raw = (int)(v >> 40);
+    c.i1 = (int)(0xFFFFFu - (uint32_t)((v >> 20) & 0xFFFFFu));
+    c.j1 = (int)(0xFFFFFu - (uint32_t)(v & 0xFFFFFu));
+  };
+  for (int i = 0; i < 16; i++)
+    for (int j = 0; j < 16; j++) h_mat[i][j] = (i < matrix.n && j < matrix.n) ? matrix.score[i][j] : -128;
+
+  int chainCtas = 0;  // CTAs the concurrent fallback sweep needs resident
+  // ------------------------------------------------------------------ block-parallel path
+  auto run_blocks = [&](const std::vector<int>& trIdx, bool allBlocks, std::vector<int>& redoOut) {
+    std::vector<BlockTask> tasks;
+    int64_t snapTot = 0;
+    for (int tr : trIdx) {
+      const Triple& T = triples[tr];
+      const int64_t Q = h_qlen[T.q], L = (int64_t)lib.seqs[T.subject].size();
+      const int64_t CB = 32ll << h_hotShift[T.q];
+      const int nblk = (int)((Q + CB - 1) / CB);
+      int prev = -1;
+      for (int c = 0; c < nblk && c < 64; c++) {
+        // bit 63 stands for every block >= 63
+        const bool on = allBlocks || ((T.dil >> std::min(c, 63)) & 1ull);
+        if (!on) {
+          prev = -1;
+          continue;
+        }
+        BlockTask t;
+        memset(&t, 0, sizeof(t));
+        t.q = T.q;
+        t.strand = T.strand;
+        t.subject = T.subject;
+        t.triple = tr;
+        t.c0 = (int)(c * CB);
+        t.c1 = (c == 63) ? (int)Q : (int)std::min<int64_t>(Q, (c + 1) * CB);
+        t.prevTask = prev;
+        t.ckOff = c > 0 ? ((int64_t)T.q * 64 + c) * ((int64_t)nGroups * R) + (int64_t)h_subjFirstGroup[T.subject] * R : -1;
+        t.snapOff = snapTot;
+        snapTot += 2 * L;
+        prev = (int)tasks.size();
+        tasks.push_back(t);
+        st.origin_cells += (double)(t.c1 - t.c0) * (double)L;
+      }
+    }
+    if (tasks.empty()) return;
+    // longest subjects first (one warp sweeps a whole task): remap prevTask through the permutation
+    std::vector<int> perm(tasks.size()), inv(tasks.size());
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) {
+      return lib.seqs[tasks[x].subject].size() > lib.seqs[tasks[y].subject].size();
+    });
+    for (size_t i = 0; i < perm.size(); i++) inv[perm[i]] = (int)i;
+    std::vector<BlockTask> sorted(tasks.size());
+    for (size_t i = 0; i < perm.size(); i++) {
+      sorted[i] = tasks[perm[i]];
+      if (sorted[i].prevTask >= 0) sorted[i].prevTask = inv[sorted[i].prevTask];
+    }
+    tasks.swap(sorted);
     std::vector<int32_t> ticketTask;
     for (size_t i = 0; i < tasks.size(); i++) {
+      tasks[i].nStripes = (int)((lib.seqs[tasks[i].subject].size() + kR2 * 32 - 1) / (kR2 * 32));
       tasks[i].firstTicket = (int)ticketTask.size();
       for (int k = 0; k < tasks[i].nStripes; k++) ticketTask.push_back((int32_t)i);
     }
     const int nTickets = (int)ticketTask.size();
-    int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, ((int64_t)nTickets + 3) / 4);
+    int blocksPerSM = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_origin_block_kernel, 128, 0));
+    if (blocksPerSM < 1) throw Error("K2b does not fit on an SM");
+    // leave room for the CTAs of the concurrent fallback sweep (persistent grids: what is not resident cannot start)
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)numSMs * blocksPerSM - chainCtas, ((int64_t)nTickets + 3) / 4));
     const int warps = grid * 4;
     const int nslot = std::min(nTickets, 2 * warps + 2);
-    std::vector<int> leftFlag(tasks.size(), 0);
-    size_t tableSize = 1u << 18;
+    int64_t maxW = 0;
+    for (auto& t : tasks) maxW = std::max<int64_t>(maxW, t.c1 - t.c0);
+    const int64_t bndStride = ((maxW + 31) >> 5) * 32 + 32;
+    size_t tableSize = 1u << 20;
     for (;;) {
-      OriginArgs a;
-      d_tasks.upload(tasks, stream);
+      BlockArgs a;
+      d_btasks.upload(tasks, stream);
       d_ticketTask.upload(ticketTask, stream);
-      a.tasks = d_tasks.p;
+      a.tasks = d_btasks.p;
       a.ticketTask = d_ticketTask.p;
       a.nTickets = nTickets;
       a.codes_fwd = d_codes_fwd.p;
       a.codes_rc = d_codes_rc.p;
       a.qoff = d_qoff.p;
-      a.qlen = d_qlen.p;
       a.scodes = d_scodes.p;
       a.soff = d_soff.p;
       a.slen = d_slen.p;
-      for (int i = 0; i < 16; i++)
-        for (int j = 0; j < 16; j++) a.mat[i][j] = (i < matrix.n && j < matrix.n) ? matrix.score[i][j] : -128;
+      memcpy(a.mat, h_mat, sizeof(h_mat));
       a.gap_init = p.gap_init;
       a.ins_ext = p.ins_gap_ext;
       a.del_ext = p.del_gap_ext;
       a.minscore = p.minscore;
+      a.ck = d_ck.p;
       a.bnd = d_bnd2.ensure((size_t)nslot * bndStride);
       a.bndStride = bndStride;
       a.nslot = nslot;
       a.progress = d_progress.ensure((size_t)nTickets);
       a.finished = d_finished.ensure((size_t)nTickets);
+      a.abort_flag = d_abort.ensure(1);
+      a.snap = d_snap.ensure((size_t)std::max<int64_t>(snapTot, 1));
       a.ticket = d_ticket.ensure(1);
       a.keys = d_keys.ensure(tableSize);
       a.vals = d_vals.ensure(tableSize);
       a.tableMask = (uint32_t)tableSize - 1;
       a.overflow = d_overflow.ensure(1);
-      a.abort_flag = d_abort.ensure(1);
-      static const bool dbgOn2 = getenv("RMGPU_DEBUG_K2") != nullptr;
-      a.dbg = nullptr;
-      if (dbgOn2) {
-        a.dbg = d_dbg.ensure(4);
-        CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 32, stream));
-      }
-      a.ck = d_ck.p;
-      a.leftFlag = d_leftFlag.ensure(tasks.size());
       CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream));
-      CUDA_CHECK(cudaMemsetAsync(a.leftFlag, 0, tasks.size() * sizeof(int), stream));
-      CUDA_CHECK(cudaMemsetAsync(a.keys, 0xFF, tableSize * 8, stream));
-      CUDA_CHECK(cudaMemsetAsync(a.vals, 0, tableSize * 8, stream));
       CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream));
       CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream));
+      CUDA_CHECK(cudaMemsetAsync(a.keys, 0xFF, tableSize * 8, stream));
+      CUDA_CHECK(cudaMemsetAsync(a.vals, 0, tableSize * 8, stream));
       CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), stream));
       CUDA_CHECK(cudaMemsetAsync(a.overflow, 0, sizeof(int), stream));
+      ResolveArgs r;
+      r.tasks = d_btasks.p;
+      r.slen = d_slen.p;
+      r.snap = a.snap;
+      r.keys = a.keys;
+      r.vals = a.vals;
+      r.tableSize = (uint32_t)tableSize;
+      r.fkeys = d_fkeys.ensure(tableSize);
+      r.fvals = d_fvals.ensure(tableSize);
+      r.fmask = (uint32_t)tableSize - 1;
+      r.overflow = a.overflow;
+      r.redo = d_leftFlag.ensure(triples.size());
+      r.verbose = allBlocks ? 1 : 0;
+      CUDA_CHECK(cudaMemsetAsync(r.fkeys, 0xFF, tableSize * 8, stream));
+      CUDA_CHECK(cudaMemsetAsync(r.fvals, 0, tableSize * 8, stream));
+      CUDA_CHECK(cudaMemsetAsync(r.redo, 0, triples.size() * sizeof(int), stream));
       EventTimer tm;
       tm.start(stream);
-      swg_origin_kernel<<<grid, 128, 0, stream>>>(a);
+      swg_origin_block_kernel<<<grid, 128, 0, stream>>>(a);
+      resolve_candidates_kernel<<<numSMs * 2, 256, 0, stream>>>(r);
       tm.stop(stream);
       CUDA_CHECK(cudaGetLastError());
-      std::vector<unsigned long long> keys(tableSize), vals(tableSize);
       int overflow = 0;
+      std::vector<int> redoFlag(triples.size(), 0);
+      std::vector<unsigned long long> keys(tableSize), vals(tableSize);
       CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaMemcpyAsync(leftFlag.data(), a.leftFlag, tasks.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaMemcpyAsync(keys.data(), a.keys, tableSize * 8, cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaMemcpyAsync(vals.data(), a.vals, tableSize * 8, cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaMemcpyAsync(redoFlag.data(), r.redo, triples.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaMemcpyAsync(keys.data(), r.fkeys, tableSize * 8, cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaMemcpyAsync(vals.data(), r.fvals, tableSize * 8, cudaMemcpyDeviceToHost, stream));
       CUDA_CHECK(cudaStreamSynchronize(stream));
-      check_abort("K2");
-      if (dbgOn2) {
-        unsigned long long d[4];
-        CUDA_CHECK(cudaMemcpy(d, a.dbg, 32, cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[K2 dbg] %.2f ms tasks %zu tickets %llu grid %d: guard-wait %.1f%% producer-wait %.1f%% of ticket cycles, mean ticket %.0f cyc\n", tm.ms(),
-                tasks.size(), d[2], grid, 100.0 * d[0] / std::max(d[3], 1ull), 100.0 * d[1] / std::max(d[3], 1ull), (double)d[3] / std::max(d[2], 1ull));
-      }
-      st.ms_origin += tm.ms();
-      st.launches += 1;
+      check_abort("K2b");
+      (void)tm;
+      st.launches += 2;
       st.d2h_bytes += (int64_t)tableSize * 16;
-      size_t used = 0;
-      for (size_t i = 0; i < tableSize; i++) used += keys[i] != kEmptyKey;
-      if (overflow || used * 2 > tableSize) {  // keep the table sparse; rerun bigger
+      if (overflow) {
         tableSize *= 4;
         if (tableSize > (1u << 28)) throw Error("candidate table overflow");
-        if (overflow) continue;
+        continue;
       }
-      for (size_t i = 0; i < tasks.size(); i++)
-        if (leftFlag[i]) {
-          if (round > 0) throw Error("origin pass: a fully swept task still reports a left origin");
-          tripleRedo[taskTriple[i]] = 1;
+      for (size_t tr = 0; tr < triples.size(); tr++)
+        if (redoFlag[tr]) {
+          if (allBlocks) throw Error("origin pass: a pseudo origin could not be resolved with every block swept");
+          redoOut.push_back((int)tr);
         }
       for (size_t i = 0; i < keys.size(); i++) {
         if (keys[i] == kEmptyKey) continue;
-        int ti = (int)(keys[i] >> 32);
-        uint32_t origin = (uint32_t)keys[i];
-        const OriginTask& t = tasks[ti];
+        const int tr = (int)(keys[i] >> 40);
+        if (redoFlag[tr]) continue;
         Candidate c;
-        c.q = t.q;
-        c.strand = t.strand;
-        c.subject = t.subject;
-        const uint32_t Lp1 = (uint32_t)lib.seqs[t.subject].size() + 1u;
-        c.i0 = (int)(origin / Lp1);
-        c.j0 = (int)(origin % Lp1);
-        c.raw = (int)(vals[i] >> 40);
-        c.i1 = (int)(0xFFFFFu - (uint32_t)((vals[i] >> 20) & 0xFFFFFu));
-        c.j1 = (int)(0xFFFFFu - (uint32_t)(vals[i] & 0xFFFFFu));
-        found.push_back({taskTriple[ti], c});
+        c.q = triples[tr].q;
+        c.strand = triples[tr].strand;
+        c.subject = triples[tr].subject;
+        c.i0 = (int)((keys[i] >> 20) & 0xFFFFFu);
+        c.j0 = (int)(keys[i] & 0xFFFFFu);
+        decode_val(vals[i], c);
+        found.push_back({tr, c});
       }
       break;
     }
-    // triples whose hits need origins from outside their windows are redone with one full sweep
-    std::vector<OriginTask> redo;
-    std::vector<int> redoTriple;
-    if (round == 0) {
-      for (size_t tr = 0; tr < triples.size(); tr++)
-        if (tripleRedo[tr]) {
-          redo.push_back(full_task(triples[tr].q, triples[tr].strand, triples[tr].subject, ~0ull));
-          redoTriple.push_back((int)tr);
-          st.origin_cells += (double)h_qlen[triples[tr].q] * (double)lib.seqs[triples[tr].subject].size();
-        }
-      // drop what the windowed tasks of those triples found: the full sweep finds all of it again
-      std::vector<std::pair<int, Candidate>> keep;
-      for (auto& f : found)
-        if (!tripleRedo[f.first]) keep.push_back(f);
-      found.swap(keep);
+  };
+
+  // ------------------------------------------------------------------ stripe-pipeline path (full sweeps)
+  std::vector<std::pair<int, Candidate>> foundChain;
+  double chainMs = 0, chainCells = 0;
+  int chainLaunches = 0, chainRedo = 0;
+  int64_t chainD2H = 0;
+  auto run_chain = [&](const std::vector<int>& trIdx) {
+    if (trIdx.empty()) return;
+    std::vector<OriginTask> tasks;
+    std::vector<int32_t> ticketTask;
+    for (int tr : trIdx) {
+      const Triple& T = triples[tr];
+      OriginTask t;
+      memset(&t, 0, sizeof(t));
+      t.q = T.q;
+      t.strand = T.strand;
+      t.subject = T.subject;
+      t.nStripes = (int)((lib.seqs[T.subject].size() + kR2 * 32 - 1) / (kR2 * 32));
+      // without checkpoints the cold column blocks are swept score-only; after an int16 wrap the mask is unreliable
+      const size_t idx = ((size_t)T.q * nS + T.subject) * 2 + T.strand;
+      // after an int16 wrap K1 under-reports the blocks that follow (true scores decay by only ~5-6 per column along
+      // a gap), so the mask is stretched 8 blocks forward; a cell >= minscore met in a score-only block still forces
+      // a full redo of the task, so exactness never depends on this guess
+      unsigned long long fwd = T.dil;
+      if (pairbest[idx] >= 32000)
+        for (int k = 1; k <= 8; k++) fwd |= T.dil << k;
+      t.mode = (fullMode || T.dil == 0) ? ~0ull : fwd;
+      t.hotShift = h_hotShift[T.q];
+      t.c0 = 0;
+      t.c1 = h_qlen[T.q];
+      t.ckOff = -1;
+      t.firstTicket = (int)ticketTask.size();
+      for (int k = 0; k < t.nStripes; k++) ticketTask.push_back((int32_t)tasks.size());
+      tasks.push_back(t);
+      chainCells += (double)h_qlen[T.q] * (double)lib.seqs[T.subject].size();
     }
-    st.n_origin_redo += (int)redo.size();
-    tasks.swap(redo);
-    taskTriple.swap(redoTriple);
+    int blocksPerSM = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_origin_kernel, 128, 0));
+    if (blocksPerSM < 1) throw Error("K2 does not fit on an SM");
+    blocksPerSM = std::min(blocksPerSM, 4);
+    const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
+    const int nTickets = (int)ticketTask.size();
+    const int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, ((int64_t)nTickets + 3) / 4);
+    const int warps = grid * 4;
+    const int nslot = std::min(nTickets, 2 * warps + 2);
+    for (int round = 0; round < 2; round++) {
+      std::vector<int> leftFlag(tasks.size(), 0);
+      size_t tableSize = 1u << 18;
+      for (;;) {
+        OriginArgs a;
+        d_tasksC.upload(tasks, stream2);
+        d_ticketTaskC.upload(ticketTask, stream2);
+        a.tasks = d_tasksC.p;
+        a.ticketTask = d_ticketTaskC.p;
+        a.nTickets = nTickets;
+        a.codes_fwd = d_codes_fwd.p;
+        a.codes_rc = d_codes_rc.p;
+        a.qoff = d_qoff.p;
+        a.qlen = d_qlen.p;
+        a.scodes = d_scodes.p;
+        a.soff = d_soff.p;
+        a.slen = d_slen.p;
+        memcpy(a.mat, h_mat, sizeof(h_mat));
+        a.gap_init = p.gap_init;
+        a.ins_ext = p.ins_gap_ext;
+        a.del_ext = p.del_gap_ext;
+        a.minscore = p.minscore;
+        a.bnd = d_bndC.ensure((size_t)nslot * bndStride);
+        a.bndStride = bndStride;
+        a.nslot = nslot;
+        a.progress = d_progressC.ensure((size_t)nTickets);
+        a.finished = d_finishedC.ensure((size_t)nTickets);
+        a.ticket = d_ticketC.ensure(1);
+        a.keys = d_keysC.ensure(tableSize);
+        a.vals = d_valsC.ensure(tableSize);
+        a.tableMask = (uint32_t)tableSize - 1;
+        a.overflow = d_overflowC.ensure(1);
+        a.abort_flag = d_abortC.ensure(1);
+        a.dbg = nullptr;
+        a.ck = d_ck.p;
+        a.leftFlag = d_leftFlagC.ensure(tasks.size());
+        CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream2));
+        CUDA_CHECK(cudaMemsetAsync(a.leftFlag, 0, tasks.size() * sizeof(int), stream2));
+        CUDA_CHECK(cudaMemsetAsync(a.keys, 0xFF, tableSize * 8, stream2));
+        CUDA_CHECK(cudaMemsetAsync(a.vals, 0, tableSize * 8, stream2));
+        CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream2));
+        CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream2));
+        CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), stream2));
+        CUDA_CHECK(cudaMemsetAsync(a.overflow, 0, sizeof(int), stream2));
+        EventTimer tm;
+        tm.start(stream2);
+        swg_origin_kernel<<<grid, 128, 0, stream2>>>(a);
+        tm.stop(stream2);
+        CUDA_CHECK(cudaGetLastError());
+        std::vector<unsigned long long> keys(tableSize), vals(tableSize);
+        int overflow = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream2));
+        CUDA_CHECK(cudaMemcpyAsync(leftFlag.data(), a.leftFlag, tasks.size() * sizeof(int), cudaMemcpyDeviceToHost, stream2));
+        CUDA_CHECK(cudaMemcpyAsync(keys.data(), a.keys, tableSize * 8, cudaMemcpyDeviceToHost, stream2));
+        CUDA_CHECK(cudaMemcpyAsync(vals.data(), a.vals, tableSize * 8, cudaMemcpyDeviceToHost, stream2));
+        CUDA_CHECK(cudaStreamSynchronize(stream2));
+        check_abort_on("K2", a.abort_flag, stream2);
+        chainMs += tm.ms();
+        chainLaunches += 1;
+        chainD2H += (int64_t)tableSize * 16;
+        if (overflow) {
+          tableSize *= 4;
+          if (tableSize > (1u << 28)) throw Error("candidate table overflow");
+          continue;
+        }
+        for (size_t i = 0; i < keys.size(); i++) {
+          if (keys[i] == kEmptyKey) continue;
+          const int ti = (int)(keys[i] >> 32);
+          if (leftFlag[ti]) continue;
+          const uint32_t origin = (uint32_t)keys[i];
+          const OriginTask& t = tasks[ti];
+          Candidate c;
+          c.q = t.q;
+          c.strand = t.strand;
+          c.subject = t.subject;
+          const uint32_t Lp1 = (uint32_t)lib.seqs[t.subject].size() + 1u;
+          c.i0 = (int)(origin / Lp1);
+          c.j0 = (int)(origin % Lp1);
+          decode_val(vals[i], c);
+          foundChain.push_back({trIdx[ti], c});
+        }
+        break;
+      }
+      // tasks that met a hit needing origins from a score-only region: once more with origins everywhere
+      bool any = false;
+      for (size_t i = 0; i < tasks.size(); i++) {
+        if (leftFlag[i]) {
+          if (tasks[i].mode == ~0ull) throw Error("origin pass: a fully swept task still reports a left origin");
+          tasks[i].mode = ~0ull;
+          any = true;
+          chainRedo++;
+        } else {
+          tasks[i].mode = 0;  // done: nothing to sweep with origins, and nothing >= minscore can appear
+          tasks[i].c1 = 0;    // (an empty window makes the ticket a no-op)
+        }
+      }
+      if (!any) break;
+    }
+  };
+
+  std::vector<int> blockTr, chainTr, redo;
+  for (size_t i = 0; i < triples.size(); i++) (triples[i].chain ? chainTr : blockTr).push_back((int)i);
+  for (int tr : chainTr) chainCtas += (int)((lib.seqs[triples[tr].subject].size() + kR2 * 32 - 1) / (kR2 * 32));
+  chainCtas = std::min((chainCtas + 3) / 4, numSMs);
+  // the fallback sweeps are long and narrow (a few warps busy for tens of ms): run them on a second stream from a
+  // second host thread while the block-parallel path fills the machine
+  const double k2t0 = now_ms();
+  std::exception_ptr chainErr;
+  std::thread chainThread([&] {
+    try {
+      if (cudaSetDevice(device) != cudaSuccess) throw Error("cudaSetDevice failed in the K2 fallback thread");
+      run_chain(chainTr);
+    } catch (...) {
+      chainErr = std::current_exception();
+    }
+  });
+  std::exception_ptr blockErr;
+  try {
+    run_blocks(blockTr, false, redo);
+    if (!redo.empty()) {
+      st.n_origin_redo += (int)redo.size();
+      std::vector<int> none;
+      run_blocks(redo, true, none);
+    }
+  } catch (...) {
+    blockErr = std::current_exception();
   }
-  // an alignment that crosses two windows of one triple is seen by both with the same origin: keep the better end
+  chainThread.join();
+  if (blockErr) std::rethrow_exception(blockErr);
+  if (chainErr) std::rethrow_exception(chainErr);
+  found.insert(found.end(), foundChain.begin(), foundChain.end());
+  st.launches += chainLaunches;
+  st.d2h_bytes += chainD2H;
+  st.n_origin_redo += chainRedo;
+  st.origin_cells += chainCells;
+  st.ms_origin = now_ms() - k2t0;  // both paths overlap: wall time of the origin pass (kernels, table downloads, host merge)
+  // one candidate per (triple, origin)
   std::sort(found.begin(), found.end(), [](const std::pair<int, Candidate>& x, const std::pair<int, Candidate>& y) {
     if (x.first != y.first) return x.first < y.first;
     if (x.second.i0 != y.second.i0) return x.second.i0 < y.second.i0;
@@ -1153,6 +1350,11 @@ rmgpu_session* rmgpu_session_open(int device) {
     s->device = device;
     s->numSMs = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    {
+      int lo = 0, hi = 0;
+      CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_CHECK(cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, hi));
+    }
   });
   if (rc) {
     delete s;
@@ -1165,6 +1367,7 @@ void rmgpu_session_close(rmgpu_session* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->stream2) cudaStreamDestroy(s->stream2);
   delete s;
 }
 

@@ -507,6 +507,47 @@ __device__ __forceinline__ void origin_emit(const OriginArgs& a, int task, uint3
   atomicExch(a.overflow, 1);
 }
 
+// One origin-propagating cell, branch-free (the tie-breaks of DESIGN.md section 3: E over F over diagonal, extension over
+// opening).  valid = the cell exists (query column and subject row inside the matrix).
+struct OriginCell {
+  int h;
+  uint32_t o;
+  bool viaDiag;
+};
+__device__ __forceinline__ OriginCell origin_cell(bool valid, int hl, uint32_t ol, int hu, uint32_t ou, int hd, uint32_t od,
+                                                  int s, uint32_t fresh, int& E, uint32_t& oE, int& f, uint32_t& of,
+                                                  int gap_init, int ins_ext, int del_ext) {
+  const int NEGI = -(1 << 28);
+  const int e_ext = E + ins_ext, e_open = hl + gap_init;
+  const bool eOpen = e_open > e_ext;
+  int e = max(e_ext, e_open);
+  uint32_t oe = eOpen ? ol : oE;
+  const int f_ext = f + del_ext, f_open = hu + gap_init;
+  const bool fOpen = f_open > f_ext;
+  int ff = max(f_ext, f_open);
+  uint32_t off = fOpen ? ou : of;
+  const int d = hd + s;
+  const uint32_t odd = hd > 0 ? od : fresh;
+  int h = e;
+  uint32_t o = oe;
+  const bool c1 = ff > h;
+  h = max(h, ff);
+  o = c1 ? off : o;
+  const bool c2 = d > h;
+  h = max(h, d);
+  o = c2 ? odd : o;
+  const bool pos = valid && h > 0;
+  OriginCell r;
+  r.h = pos ? h : 0;
+  r.o = pos ? o : 0u;
+  r.viaDiag = c2 && pos;
+  E = valid ? e : NEGI;
+  oE = valid ? oe : oE;
+  f = valid ? ff : NEGI;
+  of = valid ? off : of;
+  return r;
+}
+
 // Column blocks that K1 saw reach minscore (dilated by one block on either side by the host) are swept with origin
 // propagation; all other columns with the plain int32 recurrence (same H/E/F values, about a quarter of the
 // instructions).  Entering an origin block, every live path gets the origin kOriginLeft; a candidate carrying it,
@@ -568,24 +609,6 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
     uint32_t lastOrigin = kOriginLeft;  // nothing cached
     unsigned long long lastVal = 0;
     bool prevMode = false, needFull = false;
-    if (tk.ckOff >= 0) {
-      // start from K1's exact column state before column c0; every live path gets the "left" origin
-      const uint2* ck = a.ck + tk.ckOff;
-      const int sh = tk.strand ? 16 : 0;
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        if (row0 + r < L) {
-          const uint2 v = ck[row0 + r];
-          H[r] = (int)((v.x >> sh) & 0xffffu);
-          E[r] = (int)((v.y >> sh) & 0xffffu) + a.gap_init;
-        }
-        oH[r] = kOriginLeft;
-        oE[r] = kOriginLeft;
-      }
-      if (row0 > 0 && row0 - 1 < L) diagH = (int)((ck[row0 - 1].x >> sh) & 0xffffu);
-      diagO = kOriginLeft;
-      prevMode = true;
-    }
     for (int b = 0; b < nBlocks; b++) {
       int col = b * 32 + lane;  // column offset inside the window
       int qv = (col < W) ? (int)qc[tk.c0 + col] : -1;
@@ -666,71 +689,33 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
           diagO = inOH;
 #pragma unroll
           for (int r = 0; r < R; r++) {
-            int hl = H[r];
-            uint32_t ol = oH[r];
-            int hnew = 0;
-            uint32_t onew = 0;
-            if (active && srow[r] >= 0) {
-              int e_ext = E[r] + a.ins_ext, e_open = hl + a.gap_init;
-              if (e_ext >= e_open) {
-                E[r] = e_ext;
+            const int hl = H[r];
+            const uint32_t ol = oH[r];
+            const bool valid = active && srow[r] >= 0;
+            const int sc_ = valid ? smat[srow[r] + curQ] : 0;
+            const OriginCell c = origin_cell(valid, hl, ol, hu, ou, hd, od, sc_, (uint32_t)i1 * Lp1 + (uint32_t)(row0 + r + 1),
+                                             E[r], oE[r], f, of, a.gap_init, a.ins_ext, a.del_ext);
+            if (c.viaDiag && c.h >= a.minscore) {
+              if (c.o == kOriginLeft) {
+                needFull = true;
               } else {
-                E[r] = e_open;
-                oE[r] = ol;
-              }
-              int f_ext = f + a.del_ext, f_open = hu + a.gap_init;
-              if (f_ext >= f_open) {
-                f = f_ext;
-              } else {
-                f = f_open;
-                of = ou;
-              }
-              int s = smat[srow[r] + curQ];
-              int d = hd + s;
-              uint32_t odd = hd > 0 ? od : ((uint32_t)i1 * Lp1 + (uint32_t)(row0 + r + 1));
-              hnew = E[r];
-              onew = oE[r];
-              bool viaDiag = false;
-              if (f > hnew) {
-                hnew = f;
-                onew = of;
-              }
-              if (d > hnew) {
-                hnew = d;
-                onew = odd;
-                viaDiag = true;
-              }
-              if (hnew <= 0) {
-                hnew = 0;
-                onew = 0;
-                viaDiag = false;
-              }
-              if (viaDiag && hnew >= a.minscore) {
-                if (onew == kOriginLeft) {
-                  needFull = true;
+                // per-thread cache: one table update per (origin, lane crossing) instead of one per cell
+                const unsigned long long val = cand_val(c.h, i1, row0 + r + 1);
+                if (c.o == lastOrigin) {
+                  lastVal = val > lastVal ? val : lastVal;
                 } else {
-                  // per-thread cache: one table update per (origin, lane crossing) instead of one per cell
-                  const unsigned long long val = cand_val(hnew, i1, row0 + r + 1);
-                  if (onew == lastOrigin) {
-                    lastVal = val > lastVal ? val : lastVal;
-                  } else {
-                    if (lastOrigin != kOriginLeft) origin_emit(a, ti, lastOrigin, lastVal);
-                    lastOrigin = onew;
-                    lastVal = val;
-                  }
+                  if (lastOrigin != kOriginLeft) origin_emit(a, ti, lastOrigin, lastVal);
+                  lastOrigin = c.o;
+                  lastVal = val;
                 }
               }
-            } else {
-              // outside the matrix: keep a clean zero boundary
-              E[r] = NEGI;
-              f = NEGI;
             }
             hd = hl;
             od = ol;
-            H[r] = hnew;
-            oH[r] = onew;
-            hu = hnew;
-            ou = onew;
+            H[r] = c.h;
+            oH[r] = c.o;
+            hu = c.h;
+            ou = c.o;
           }
           outOH = ou;
           outOF = of;
@@ -770,6 +755,302 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
         atomicAdd(&a.dbg[3], (unsigned long long)(clock64() - k2t0));
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2b: block-parallel origin pass (the common path).  A task = one (query, strand, subject) triple x one hot column
+// block [c0, c1) (CB columns, CB = the K1 checkpoint spacing).  Every task starts from K1's exact (H, E') column
+// checkpoint, so all blocks of a triple run in parallel and one warp does a whole task by itself, sweeping the
+// subject's 256-row stripes one after the other (the stripe boundary lives in a private scratch line; no inter-warp
+// pipeline, no flags).  Paths that are alive at the left edge carry a PSEUDO origin naming the boundary cell
+// (row, H-or-E state); each task snapshots the origins of its last column, and resolve_candidates_kernel follows
+// pseudo origins through those snapshots back to the real origin cell.  Origins are encoded relative to the task,
+// (i0 - c0) * (L + 1) + j0, which must stay below 2^31 (bit 31 marks pseudo origins).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kPseudoBit = 0x80000000u;
+constexpr uint32_t kPseudoEBit = 1u << 20;  // pseudo origin of the E state (else H) of boundary row (bits 0..19, 1-based)
+
+struct BlockTask {
+  int32_t q, strand, subject, triple;
+  int32_t c0, c1;     // query columns [c0, c1), 0-based
+  int32_t prevTask;   // task of the same triple covering [.., c0), or -1
+  int32_t firstTicket, nStripes;  // one ticket per 256-row stripe; the stripes of a task form a pipeline
+  int32_t pad_;
+  int64_t ckOff;      // subject's first row in the K1 checkpoint taken before column c0, or -1 (c0 == 0)
+  int64_t snapOff;    // this task's origin snapshot: snap[snapOff + row] = oH, snap[snapOff + L + row] = oE (0-based row)
+};
+
+struct BlockArgs {
+  const BlockTask* tasks;
+  const int32_t* ticketTask;   // [nTickets]
+  int nTickets;
+  const uint8_t* codes_fwd;
+  const uint8_t* codes_rc;
+  const int64_t* qoff;
+  const uint8_t* scodes;
+  const int64_t* soff;
+  const int32_t* slen;
+  int32_t mat[16][16];
+  int32_t gap_init, ins_ext, del_ext, minscore;
+  const uint2* ck;
+  OriginBoundary* bnd;         // [nslot * bndStride] stripe boundary ring (same protocol as swg_origin_kernel)
+  int64_t bndStride;
+  int nslot;
+  int* progress;
+  int* finished;
+  int* abort_flag;
+  uint32_t* snap;
+  int* ticket;
+  unsigned long long* keys;    // (task << 32 | task-relative or pseudo origin) -> best end
+  unsigned long long* vals;
+  uint32_t tableMask;
+  int* overflow;
+};
+
+__device__ __forceinline__ void table_emit(unsigned long long* keys, unsigned long long* vals, uint32_t mask, int* overflow,
+                                           unsigned long long key, unsigned long long val) {
+  uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+  for (uint32_t probe = 0; probe <= mask; probe++) {
+    unsigned long long old = atomicCAS(&keys[slot], kEmptyKey, key);
+    if (old == kEmptyKey || old == key) {
+      atomicMax(&vals[slot], val);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+  atomicExch(overflow, 1);
+}
+
+__global__ void __launch_bounds__(128) swg_origin_block_kernel(BlockArgs a) {
+  __shared__ int32_t smat[16 * 16];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  constexpr int R = kR2;
+  const int NEGI = -(1 << 28);
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= a.nTickets) break;
+    const int ti = a.ticketTask[t];
+    const BlockTask tk = a.tasks[ti];
+    const int st = t - tk.firstTicket;  // stripe of this ticket
+    const int L = a.slen[tk.subject];
+    const uint32_t Lp1 = (uint32_t)L + 1u;
+    const uint8_t* qc = (tk.strand ? a.codes_rc : a.codes_fwd) + a.qoff[tk.q];
+    const uint8_t* sc = a.scodes + a.soff[tk.subject];
+    const int W = tk.c1 - tk.c0;
+    const int qBlocks = (W + 31) >> 5, nBlocks = qBlocks + 1;
+    const int sh = tk.strand ? 16 : 0;
+    const bool hasPrev = st > 0, hasNext = st + 1 < tk.nStripes;
+    const OriginBoundary* bndIn = a.bnd + (int64_t)((t - 1 + a.nslot) % a.nslot) * a.bndStride;
+    OriginBoundary* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
+    if (hasNext) {
+      // the reader (ticket + 1) of the last ticket that wrote this ring slot must be done
+      for (int tOld = t - a.nslot; tOld >= 0; tOld -= a.nslot) {
+        const BlockTask& ot = a.tasks[a.ticketTask[tOld]];
+        if (tOld - ot.firstTicket + 1 >= ot.nStripes) continue;  // that ticket had no stripe below: it wrote nothing
+        if (lane == 0) wait_ge(&a.finished[tOld + 1], 1, a.abort_flag);
+        __syncwarp();
+        break;
+      }
+    }
+    uint32_t lastOrigin = 0xFFFFFFFFu;  // nothing cached
+    unsigned long long lastVal = 0;
+    const int row0 = (st * 32 + lane) * R;
+    int srow[R], H[R], E[R];
+    uint32_t oH[R], oE[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      srow[r] = (row0 + r < L) ? (int)sc[row0 + r] * 16 : -1;
+      H[r] = 0;
+      E[r] = NEGI;
+      oH[r] = 0;
+      oE[r] = 0;
+    }
+    int diagH = 0;
+    uint32_t diagO = 0;
+    if (tk.ckOff >= 0) {
+      const uint2* ck = a.ck + tk.ckOff;
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        if (row0 + r < L) {
+          const uint2 v = ck[row0 + r];
+          H[r] = (int)((v.x >> sh) & 0xffffu);
+          E[r] = (int)((v.y >> sh) & 0xffffu) + a.gap_init;
+          oH[r] = kPseudoBit | (uint32_t)(row0 + r + 1);
+          oE[r] = kPseudoBit | kPseudoEBit | (uint32_t)(row0 + r + 1);
+        }
+      if (row0 > 0 && row0 - 1 < L) {
+        diagH = (int)((ck[row0 - 1].x >> sh) & 0xffffu);
+        diagO = kPseudoBit | (uint32_t)row0;
+      }
+    }
+    int outH = 0, outF = NEGI, curQ = -1;
+    uint32_t outOH = 0, outOF = 0;
+    OriginBoundary wb = {0, NEGI, 0, 0};
+    for (int b = 0; b < nBlocks; b++) {
+      const int col = b * 32 + lane;
+      const int qv = (col < W) ? (int)qc[tk.c0 + col] : -1;
+      OriginBoundary bv = {0, NEGI, 0, 0};
+      if (hasPrev && b < qBlocks) {
+        if (lane == 0 && ld_acquire(&a.progress[t - 1]) < b + 1) wait_ge(&a.progress[t - 1], b + 1, a.abort_flag);
+        __syncwarp();
+        const int4 raw = __ldcg(reinterpret_cast<const int4*>(&bndIn[col]));
+        bv.h = raw.x;
+        bv.f = raw.y;
+        bv.oh = (uint32_t)raw.z;
+        bv.of = (uint32_t)raw.w;
+      }
+      for (int j = 0; j < 32; j++) {
+        int inQ = __shfl_up_sync(0xffffffffu, curQ, 1);
+        int inH = __shfl_up_sync(0xffffffffu, outH, 1);
+        int inF = __shfl_up_sync(0xffffffffu, outF, 1);
+        uint32_t inOH = __shfl_up_sync(0xffffffffu, outOH, 1);
+        uint32_t inOF = __shfl_up_sync(0xffffffffu, outOF, 1);
+        const int fq = __shfl_sync(0xffffffffu, qv, j);
+        const int fh = __shfl_sync(0xffffffffu, bv.h, j);
+        const int ff = __shfl_sync(0xffffffffu, bv.f, j);
+        const uint32_t foh = __shfl_sync(0xffffffffu, bv.oh, j);
+        const uint32_t fof = __shfl_sync(0xffffffffu, bv.of, j);
+        if (lane == 0) {
+          inQ = fq;
+          inH = fh;
+          inF = ff;
+          inOH = foh;
+          inOF = fof;
+        }
+        curQ = inQ;
+        const int cw = b * 32 + j - lane;  // column inside the block, 0-based
+        const int i1 = tk.c0 + cw + 1;     // 1-based query column
+        int hd = diagH, hu = inH, f = inF;
+        uint32_t od = diagO, ou = inOH, of = inOF;
+        const bool active = curQ >= 0;
+        if (cw >= 0) {  // before its first column a lane must keep the checkpointed state untouched
+          diagH = inH;
+          diagO = inOH;
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const int hl = H[r];
+            const uint32_t ol = oH[r];
+            const bool valid = active && srow[r] >= 0;
+            const int sc_ = valid ? smat[srow[r] + curQ] : 0;
+            const OriginCell c = origin_cell(valid, hl, ol, hu, ou, hd, od, sc_, (uint32_t)(cw + 1) * Lp1 + (uint32_t)(row0 + r + 1),
+                                             E[r], oE[r], f, of, a.gap_init, a.ins_ext, a.del_ext);
+            if (c.viaDiag && c.h >= a.minscore) {
+              const unsigned long long val = cand_val(c.h, i1, row0 + r + 1);
+              if (c.o == lastOrigin) {
+                lastVal = val > lastVal ? val : lastVal;
+              } else {
+                if (lastOrigin != 0xFFFFFFFFu)
+                  table_emit(a.keys, a.vals, a.tableMask, a.overflow, ((unsigned long long)(uint32_t)ti << 32) | lastOrigin, lastVal);
+                lastOrigin = c.o;
+                lastVal = val;
+              }
+            }
+            hd = hl;
+            od = ol;
+            H[r] = c.h;
+            oH[r] = c.o;
+            hu = c.h;
+            ou = c.o;
+          }
+        }
+        outH = hu;
+        outF = f;
+        outOH = ou;
+        outOF = of;
+        if (cw == W - 1) {  // last column of the block: snapshot the origins of (H, E) for the next block's tasks
+          uint32_t* sn = a.snap + tk.snapOff;
+#pragma unroll
+          for (int r = 0; r < R; r++)
+            if (row0 + r < L) {
+              sn[row0 + r] = oH[r];
+              sn[L + row0 + r] = oE[r];
+            }
+        }
+        if (hasNext) {
+          const int oh = __shfl_sync(0xffffffffu, outH, 31);
+          const int of2 = __shfl_sync(0xffffffffu, outF, 31);
+          const uint32_t ooh = __shfl_sync(0xffffffffu, outOH, 31);
+          const uint32_t oof = __shfl_sync(0xffffffffu, outOF, 31);
+          const int c = b * 32 + j - 31;
+          if (lane == (c & 31)) {
+            wb.h = oh;
+            wb.f = of2;
+            wb.oh = ooh;
+            wb.of = oof;
+          }
+          if (c >= 0 && (c & 31) == 31) {
+            *reinterpret_cast<int4*>(&bndOut[(c & ~31) + lane]) = make_int4(wb.h, wb.f, (int)wb.oh, (int)wb.of);
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release(&a.progress[t], (c >> 5) + 1);
+          }
+        }
+      }
+    }
+    if (lastOrigin != 0xFFFFFFFFu)
+      table_emit(a.keys, a.vals, a.tableMask, a.overflow, ((unsigned long long)(uint32_t)ti << 32) | lastOrigin, lastVal);
+    __syncwarp();
+    if (lane == 0) st_release(&a.finished[t], 1);
+  }
+}
+
+// Follows pseudo origins through the per-task snapshots to the real origin cell and merges every candidate into the
+// final table keyed by (triple, i0, j0).  A pseudo origin that leads into a column block that was not swept marks
+// the triple for a redo with all blocks.
+struct ResolveArgs {
+  const BlockTask* tasks;
+  const int32_t* slen;
+  const uint32_t* snap;
+  const unsigned long long* keys;
+  const unsigned long long* vals;
+  uint32_t tableSize;
+  unsigned long long* fkeys;   // (triple << 40 | i0 << 20 | j0)
+  unsigned long long* fvals;
+  uint32_t fmask;
+  int* overflow;
+  int* redo;                   // [nTriples]
+  int verbose;
+};
+
+__global__ void resolve_candidates_kernel(ResolveArgs a) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < a.tableSize; s += gridDim.x * blockDim.x) {
+    const unsigned long long key = a.keys[s];
+    if (key == kEmptyKey) continue;
+    int t = (int)(key >> 32);
+    uint32_t o = (uint32_t)key;
+    const int triple = a.tasks[t].triple;
+    const int L = a.slen[a.tasks[t].subject];
+    bool ok = true;
+    for (int guard = 0; (o & kPseudoBit) && guard < 128; guard++) {
+      const int pt = a.tasks[t].prevTask;
+      if (pt < 0) {
+        ok = false;
+        break;
+      }
+      const uint32_t row = o & 0xFFFFFu;  // 1-based
+      const bool isE = o & kPseudoEBit;
+      o = a.snap[a.tasks[pt].snapOff + (isE ? L : 0) + (row - 1)];
+      t = pt;
+      if (o == 0) {
+        ok = false;
+        break;
+      }
+    }
+    if (!ok || (o & kPseudoBit)) {
+      if (atomicExch(&a.redo[triple], 1) == 0 && a.verbose)
+        printf("[resolve] triple %d: task %d (c0 %d) origin %x -> stuck at task %d (c0 %d prev %d) o %x val %llx\n", triple, (int)(key >> 32),
+               a.tasks[(int)(key >> 32)].c0, (uint32_t)key, t, a.tasks[t].c0, a.tasks[t].prevTask, o, a.vals[s]);
+      continue;
+    }
+    const uint32_t Lp1 = (uint32_t)L + 1u;
+    const unsigned long long i0 = (unsigned long long)(o / Lp1) + (unsigned long long)a.tasks[t].c0;
+    const unsigned long long j0 = o % Lp1;
+    table_emit(a.fkeys, a.fvals, a.fmask, a.overflow, ((unsigned long long)(uint32_t)triple << 40) | (i0 << 20) | j0, a.vals[s]);
   }
 }
 
