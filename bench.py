@@ -30,13 +30,21 @@ METRIC = "GCUPS (1e9 Smith-Waterman-Gotoh cell updates/s, Q*L*2 per stage) searc
 GAP = dict(gap_init=-30, ins_gap_ext=-6, del_gap_ext=-5, minscore=225, masklevel=101, minmatch=9, bandwidth=14)
 
 
-def workload(args, rank):
-    from repeatmasker_b200 import synth
+def workload(args, rank, world=1):
+    """Library (replicated) and this rank's fragments.  One seeded genome of world x genome_bp bases is cut into
+    SimpleBatcher fragments and fragment b goes to rank b mod world (repeatmasker_b200.sharding): per-GPU work is
+    fixed as N grows (weak scaling) and no rank ever needs another rank's data."""
+    from repeatmasker_b200 import sharding, synth
 
     snames, sseqs = synth.make_library(1001, n_families=args.families)
-    genome, truth = synth.make_genome(1001 + 7919 * rank, args.genome_bp, sseqs, coverage=0.45)
-    qn, qs = synth.fragment(genome, f"synth{rank}", frag=60000, overlap=2000)
-    return snames, sseqs, qn, qs
+    qn, qs = [], []
+    for part in range(world):  # the genome is generated 1 Mbp at a time so that every N sees the same first Mbp
+        genome, truth = synth.make_genome(1001 + 7919 * part, args.genome_bp, sseqs, coverage=0.45)
+        n, q = synth.fragment(genome, f"synth{part}", frag=60000, overlap=2000)
+        qn += n
+        qs += q
+    mine = sharding.my_fragments(len(qs), rank, world)
+    return snames, sseqs, [qn[i] for i in mine], [qs[i] for i in mine]
 
 
 def matrix_file(tmpdir):
@@ -131,6 +139,18 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def traffic_from_profile(cells_step):
+    """dram__bytes_read.sum + dram__bytes_write.sum of K1 from the committed `ncu --set full` capture
+    (profiles/k1_traffic.json, taken on this workload), per launch; None when the capture is for another size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        if abs(t["cells_per_launch"] - cells_step) / cells_step < 0.02:
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def config_dict(args, snames, sseqs, qn, qs, world):
     Q, L = sum(len(x) for x in qs), sum(len(x) for x in sseqs)
     return {"workload": "BASELINE configs[1]: 1 Mbp synthetic genome (45% implanted 10-30%-diverged copies) x 500-family "
@@ -149,7 +169,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-bp", type=int, default=1_000_000)
     ap.add_argument("--families", type=int, default=500)
-    ap.add_argument("--cpu-families", type=int, default=4, help="families per oracle process in the CPU sample")
+    ap.add_argument("--cpu-families", type=int, default=4, help="families per oracle process in the --impl reference sample")
+    ap.add_argument("--cpu-baseline-families", type=int, default=24, help="families in the single-thread cpu_baseline sample")
     ap.add_argument("--cpu-query-bp", type=int, default=60000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -175,7 +196,7 @@ def main():
     if world > 1:
         dist.barrier()
 
-    snames, sseqs, qn, qs = workload(args, rank)
+    snames, sseqs, qn, qs = workload(args, rank, world)
     tmp = tempfile.TemporaryDirectory()
     m = matrix_file(tmp.name)
     params = engine.make_params(device=local, **GAP)
@@ -254,10 +275,10 @@ def main():
                     "mbp_per_s": Q * world * args.steps / t_e2e_max / 1e6,
                     "what": "Session.set_library + set_queries (host buffers -> HBM) + search (records back on the host) per step"},
             "gpu_launches": int(sum(s["launches"] for s in st_res)),
-            "roofline": {"bound": "int-simd (DPX VIADDMNMX/VIMNMX3 16x2); not hbm, not tensor", "kernel": "swg_score_kernel<8>",
+            "roofline": {"bound": "int-simd (DPX VIADDMNMX/VIMNMX3 16x2); not hbm, not tensor", "kernel": "swg_score_kernel<16>",
                          "achieved": achieved, "peak": peak_cups / 1e9, "unit": "GCUPS", "frac": achieved / (peak_cups / 1e9),
                          "peak_source": "rmgpu_measure_dpx_peak: register-resident loop of the same recurrence, measured live on this GPU",
-                         "traffic": None, "k1_ms_per_launch": k1_ms, "dpx_warp_instr_per_s": dpx_ips,
+                         "traffic": traffic_from_profile(cells_step), "k1_ms_per_launch": k1_ms, "dpx_warp_instr_per_s": dpx_ips,
                          "hbm_algorithmic_gbs": (Q / 2 + sum(len(x) for x in sseqs) * 8) / (k1_ms * 1e-3) / 1e9,
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},
             "stage_ms": {k: sum(s[k] for s in st_res) / len(st_res) for k in ("ms_score", "ms_origin", "ms_traceback", "ms_host_post", "ms_total")},
@@ -266,6 +287,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             with tempfile.TemporaryDirectory() as d:
+                args.cpu_families = args.cpu_baseline_families
                 c, dt, desc = cpu_sample(args, d, snames, sseqs, qn, qs, 1)
             line["cpu_baseline"] = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port", "sample": desc,
                                     "host_cores": os.cpu_count()}
