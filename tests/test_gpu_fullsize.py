@@ -1,0 +1,150 @@
+"""BASELINE configuration 2 at FULL size (1 Mbp x 500 families, ~1.2e12 cells): the oracle would need hours, so the
+result is checked through size-independent properties, with the oracle's scoring functions as the checker:
+  * every reported alignment, re-scored column by column with the matrix and gap penalties, gives exactly the raw
+    score the DP reported, and its complexity-adjusted score is the reported score;
+  * coordinates, alignment rows and percentage strings are mutually consistent;
+  * output order is the specified order; '*' flags are consistent; no two hits share (query, strand, subject, origin);
+  * K1's best score per (query, subject, strand) bounds every hit of that triple and reaches it for the best one;
+  * a second run returns the identical result (no dependence on the dynamic ticket schedule);
+  * searching the fragments in two halves (two "ranks") returns the same hits as one batch.
+Also a many-family library (BASELINE configuration 5 in miniature) against the oracle."""
+import ctypes as C
+
+import pytest
+
+import util
+from repeatmasker_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def config2(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cfg2")
+    snames, sseqs = synth.make_library(1001, n_families=500)
+    genome, truth = synth.make_genome(1001, 1_000_000, sseqs, coverage=0.45)
+    qn, qs = synth.fragment(genome, "synth0", frag=60000, overlap=2000)
+    m = util.write_matrix("20p41g.matrix", str(d / "20p41g.matrix"))
+    s = engine.Session()
+    s.set_matrix(m)
+    s.set_library(sseqs, snames)
+    s.set_queries(qs, qn)
+    p = engine.make_params()
+    hits, st = s.search(p)
+    return dict(s=s, p=p, hits=hits, st=st, snames=snames, sseqs=sseqs, qn=qn, qs=qs, m=m, truth=truth)
+
+
+def test_full_size_alignments_rescore_exactly(config2):
+    c = config2
+    om = util.parse_matrix(c["m"])
+    op = util.OraParams(gap_init=-30, ins_gap_ext=-6, del_gap_ext=-5)
+    lib = util.oracle_lib()
+    assert len(c["hits"]) > 800
+    assert c["st"]["cells"] == 2.0 * sum(map(len, c["qs"])) * sum(map(len, c["sseqs"]))
+    qlen = dict(zip(c["qn"], map(len, c["qs"])))
+    slen = dict(zip(c["snames"], map(len, c["sseqs"])))
+    qseq = dict(zip(c["qn"], c["qs"]))
+    sseq = dict(zip(c["snames"], c["sseqs"]))
+    for h in c["hits"]:
+        raw, adj = C.c_int(), C.c_int()
+        lib.ora_rescore(h["qaln"].encode(), h["saln"].encode(), C.byref(om), C.byref(op), C.byref(raw), C.byref(adj))
+        assert raw.value == h["raw_score"], h
+        assert adj.value == h["score"] >= 225, h
+        qa, sa = h["qaln"].replace("-", ""), h["saln"].replace("-", "")
+        assert len(qa) == h["qend"] - h["qstart"] + 1 and len(sa) == h["send"] - h["sstart"] + 1
+        assert h["qleft"] == qlen[h["qname"]] - h["qend"] and h["sleft"] == slen[h["sname"]] - h["send"]
+        assert sa == sseq[h["sname"]][h["sstart"] - 1:h["send"]]
+        frag = qseq[h["qname"]][h["qstart"] - 1:h["qend"]]
+        assert qa == (synth.revcomp(frag) if h["strand"] == "C" else frag)
+        assert h["qaln"][0] != "-" and h["saln"][0] != "-" and h["qaln"][-1] != "-" and h["saln"][-1] != "-"
+        span = len(qa)
+        nsub = sum(1 for a, b in zip(h["qaln"], h["saln"]) if a != b and a != "-" and b != "-")
+        assert h["div"] == "%.2f" % (100.0 * nsub / span)
+        assert h["dele"] == "%.2f" % (100.0 * h["qaln"].count("-") / span)
+        assert h["ins"] == "%.2f" % (100.0 * h["saln"].count("-") / span)
+
+
+def test_full_size_order_flags_and_uniqueness(config2):
+    hits = config2["hits"]
+    qi = {n: i for i, n in enumerate(config2["qn"])}
+    si = {n: i for i, n in enumerate(config2["snames"])}
+    key = lambda h: (qi[h["qname"]], h["qstart"], -si[h["sname"]], h["sstart"], h["qend"], h["strand"] == "C", h["send"])
+    assert [key(h) for h in hits] == sorted(key(h) for h in hits)
+    seen = set()
+    for h in hits:
+        k = (h["qname"], h["strand"], h["sname"], h["qstart"] if h["strand"] == "+" else h["qend"], h["sstart"])
+        assert k not in seen, k  # one hit per alignment origin
+        seen.add(k)
+    byq = {}
+    for h in hits:
+        byq.setdefault(h["qname"], []).append(h)
+    for hs in byq.values():
+        for h in hs:
+            star = any(o["score"] > h["score"] and o["qstart"] <= h["qend"] and o["qend"] >= h["qstart"] for o in hs)
+            assert star == h["star"]
+
+
+def test_full_size_score_pass_bounds_hits_and_is_deterministic(config2):
+    c = config2
+    best, ms = c["s"].score_only(c["p"])
+    ns = len(c["sseqs"])
+    qi = {n: i for i, n in enumerate(c["qn"])}
+    si = {n: i for i, n in enumerate(c["snames"])}
+    top = {}
+    for h in c["hits"]:
+        k = (qi[h["qname"]], si[h["sname"]], 1 if h["strand"] == "C" else 0)
+        top[k] = max(top.get(k, 0), h["raw_score"])
+    for (q, s, strand), raw in top.items():
+        b = best[(q * ns + s) * 2 + strand]
+        assert b == min(raw, 32767) or (b == 32767 and raw >= 32000), (q, s, strand, b, raw)
+    again, _ = c["s"].search(c["p"])
+    assert again == c["hits"]
+    cells = 2.0 * sum(map(len, c["qs"])) * sum(map(len, c["sseqs"]))
+    assert cells / (ms * 1e-3) / 1e9 > 1000, "K1 slower than 1,000 GCUPS on a B200: not running the DPX path?"
+
+
+def test_full_size_sharded_equals_single_batch(config2):
+    """Fragments are independent units: two 'ranks' each searching their round-robin share give the same hits."""
+    from repeatmasker_b200 import sharding
+
+    c = config2
+    parts = []
+    ids = []
+    for rank in range(2):
+        mine = sharding.my_fragments(len(c["qs"]), rank, 2)
+        c["s"].set_queries([c["qs"][i] for i in mine], [c["qn"][i] for i in mine])
+        hits, _ = c["s"].search(c["p"])
+        parts.append(sharding.split_hits_by_fragment(hits, [c["qn"][i] for i in mine]))
+        ids.append(mine)
+    merged = [None] * len(c["qs"])
+    for mine, part in zip(ids, parts):
+        for f, h in zip(mine, part):
+            merged[f] = h
+    strip = lambda h: {k: v for k, v in h.items() if k != "query_index"}
+    want = sharding.split_hits_by_fragment(c["hits"], c["qn"])
+    assert [[strip(h) for h in f] for f in merged] == [[strip(h) for h in f] for f in want]
+    c["s"].set_queries(c["qs"], c["qn"])
+
+
+def test_many_family_library_against_oracle(tmp_path):
+    """Configuration 5 in miniature: thousands of short families plus a few long ones, many small query records
+    (several ticket-order groups, many fillers per stripe)."""
+    snames, sseqs = synth.make_library(77, n_families=3000, mu=4.6, sigma=0.5, lo=40, hi=400)
+    ln, ls = synth.make_library(78, n_families=6, mu=8.2, sigma=0.3, lo=2000, hi=6000)
+    snames = [f"L{n}" for n in ln] + snames
+    sseqs = ls + sseqs
+    genome, _ = synth.make_genome(79, 24000, sseqs, coverage=0.5)
+    qn, qs = synth.fragment(genome, "chrM", frag=700, overlap=60)
+    assert len(qs) >= 30
+    q, s, m = str(tmp_path / "q.fa"), str(tmp_path / "s.fa"), str(tmp_path / "m.matrix")
+    synth.write_fasta(q, qn, qs)
+    synth.write_fasta(s, snames, sseqs)
+    util.write_matrix("20p43g.matrix", m)
+    want, _ = util.run_oracle(q, s, m, minscore=200)
+    got, st = engine.search_files(q, s, m, minscore=200)
+    assert len(want) > 20
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for k in ("score", "div", "dele", "ins", "qname", "qstart", "qend", "strand", "sname", "sstart", "send", "star",
+                  "qaln", "saln"):
+            assert g[k] == w[k], (k, g, w)
