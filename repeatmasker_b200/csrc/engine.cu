@@ -157,6 +157,8 @@ struct rmgpu_session {
   DevBuf<unsigned long long> d_keysC, d_valsC;
   DevBuf<BlockTask> d_btasks;
   DevBuf<uint32_t> d_snap;
+  DevBuf<int32_t> d_ticketStripe, d_prodTicket, d_consTicket;
+  int blockLevelWidth = 0;
   DevBuf<unsigned long long> d_fkeys, d_fvals;
   int32_t h_mat[16][16];
   void check_abort(const char* what);
@@ -642,11 +644,32 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       if (sorted[i].prevTask >= 0) sorted[i].prevTask = inv[sorted[i].prevTask];
     }
     tasks.swap(sorted);
-    std::vector<int32_t> ticketTask;
-    for (size_t i = 0; i < tasks.size(); i++) {
-      tasks[i].nStripes = (int)((lib.seqs[tasks[i].subject].size() + kR2 * 32 - 1) / (kR2 * 32));
-      tasks[i].firstTicket = (int)ticketTask.size();
-      for (int k = 0; k < tasks[i].nStripes; k++) ticketTask.push_back((int32_t)i);
+    // tickets go stripe level by stripe level over all tasks (all first stripes, then all second stripes, ...): a
+    // consumer stripe is claimed after (nearly) a whole level of other tickets, so it does not poll its producer
+    std::vector<int32_t> ticketTask, ticketStripe, prodTicket, consTicket;
+    int maxStripes = 0;
+    for (auto& t : tasks) {
+      t.nStripes = (int)((lib.seqs[t.subject].size() + kR2 * 32 - 1) / (kR2 * 32));
+      maxStripes = std::max(maxStripes, t.nStripes);
+    }
+    {
+      std::vector<int32_t> prevOf(tasks.size(), -1);
+      size_t levelWidthMax = 0;
+      for (int level = 0; level < maxStripes; level++) {
+        size_t before = ticketTask.size();
+        for (size_t i = 0; i < tasks.size(); i++) {
+          if (level >= tasks[i].nStripes) continue;
+          const int32_t tkt = (int32_t)ticketTask.size();
+          ticketTask.push_back((int32_t)i);
+          ticketStripe.push_back(level);
+          prodTicket.push_back(prevOf[i]);
+          consTicket.push_back(-1);
+          if (prevOf[i] >= 0) consTicket[prevOf[i]] = tkt;
+          prevOf[i] = tkt;
+        }
+        levelWidthMax = std::max(levelWidthMax, ticketTask.size() - before);
+      }
+      blockLevelWidth = (int)levelWidthMax;
     }
     const int nTickets = (int)ticketTask.size();
     int blocksPerSM = 0;
@@ -655,7 +678,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     // leave room for the CTAs of the concurrent fallback sweep (persistent grids: what is not resident cannot start)
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)numSMs * blocksPerSM - chainCtas, ((int64_t)nTickets + 3) / 4));
     const int warps = grid * 4;
-    const int nslot = std::min(nTickets, 2 * warps + 2);
+    // a slot's reader is at most one level (blockLevelWidth tickets) after its writer
+    const int nslot = (int)std::min<int64_t>(nTickets, std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)blockLevelWidth + 2));
     int64_t maxW = 0;
     for (auto& t : tasks) maxW = std::max<int64_t>(maxW, t.c1 - t.c0);
     const int64_t bndStride = ((maxW + 31) >> 5) * 32 + 32;
@@ -664,8 +688,14 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       BlockArgs a;
       d_btasks.upload(tasks, stream);
       d_ticketTask.upload(ticketTask, stream);
+      d_ticketStripe.upload(ticketStripe, stream);
+      d_prodTicket.upload(prodTicket, stream);
+      d_consTicket.upload(consTicket, stream);
       a.tasks = d_btasks.p;
       a.ticketTask = d_ticketTask.p;
+      a.ticketStripe = d_ticketStripe.p;
+      a.prodTicket = d_prodTicket.p;
+      a.consTicket = d_consTicket.p;
       a.nTickets = nTickets;
       a.codes_fwd = d_codes_fwd.p;
       a.codes_rc = d_codes_rc.p;
@@ -766,6 +796,11 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   int64_t chainD2H = 0;
   auto run_chain = [&](const std::vector<int>& trIdx) {
     if (trIdx.empty()) return;
+    // A sweep is one long dependent chain of columns: when there are too few of them to fill the machine the time is
+    // the per-column latency of one warp, which falls with the rows a lane owns -> 2 rows per lane instead of 8.
+    int64_t stripes8 = 0;
+    for (int tr : trIdx) stripes8 += (int64_t)(lib.seqs[triples[tr].subject].size() + 255) / 256;
+    const int chainR = (stripes8 * 4 <= (int64_t)numSMs * 16) ? 2 : 8;
     std::vector<OriginTask> tasks;
     std::vector<int32_t> ticketTask;
     for (int tr : trIdx) {
@@ -775,7 +810,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       t.q = T.q;
       t.strand = T.strand;
       t.subject = T.subject;
-      t.nStripes = (int)((lib.seqs[T.subject].size() + kR2 * 32 - 1) / (kR2 * 32));
+      t.nStripes = (int)((lib.seqs[T.subject].size() + chainR * 32 - 1) / (chainR * 32));
       // without checkpoints the cold column blocks are swept score-only; after an int16 wrap the mask is unreliable
       const size_t idx = ((size_t)T.q * nS + T.subject) * 2 + T.strand;
       // after an int16 wrap K1 under-reports the blocks that follow (true scores decay by only ~5-6 per column along
@@ -795,7 +830,10 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       chainCells += (double)h_qlen[T.q] * (double)lib.seqs[T.subject].size();
     }
     int blocksPerSM = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_origin_kernel, 128, 0));
+    if (chainR == 2)
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_origin_kernel<2>, 128, 0));
+    else
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_origin_kernel<8>, 128, 0));
     if (blocksPerSM < 1) throw Error("K2 does not fit on an SM");
     blocksPerSM = std::min(blocksPerSM, 4);
     const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
@@ -849,7 +887,10 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         CUDA_CHECK(cudaMemsetAsync(a.overflow, 0, sizeof(int), stream2));
         EventTimer tm;
         tm.start(stream2);
-        swg_origin_kernel<<<grid, 128, 0, stream2>>>(a);
+        if (chainR == 2)
+          swg_origin_kernel<2><<<grid, 128, 0, stream2>>>(a);
+        else
+          swg_origin_kernel<8><<<grid, 128, 0, stream2>>>(a);
         tm.stop(stream2);
         CUDA_CHECK(cudaGetLastError());
         std::vector<unsigned long long> keys(tableSize), vals(tableSize);
@@ -905,8 +946,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
 
   std::vector<int> blockTr, chainTr, redo;
   for (size_t i = 0; i < triples.size(); i++) (triples[i].chain ? chainTr : blockTr).push_back((int)i);
-  for (int tr : chainTr) chainCtas += (int)((lib.seqs[triples[tr].subject].size() + kR2 * 32 - 1) / (kR2 * 32));
-  chainCtas = std::min((chainCtas + 3) / 4, numSMs);
+  for (int tr : chainTr) chainCtas += (int)((lib.seqs[triples[tr].subject].size() + 63) / 64);
+  chainCtas = std::min((chainCtas + 3) / 4, numSMs * 2);
   // the fallback sweeps are long and narrow (a few warps busy for tens of ms): run them on a second stream from a
   // second host thread while the block-parallel path fills the machine
   const double k2t0 = now_ms();

@@ -552,12 +552,12 @@ __device__ __forceinline__ OriginCell origin_cell(bool valid, int hl, uint32_t o
 // propagation; all other columns with the plain int32 recurrence (same H/E/F values, about a quarter of the
 // instructions).  Entering an origin block, every live path gets the origin kOriginLeft; a candidate carrying it,
 // or any cell >= minscore met in score-only mode, flags the task and the host redoes it with mode = all ones.
+template <int R>
 __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
   __shared__ int32_t smat[16 * 16];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  constexpr int R = kR2;
   const int NEGI = -(1 << 28);
   for (;;) {
     int t = 0;
@@ -783,7 +783,10 @@ struct BlockTask {
 
 struct BlockArgs {
   const BlockTask* tasks;
-  const int32_t* ticketTask;   // [nTickets]
+  const int32_t* ticketTask;   // [nTickets] task of the ticket; tickets go stripe level by stripe level over all tasks
+  const int32_t* ticketStripe; // [nTickets] stripe of the ticket
+  const int32_t* prodTicket;   // [nTickets] ticket of (task, stripe-1) or -1: always an older ticket
+  const int32_t* consTicket;   // [nTickets] ticket of (task, stripe+1) or -1
   int nTickets;
   const uint8_t* codes_fwd;
   const uint8_t* codes_rc;
@@ -836,7 +839,7 @@ __global__ void __launch_bounds__(128) swg_origin_block_kernel(BlockArgs a) {
     if (t >= a.nTickets) break;
     const int ti = a.ticketTask[t];
     const BlockTask tk = a.tasks[ti];
-    const int st = t - tk.firstTicket;  // stripe of this ticket
+    const int st = a.ticketStripe[t];  // stripe of this ticket
     const int L = a.slen[tk.subject];
     const uint32_t Lp1 = (uint32_t)L + 1u;
     const uint8_t* qc = (tk.strand ? a.codes_rc : a.codes_fwd) + a.qoff[tk.q];
@@ -844,15 +847,16 @@ __global__ void __launch_bounds__(128) swg_origin_block_kernel(BlockArgs a) {
     const int W = tk.c1 - tk.c0;
     const int qBlocks = (W + 31) >> 5, nBlocks = qBlocks + 1;
     const int sh = tk.strand ? 16 : 0;
-    const bool hasPrev = st > 0, hasNext = st + 1 < tk.nStripes;
-    const OriginBoundary* bndIn = a.bnd + (int64_t)((t - 1 + a.nslot) % a.nslot) * a.bndStride;
+    const int tProd = a.prodTicket[t];
+    const bool hasPrev = tProd >= 0, hasNext = a.consTicket[t] >= 0;
+    const OriginBoundary* bndIn = a.bnd + (int64_t)((hasPrev ? tProd : 0) % a.nslot) * a.bndStride;
     OriginBoundary* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
     if (hasNext) {
-      // the reader (ticket + 1) of the last ticket that wrote this ring slot must be done
+      // the reader of the last ticket that wrote this ring slot must be done
       for (int tOld = t - a.nslot; tOld >= 0; tOld -= a.nslot) {
-        const BlockTask& ot = a.tasks[a.ticketTask[tOld]];
-        if (tOld - ot.firstTicket + 1 >= ot.nStripes) continue;  // that ticket had no stripe below: it wrote nothing
-        if (lane == 0) wait_ge(&a.finished[tOld + 1], 1, a.abort_flag);
+        const int cOld = a.consTicket[tOld];
+        if (cOld < 0) continue;  // that ticket had no stripe below: it wrote nothing
+        if (lane == 0) wait_ge(&a.finished[cOld], 1, a.abort_flag);
         __syncwarp();
         break;
       }
@@ -896,7 +900,7 @@ __global__ void __launch_bounds__(128) swg_origin_block_kernel(BlockArgs a) {
       const int qv = (col < W) ? (int)qc[tk.c0 + col] : -1;
       OriginBoundary bv = {0, NEGI, 0, 0};
       if (hasPrev && b < qBlocks) {
-        if (lane == 0 && ld_acquire(&a.progress[t - 1]) < b + 1) wait_ge(&a.progress[t - 1], b + 1, a.abort_flag);
+        if (lane == 0 && ld_acquire(&a.progress[tProd]) < b + 1) wait_ge(&a.progress[tProd], b + 1, a.abort_flag);
         __syncwarp();
         const int4 raw = __ldcg(reinterpret_cast<const int4*>(&bndIn[col]));
         bv.h = raw.x;
