@@ -12,6 +12,7 @@
 #include <memory>
 #include <numeric>
 #include <set>
+#include <atomic>
 #include <exception>
 #include <string>
 #include <thread>
@@ -596,6 +597,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     for (int j = 0; j < 16; j++) h_mat[i][j] = (i < matrix.n && j < matrix.n) ? matrix.score[i][j] : -128;
 
   int chainCtas = 0;  // CTAs the concurrent fallback sweep needs resident
+  std::atomic<int> chainLaunched{0};  // set once the fallback sweep's kernel is in its stream (or there is none)
   // ------------------------------------------------------------------ block-parallel path
   auto run_blocks = [&](const std::vector<int>& trIdx, bool allBlocks, std::vector<int>& redoOut) {
     std::vector<BlockTask> tasks;
@@ -683,8 +685,9 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     int64_t maxW = 0;
     for (auto& t : tasks) maxW = std::max<int64_t>(maxW, t.c1 - t.c0);
     const int64_t bndStride = ((maxW + 31) >> 5) * 32 + 32;
-    size_t tableSize = 1u << 20;
+    size_t tableSize = 1u << 23;  // first-level table (task, relative or pseudo origin): kept very sparse, probing is atomics
     for (;;) {
+      const size_t ftableSize = tableSize >> 6;  // final table (triple, origin): the only one downloaded
       BlockArgs a;
       d_btasks.upload(tasks, stream);
       d_ticketTask.upload(ticketTask, stream);
@@ -735,15 +738,17 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       r.keys = a.keys;
       r.vals = a.vals;
       r.tableSize = (uint32_t)tableSize;
-      r.fkeys = d_fkeys.ensure(tableSize);
-      r.fvals = d_fvals.ensure(tableSize);
-      r.fmask = (uint32_t)tableSize - 1;
+      r.fkeys = d_fkeys.ensure(ftableSize);
+      r.fvals = d_fvals.ensure(ftableSize);
+      r.fmask = (uint32_t)ftableSize - 1;
       r.overflow = a.overflow;
       r.redo = d_leftFlag.ensure(triples.size());
       r.verbose = allBlocks ? 1 : 0;
-      CUDA_CHECK(cudaMemsetAsync(r.fkeys, 0xFF, tableSize * 8, stream));
-      CUDA_CHECK(cudaMemsetAsync(r.fvals, 0, tableSize * 8, stream));
+      CUDA_CHECK(cudaMemsetAsync(r.fkeys, 0xFF, ftableSize * 8, stream));
+      CUDA_CHECK(cudaMemsetAsync(r.fvals, 0, ftableSize * 8, stream));
       CUDA_CHECK(cudaMemsetAsync(r.redo, 0, triples.size() * sizeof(int), stream));
+      // let the (small, high-priority) fallback sweep take its SM slots first, then fill the rest of the machine
+      for (double w0 = now_ms(); !chainLaunched.load() && now_ms() - w0 < 100.0;) std::this_thread::yield();
       EventTimer tm;
       tm.start(stream);
       swg_origin_block_kernel<<<grid, 128, 0, stream>>>(a);
@@ -752,17 +757,17 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       CUDA_CHECK(cudaGetLastError());
       int overflow = 0;
       std::vector<int> redoFlag(triples.size(), 0);
-      std::vector<unsigned long long> keys(tableSize), vals(tableSize);
+      std::vector<unsigned long long> keys(ftableSize), vals(ftableSize);
       CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
       CUDA_CHECK(cudaMemcpyAsync(redoFlag.data(), r.redo, triples.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaMemcpyAsync(keys.data(), r.fkeys, tableSize * 8, cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaMemcpyAsync(vals.data(), r.fvals, tableSize * 8, cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaMemcpyAsync(keys.data(), r.fkeys, ftableSize * 8, cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaMemcpyAsync(vals.data(), r.fvals, ftableSize * 8, cudaMemcpyDeviceToHost, stream));
       CUDA_CHECK(cudaStreamSynchronize(stream));
       check_abort("K2b");
       (void)tm;
       st.launches += 2;
-      st.d2h_bytes += (int64_t)tableSize * 16;
-      if (overflow) {
+      st.d2h_bytes += (int64_t)ftableSize * 16;
+      if (overflow) {  // a probe sequence got long in one of the two tables
         tableSize *= 4;
         if (tableSize > (1u << 28)) throw Error("candidate table overflow");
         continue;
@@ -843,7 +848,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     const int nslot = std::min(nTickets, 2 * warps + 2);
     for (int round = 0; round < 2; round++) {
       std::vector<int> leftFlag(tasks.size(), 0);
-      size_t tableSize = 1u << 18;
+      size_t tableSize = 1u << 18;  // grows x4 on overflow
       for (;;) {
         OriginArgs a;
         d_tasksC.upload(tasks, stream2);
@@ -892,6 +897,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         else
           swg_origin_kernel<8><<<grid, 128, 0, stream2>>>(a);
         tm.stop(stream2);
+        chainLaunched.store(1);
         CUDA_CHECK(cudaGetLastError());
         std::vector<unsigned long long> keys(tableSize), vals(tableSize);
         int overflow = 0;
@@ -959,6 +965,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     } catch (...) {
       chainErr = std::current_exception();
     }
+    chainLaunched.store(1);
   });
   std::exception_ptr blockErr;
   try {

@@ -496,7 +496,7 @@ __device__ __forceinline__ unsigned long long cand_val(int h, int i, int j) {
 __device__ __forceinline__ void origin_emit(const OriginArgs& a, int task, uint32_t origin, unsigned long long val) {
   uint64_t key = ((uint64_t)(uint32_t)task << 32) | origin;
   uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & a.tableMask;
-  for (uint32_t probe = 0; probe <= a.tableMask; probe++) {
+  for (uint32_t probe = 0; probe < 128u && probe <= a.tableMask; probe++) {
     unsigned long long old = atomicCAS(&a.keys[slot], kEmptyKey, key);
     if (old == kEmptyKey || old == key) {
       atomicMax(&a.vals[slot], val);
@@ -814,7 +814,7 @@ struct BlockArgs {
 __device__ __forceinline__ void table_emit(unsigned long long* keys, unsigned long long* vals, uint32_t mask, int* overflow,
                                            unsigned long long key, unsigned long long val) {
   uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & mask;
-  for (uint32_t probe = 0; probe <= mask; probe++) {
+  for (uint32_t probe = 0; probe < 128u && probe <= mask; probe++) {  // a long probe sequence = table too full: grow it
     unsigned long long old = atomicCAS(&keys[slot], kEmptyKey, key);
     if (old == kEmptyKey || old == key) {
       atomicMax(&vals[slot], val);
