@@ -178,7 +178,9 @@ struct rmgpu_session {
   void set_queries(SeqSet s);
   void build_classes_and_profile();
   void run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest, std::vector<unsigned long long>& hotmask,
-                 double& ms, int& launches);
+                 double& ms, int& launches, bool exact);
+  int ovfThresh = 32000;  // K1 reports 32767 for any best at or above this
+  int scoreSlack = 0;  // how much below the true best the sampled K1 best can be (0 in exact mode)
   void run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest,
                   const std::vector<unsigned long long>& hotmask, std::vector<Candidate>& cands, rmgpu_stats& st);
   void run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands, std::vector<std::vector<uint8_t>>& ops,
@@ -459,7 +461,7 @@ void rmgpu_session::check_abort_on(const char* what, int* flag, cudaStream_t stq
 
 // K1 over the resident batch x library.
 void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest,
-                              std::vector<unsigned long long>& hotmask, double& ms, int& launches) {
+                              std::vector<unsigned long long>& hotmask, double& ms, int& launches, bool exact) {
   const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
   pairbest.assign((size_t)nQ * nS * 2, 0);
   hotmask.assign((size_t)nQ * nS * 2, 0);
@@ -469,7 +471,14 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
     throw Error("gap penalties must be negative");
   build_classes_and_profile();
   int blocksPerSM = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R>, kScoreWarps * 32, 0));
+  if (exact)
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R, true>, kScoreWarps * 32, 0));
+  else
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R, false>, kScoreWarps * 32, 0));
+  scoreSlack = exact ? 0 : 7 * std::abs(p.ins_gap_ext);
+  // between two samples (8 columns) a score can rise by at most 8 * max matrix score
+  ovfThresh = 32767 - 9 * std::max(matrix.max_score(), 1) - scoreSlack;
+  if (ovfThresh < 16384) throw Error("matrix scores too large for the int16 score pass");
   if (blocksPerSM < 1) throw Error("K1 does not fit on an SM");
   const int64_t nTickets = (int64_t)nQ * nStripes;
   if (nTickets >= (1ll << 31)) throw Error("too many stripe tasks in one batch");
@@ -504,7 +513,8 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   a.gi2 = pack2(p.gap_init);
   a.ie2 = pack2(p.ins_gap_ext);
   a.df2 = pack2(std::max(p.del_gap_ext, p.gap_init));
-  a.minscore = std::min(p.minscore, 32000);
+  a.minscore = std::max(1, std::min(p.minscore, ovfThresh) - scoreSlack);
+  a.ovfThresh = ovfThresh;
   a.abort_flag = d_abort.ensure(1);
   // column checkpoints for the origin pass (64 per query): only when they fit the budget
   {
@@ -529,7 +539,10 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   tm.start(stream);
   // tag 0 = "never written": the boundary ring must not hold tags of an earlier launch
   CUDA_CHECK(cudaMemsetAsync(a.bnd, 0, (size_t)nslot * bndStride * sizeof(unsigned long long), stream));
-  swg_score_kernel<R><<<grid, kScoreWarps * 32, 0, stream>>>(a);
+  if (exact)
+    swg_score_kernel<R, true><<<grid, kScoreWarps * 32, 0, stream>>>(a);
+  else
+    swg_score_kernel<R, false><<<grid, kScoreWarps * 32, 0, stream>>>(a);
   tm.stop(stream);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpyAsync(pairbest.data(), a.pairbest, pairbest.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -567,7 +580,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     for (int s = 0; s < nS; s++)
       for (int strand = 0; strand < 2; strand++) {
         const size_t idx = ((size_t)q * nS + s) * 2 + strand;
-        if (pairbest[idx] < std::min(p.minscore, 32000)) continue;
+        if (pairbest[idx] < std::max(1, std::min(p.minscore, ovfThresh) - scoreSlack)) continue;
         const int64_t Q = h_qlen[q], L = (int64_t)lib.seqs[s].size();
         if ((Q + 1) * (L + 1) >= (1ll << 32))
           throw Error("query x subject too large for one origin pass (" + queries.names[q] + " x " + lib.names[s] +
@@ -580,7 +593,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         t.dil = m | (m << 1) | (m >> 1);
         const int64_t CB = 32ll << h_hotShift[q];
         // checkpoints are exact only when K1 is (no merged residue class, no int16 wrap)
-        t.chain = pairbest[idx] >= 32000 || fullMode || !ckEnabled || !classesExact || t.dil == 0 ||
+        t.chain = pairbest[idx] >= 32767 || fullMode || !ckEnabled || !classesExact || t.dil == 0 ||
                   (CB + 2) * (L + 1) >= (1ll << 31);
         triples.push_back(t);
       }
@@ -822,7 +835,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       // a gap), so the mask is stretched 8 blocks forward; a cell >= minscore met in a score-only block still forces
       // a full redo of the task, so exactness never depends on this guess
       unsigned long long fwd = T.dil;
-      if (pairbest[idx] >= 32000)
+      if (pairbest[idx] >= 32767)
         for (int k = 1; k <= 8; k++) fwd |= T.dil << k;
       t.mode = (fullMode || T.dil == 0) ? ~0ull : fwd;
       t.hotShift = h_hotShift[T.q];
@@ -1177,7 +1190,7 @@ rmgpu_result* rmgpu_session::search(const rmgpu_params& p) {
 
   std::vector<int32_t> pairbest;
   std::vector<unsigned long long> hotmask;
-  run_score(p, pairbest, hotmask, st.ms_score, st.launches);
+  run_score(p, pairbest, hotmask, st.ms_score, st.launches, /*exact=*/false);
   st.score_launches = 1;
   st.d2h_bytes += (int64_t)pairbest.size() * 12;
   std::vector<Candidate> cands;
@@ -1473,7 +1486,7 @@ int rmgpu_session_score_only(rmgpu_session* s, const rmgpu_params* p, int32_t* b
     std::vector<unsigned long long> hm;
     double t = 0;
     int launches = 0;
-    s->run_score(*p, pb, hm, t, launches);
+    s->run_score(*p, pb, hm, t, launches, /*exact=*/true);
     if (best) memcpy(best, pb.data(), pb.size() * sizeof(int32_t));
     if (ms) *ms = t;
   });

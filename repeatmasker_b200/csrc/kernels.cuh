@@ -159,7 +159,8 @@ struct ScoreArgs {
   int* finished;              // [nTickets]
   int* ticket;                // global ticket counter
   uint32_t gi2, ie2, df2;     // gap_init, ins_gap_ext, max(del_gap_ext, gap_init), replicated in both halves
-  int minscore;
+  int minscore;               // hot-mask threshold (already lowered by the sampling slack in the search path)
+  int ovfThresh;              // a best at or above this is reported as 32767 = "int16 may have wrapped, redo in int32"
   int* abort_flag;            // set by the watchdog
   uint2* ck;                  // optional column checkpoints [(q*64 + cb) * ckRows + g*R + r] = (H, E') before column cb*CB
   int64_t ckRows;             // nGroups * R
@@ -187,7 +188,12 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 
 constexpr int kScoreWarps = 8;
 
-template <int R>
+// EXACT: the running best is folded in at every cell (rmgpu_session_score_only, tests).  !EXACT (the search path, where
+// K1 is only a filter): the best is sampled from E' every 8th column.  E'[i][j] = max_k (H[i-k][j] + (k-1)*ins_ext), so
+// a sample sees every H of the previous 8 columns of its row less at most 7*|ins_ext|; the host lowers its thresholds
+// by that slack (ScoreArgs::minscore already includes it), which keeps the filter free of false negatives and saves
+// 6 of the 104 integer-pipe instructions per lane-column.
+template <int R, bool EXACT>
 __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArgs a) {
   __shared__ uint4 s_feed[kScoreWarps][32];  // (selector, H above, F' above) for the 32 columns of the current block
   __shared__ uint2 s_out[kScoreWarps][32];   // last row's (H, F') of the last 32 columns lane 31 finished
@@ -323,7 +329,11 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           f = __viaddmax_s16x2(f, a.df2, tt);                        // F' of the next row         (the only chain)
           hd = hl;
           H[r] = h;
-          bestBlk = __vmaxs2(bestBlk, h);
+          if (EXACT) bestBlk = __vmaxs2(bestBlk, h);
+        }
+        if (!EXACT && (j & 7) == 7) {
+#pragma unroll
+          for (int r = 0; r < R; r++) bestBlk = __vmaxs2(bestBlk, E[r]);
         }
         outH = h;
         outF = f;
@@ -360,9 +370,9 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     // per (query, subject, strand) best
     if (sj >= 0) {
       int f = (int)(int16_t)(best & 0xffffu), rc = (int)(int16_t)(best >> 16);
-      // an int16 wrap shows up as a negative or >= 32000 best: report 32767 so the pair goes to the int32 pass
-      if (f < 0 || f >= 32000) f = 32767;
-      if (rc < 0 || rc >= 32000) rc = 32767;
+      // a best this close to 32767 may hide an int16 wrap: report 32767 so that the triple is redone in int32
+      if (f < 0 || f >= a.ovfThresh) f = 32767;
+      if (rc < 0 || rc >= a.ovfThresh) rc = 32767;
       int32_t* pb = a.pairbest + ((int64_t)q * a.nSubjects + sj) * 2;
       if (f > 0) atomicMax(pb, f);
       if (rc > 0) atomicMax(pb + 1, rc);
