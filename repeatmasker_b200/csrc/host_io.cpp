@@ -79,10 +79,17 @@ ScoreMatrix ScoreMatrix::from_file(const std::string& path) {
 }
 
 char complement_letter(char c) {
-  static const char* from = "ACGTYRMKHBVD";
-  static const char* to = "TGCARYKMDVBH";
-  const char* p = std::strchr(from, c);
-  return (p && c) ? to[p - from] : c;
+  // table of CrossmatchSearchEngine.pm:833 (tr/ACGTYRMKHBVD/TGCARYKMDVBH/), everything else maps to itself
+  static const struct Table {
+    char t[256];
+    Table() {
+      for (int i = 0; i < 256; i++) t[i] = (char)i;
+      const char* from = "ACGTYRMKHBVD";
+      const char* to = "TGCARYKMDVBH";
+      for (int i = 0; from[i]; i++) t[(unsigned char)from[i]] = to[i];
+    }
+  } table;
+  return table.t[(unsigned char)c];
 }
 
 std::string revcomp_letters(const std::string& s) {

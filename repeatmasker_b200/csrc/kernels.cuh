@@ -1109,14 +1109,18 @@ struct TraceArgs {
 // (the diagonal source), the others wave w-1.
 constexpr int kTraceWarpBand = 256;    // ints per array per warp in warp mode
 constexpr int kTraceWarps = 4;
-constexpr int kTraceBlockBand = 3072;  // ints per array in block mode
+constexpr int kTraceBlockBand = 2048;  // ints per array in block mode
+constexpr int kTraceSeqBlock = 10240;  // query / subject bytes of a candidate staged in shared memory (block mode)
+constexpr int kTraceSeqWarp = 1024;    // the same per warp in warp mode
 
 template <bool BLOCK>
 __global__ void __launch_bounds__(kTraceWarps * 32) traceback_kernel(TraceArgs a) {
   constexpr int T = BLOCK ? kTraceWarps * 32 : 32;
   constexpr int SB = BLOCK ? kTraceBlockBand : kTraceWarpBand;
+  constexpr int SQ = BLOCK ? kTraceSeqBlock : kTraceSeqWarp;
   __shared__ int32_t smat[16 * 16];
   __shared__ int32_t sband[BLOCK ? 1 : kTraceWarps][3][SB];
+  __shared__ uint8_t sseq[BLOCK ? 1 : kTraceWarps][2][SQ];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
   __syncthreads();
   const int tid = BLOCK ? threadIdx.x : (threadIdx.x & 31);
@@ -1134,6 +1138,12 @@ __global__ void __launch_bounds__(kTraceWarps * 32) traceback_kernel(TraceArgs a
   const int n = tc.i1 - tc.i0 + 1, m = tc.j1 - tc.j0 + 1;
   const uint8_t* qc = (tc.strand ? a.codes_rc : a.codes_fwd) + a.qoff[tc.q] + (tc.i0 - 1);
   const uint8_t* sc = a.scodes + a.soff[tc.subject] + (tc.j0 - 1);
+  if (n <= SQ && m <= SQ) {  // stage both sequences: the waves then never wait on global memory for their residues
+    for (int i = tid; i < n; i += T) sseq[wib][0][i] = qc[i];
+    for (int i = tid; i < m; i += T) sseq[wib][1][i] = sc[i];
+    qc = sseq[wib][0];
+    sc = sseq[wib][1];
+  }
   const int dlo = min(0, n - m) - tc.W, dhi = max(0, n - m) + tc.W;
   const int bw = dhi - dlo + 1;
   uint8_t* dir = a.dir + tc.dirOff;
