@@ -126,6 +126,13 @@ int rmgpu_session_score_only(rmgpu_session *s, const rmgpu_params *p, int32_t *b
 int rmgpu_session_counts(const rmgpu_session *s, int32_t *n_queries, int32_t *n_subjects, int64_t *query_bases,
                          int64_t *subject_bases);
 
+/* ---- Persistent worker (repeatmasker_b200/rmgpu_server).  With RMGPU_SERVER=<unix socket path> in the environment,
+ * rmgpu_search() makes no CUDA call in the calling process: it sends the request to the server, which keeps one
+ * session (matrix + packed library resident in HBM) per GPU.  This is what a forked, short-lived RepeatMasker batch child
+ * (RepeatMasker:1043-1180) should use.  The two calls below are management helpers: 0 = server answered.            */
+int rmgpu_server_ping(const char *socket_path);
+int rmgpu_server_quit(const char *socket_path);
+
 /* Measured integer-SIMD ("DPX") peak of this GPU: a register-resident loop of the bare recurrence.
  * Returns 16-bit-lane cell updates per second (GCUPS*1e9) in *cups and raw VIADDMNMX.S16x2 warp-instructions/s. */
 int rmgpu_measure_dpx_peak(int device, double *cups, double *dpx_instr_per_s);

@@ -21,6 +21,7 @@
 #include "../../include/rmgpu.h"
 #include "host.hpp"
 #include "kernels.cuh"
+#include "remote.hpp"
 
 namespace rmgpu {
 
@@ -1322,16 +1323,7 @@ rmgpu_result* rmgpu_session::search(const rmgpu_params& p) {
     }
   }
   // marshal
-  struct Arena {
-    std::vector<std::unique_ptr<char[]>> blocks;
-    const char* dup(const std::string& s) {
-      std::unique_ptr<char[]> b(new char[s.size() + 1]);
-      memcpy(b.get(), s.c_str(), s.size() + 1);
-      blocks.push_back(std::move(b));
-      return blocks.back().get();
-    }
-  };
-  auto* arena = new Arena();
+  auto* arena = new ResultArena();
   res->opaque = arena;
   res->n_hits = (int32_t)hits.size();
   res->hits = hits.empty() ? nullptr : new rmgpu_hit[hits.size()];
@@ -1503,6 +1495,15 @@ int rmgpu_session_counts(const rmgpu_session* s, int32_t* nq, int32_t* ns, int64
 int rmgpu_search(const rmgpu_params* p, const char* query_fasta, const char* subject_fasta, const char* matrix_file,
                  rmgpu_result** out) {
   *out = nullptr;
+  // RMGPU_SERVER=<unix socket>: hand the search to a persistent rmgpu_server (library resident in HBM, no CUDA context
+  // in this process -- RepeatMasker forks one short-lived child per batch, RepeatMasker:1043)
+  if (const char* sock = getenv("RMGPU_SERVER"))
+    if (*sock) {
+      std::string err;
+      int rc = rmgpu::remote_search(sock, p, query_fasta, subject_fasta, matrix_file, out, err);
+      g_last_error = err;
+      return rc;
+    }
   rmgpu_session* s = rmgpu_session_open(p->device);
   if (!s) return 1;
   int rc = rmgpu_session_set_matrix_file(s, matrix_file);
@@ -1515,13 +1516,23 @@ int rmgpu_search(const rmgpu_params* p, const char* query_fasta, const char* sub
   return rc;
 }
 
+int rmgpu_server_ping(const char* socket_path) {
+  std::string err;
+  int rc = rmgpu::remote_command(socket_path, rmgpu::kWirePing, err);
+  g_last_error = err;
+  return rc;
+}
+int rmgpu_server_quit(const char* socket_path) {
+  std::string err;
+  int rc = rmgpu::remote_command(socket_path, rmgpu::kWireQuit, err);
+  g_last_error = err;
+  return rc;
+}
+
 void rmgpu_free(rmgpu_result* r) {
   if (!r) return;
   delete[] r->hits;
-  struct Arena {
-    std::vector<std::unique_ptr<char[]>> blocks;
-  };
-  delete reinterpret_cast<Arena*>(r->opaque);
+  delete reinterpret_cast<ResultArena*>(r->opaque);
   delete r;
 }
 

@@ -1,6 +1,8 @@
 // host.hpp -- host-side data model of librmgpu (C++17).  No oracle code is used anywhere in this directory.
 #pragma once
 #include <cstdint>
+#include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -47,5 +49,18 @@ std::string revcomp_letters(const std::string& s);
 
 // SearchResult.pm:2111-2150 in double precision, perl int() truncation.
 int complexity_adjust(int raw, const int64_t counts[kMaxAlpha], const ScoreMatrix& m);
+
+// Owner of the strings an rmgpu_result points to (rmgpu_result::opaque).
+struct ResultArena {
+  std::vector<std::unique_ptr<char[]>> blocks;
+  const char* dup(const char* p, size_t n) {
+    std::unique_ptr<char[]> b(new char[n + 1]);
+    if (n) memcpy(b.get(), p, n);
+    b[n] = 0;
+    blocks.push_back(std::move(b));
+    return blocks.back().get();
+  }
+  const char* dup(const std::string& s) { return dup(s.data(), s.size()); }
+};
 
 }  // namespace rmgpu

@@ -52,7 +52,8 @@ _lib = None
 EXPORTS = ["rmgpu_version", "rmgpu_abi_version", "rmgpu_last_error", "rmgpu_search", "rmgpu_free",
            "rmgpu_session_open", "rmgpu_session_close", "rmgpu_session_set_matrix_file", "rmgpu_session_set_library",
            "rmgpu_session_set_library_fasta", "rmgpu_session_set_queries", "rmgpu_session_set_queries_fasta",
-           "rmgpu_session_search", "rmgpu_session_score_only", "rmgpu_session_counts", "rmgpu_measure_dpx_peak"]
+           "rmgpu_session_search", "rmgpu_session_score_only", "rmgpu_session_counts", "rmgpu_measure_dpx_peak",
+           "rmgpu_server_ping", "rmgpu_server_quit"]
 
 
 def lib():
@@ -81,6 +82,8 @@ def lib():
     L.rmgpu_session_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)]
     L.rmgpu_measure_dpx_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.rmgpu_server_ping.argtypes = [C.c_char_p]
+    L.rmgpu_server_quit.argtypes = [C.c_char_p]
     _lib = L
     return L
 
@@ -180,6 +183,49 @@ def search_files(query, subject, matrix, **kw):
         return _hits_to_dicts(res)
     finally:
         lib().rmgpu_free(res)
+
+
+SERVER_BIN = os.path.join(HERE, "rmgpu_server")
+
+
+class Server:
+    """Context manager around the persistent worker process (rmgpu_server): `with Server(sock, gpus=[0]) as s: ...`
+    While it is open, RMGPU_SERVER points at it, so rmgpu_search() / search_files() / GpuSearchEngine.search() in this
+    process and in its children run as thin clients."""
+
+    def __init__(self, socket_path, gpus=(0,)):
+        self.socket_path, self.gpus, self.proc, self._old = socket_path, list(gpus), None, None
+
+    def __enter__(self):
+        import subprocess
+        import time
+
+        self.proc = subprocess.Popen([SERVER_BIN, "--socket", self.socket_path, "--gpus", ",".join(map(str, self.gpus))],
+                                     stderr=subprocess.PIPE, text=True)
+        for _ in range(200):
+            if os.path.exists(self.socket_path) and lib().rmgpu_server_ping(self.socket_path.encode()) == 0:
+                break
+            if self.proc.poll() is not None:
+                raise RmgpuError("rmgpu_server exited: " + self.proc.stderr.read())
+            time.sleep(0.05)
+        else:
+            raise RmgpuError("rmgpu_server did not come up")
+        self._old = os.environ.get("RMGPU_SERVER")
+        os.environ["RMGPU_SERVER"] = self.socket_path
+        return self
+
+    def __exit__(self, *exc):
+        if self._old is None:
+            os.environ.pop("RMGPU_SERVER", None)
+        else:
+            os.environ["RMGPU_SERVER"] = self._old
+        try:
+            lib().rmgpu_server_quit(self.socket_path.encode())
+            self.proc.wait(timeout=20)
+        except Exception:
+            self.proc.kill()
+        self.log = self.proc.stderr.read()
+        return False
 
 
 def measure_dpx_peak(device=-1):

@@ -55,3 +55,37 @@ def test_python_mirror_croaks_like_reference(tmp_path):
     with pytest.raises(engine.RmgpuError, match="does not exist"):
         e.getParameters()
     assert e.setMinScore(225) is None and e.getMinScore() == 225
+
+
+def test_persistent_worker_protocol_without_gpu(tmp_path):
+    """rmgpu_server comes up, answers ping, relays a search request and its error text over the wire, and quits.
+    (On the CPU box the search itself fails loudly -- no CUDA device -- which is exactly what must travel back.)"""
+    import torch
+
+    from repeatmasker_b200 import synth
+
+    rm_build.build()
+    q, s_, m = str(tmp_path / "q.fa"), str(tmp_path / "s.fa"), str(tmp_path / "m.matrix")
+    synth.write_fasta(q, ["q"], ["ACGTACGTAGCTAGCTAGCTAGCATCGATCGATCG"])
+    synth.write_fasta(s_, ["s"], ["ACGTACGTAGCTAGCTAGCTAGCATCGATCGATCG"])
+    util.write_matrix("20p43g.matrix", m)
+    sock = str(tmp_path / "rmgpu.sock")
+    with engine.Server(sock) as srv:
+        assert engine.lib().rmgpu_server_ping(sock.encode()) == 0
+        assert os.environ["RMGPU_SERVER"] == sock
+        if torch.cuda.is_available():
+            hits, st = engine.search_files(q, s_, m, minscore=100)
+            assert len(hits) == 1
+            with pytest.raises(engine.RmgpuError, match="does not exist"):
+                engine.search_files(q, str(tmp_path / "missing.fa"), m)
+        else:
+            with pytest.raises(engine.RmgpuError, match="no CUDA device"):
+                engine.search_files(q, s_, m, minscore=100)
+    assert "RMGPU_SERVER" not in os.environ
+    assert srv.proc.returncode == 0
+    with pytest.raises(engine.RmgpuError, match="cannot reach rmgpu_server"):
+        os.environ["RMGPU_SERVER"] = sock
+        try:
+            engine.search_files(q, s_, m)
+        finally:
+            del os.environ["RMGPU_SERVER"]
