@@ -79,6 +79,14 @@ struct Reader {
   }
 };
 
+// the server does not share the client's working directory
+std::string absolutize(const char* path) {
+  if (!path || path[0] == '/' || path[0] == 0) return path ? path : "";
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof(cwd))) return path;
+  return std::string(cwd) + "/" + path;
+}
+
 int connect_unix(const char* path, std::string& err) {
   int fd = ::socket(AF_UNIX, SOCK_STREAM, 0);
   if (fd < 0) {
@@ -171,9 +179,9 @@ int remote_search(const char* socket_path, const rmgpu_params* p, const char* qu
   std::vector<uint8_t> req;
   put_u32(req, kWireSearch);
   put(req, p, sizeof(*p));
-  put_str(req, query);
-  put_str(req, subject);
-  put_str(req, matrix);
+  put_str(req, absolutize(query).c_str());
+  put_str(req, absolutize(subject).c_str());
+  put_str(req, absolutize(matrix).c_str());
   int32_t status = 1;
   uint32_t elen = 0;
   uint64_t blen = 0;
