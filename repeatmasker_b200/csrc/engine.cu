@@ -78,6 +78,8 @@ struct EventTimer {
   }
 };
 
+constexpr int64_t kCheckpointBudget = 48ll << 30;  // K1 column checkpoints: at most this many bytes per pass
+
 static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -186,7 +188,9 @@ struct rmgpu_session {
                   const std::vector<unsigned long long>& hotmask, std::vector<Candidate>& cands, rmgpu_stats& st);
   void run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands, std::vector<std::vector<uint8_t>>& ops,
                      rmgpu_stats& st);
-  rmgpu_result* search(const rmgpu_params& p);
+  rmgpu_result* search(const rmgpu_params& p);        // whole resident batch, in memory-bounded chunks of queries
+  rmgpu_result* search_batch(const rmgpu_params& p);  // one chunk: K1 -> K2 -> K3 -> host post
+  int query_capacity() const;
 };
 
 // -------------------------------------------------------------------------------------------------------------
@@ -521,7 +525,7 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   {
     static const bool noCk = getenv("RMGPU_NO_CHECKPOINTS") != nullptr;
     const int64_t ckElems = (int64_t)nQ * 64 * nGroups * R;
-    ckEnabled = !noCk && ckElems * (int64_t)sizeof(uint2) <= (24ll << 30);
+    ckEnabled = !noCk && ckElems * (int64_t)sizeof(uint2) <= kCheckpointBudget;
     a.ck = ckEnabled ? d_ck.ensure((size_t)ckElems) : nullptr;
     a.ckRows = (int64_t)nGroups * R;
   }
@@ -1176,7 +1180,70 @@ struct IntervalUnion {  // disjoint, merged closed intervals
 
 }  // namespace
 
+// How many query records one pass may hold: the K1 column checkpoints (64 x rows x 8 B per query) and the stripe
+// boundary ring (up to stripes x columns x 8 B per query) must fit in a share of the free HBM.
+int rmgpu_session::query_capacity() const {
+  size_t freeB = 0, totalB = 0;
+  if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) return 1 << 30;
+  static const char* capEnv = getenv("RMGPU_QUERY_CHUNK");
+  if (capEnv && atoi(capEnv) > 0) return atoi(capEnv);
+  const double budget = 0.45 * (double)(freeB + d_ck.cap * sizeof(uint2) + d_bnd1.cap * 8);
+  const double perQuery = 64.0 * nGroups * R * 8.0 + (double)nStripes * ((double)maxQ + 64.0) * 8.0;
+  const double byCk = (double)kCheckpointBudget / std::max(64.0 * nGroups * R * 8.0, 1.0);
+  return (int)std::max(1.0, std::floor(std::min(budget / std::max(perQuery, 1.0), byCk)));
+}
+
 rmgpu_result* rmgpu_session::search(const rmgpu_params& p) {
+  if (!haveMatrix || !haveLib || !haveQueries) throw Error("matrix, library and queries must be set before searching");
+  const int nQ = (int)queries.seqs.size();
+  const int cap = query_capacity();
+  if (nQ <= cap) return search_batch(p);
+  // too many query records for one pass: run the pipeline chunk by chunk and merge (records are independent units)
+  SeqSet all = std::move(queries);
+  auto* res = new rmgpu_result();
+  memset(res, 0, sizeof(*res));
+  auto* arena = new ResultArena();
+  res->opaque = arena;
+  std::vector<rmgpu_hit> hits;
+  try {
+    for (int q0 = 0; q0 < nQ; q0 += cap) {
+      const int q1 = std::min(nQ, q0 + cap);
+      SeqSet sub;
+      sub.names.assign(all.names.begin() + q0, all.names.begin() + q1);
+      sub.seqs.assign(all.seqs.begin() + q0, all.seqs.begin() + q1);
+      set_queries(std::move(sub));
+      rmgpu_result* part = search_batch(p);
+      for (int i = 0; i < part->n_hits; i++) {
+        rmgpu_hit h = part->hits[i];
+        h.query_index += q0;
+        hits.push_back(h);
+      }
+      const rmgpu_stats& a = part->stats;
+      rmgpu_stats& b = res->stats;
+      b.cells += a.cells; b.ms_total += a.ms_total; b.ms_h2d += a.ms_h2d; b.ms_d2h += a.ms_d2h; b.ms_score += a.ms_score;
+      b.ms_origin += a.ms_origin; b.ms_traceback += a.ms_traceback; b.ms_host_post += a.ms_host_post;
+      b.h2d_bytes += a.h2d_bytes; b.d2h_bytes += a.d2h_bytes; b.launches += a.launches; b.score_launches += a.score_launches;
+      b.n_pairs_passed += a.n_pairs_passed; b.n_candidates += a.n_candidates; b.origin_cells += a.origin_cells;
+      b.n_origin_redo += a.n_origin_redo;
+      arena->children.emplace_back(reinterpret_cast<ResultArena*>(part->opaque));
+      delete[] part->hits;
+      delete part;
+    }
+  } catch (...) {
+    queries = std::move(all);
+    haveQueries = false;  // the device holds a partial batch: force a fresh set_queries
+    delete arena;
+    delete res;
+    throw;
+  }
+  set_queries(std::move(all));
+  res->n_hits = (int32_t)hits.size();
+  res->hits = hits.empty() ? nullptr : new rmgpu_hit[hits.size()];
+  if (!hits.empty()) memcpy(res->hits, hits.data(), hits.size() * sizeof(rmgpu_hit));
+  return res;
+}
+
+rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
   if (!haveMatrix || !haveLib || !haveQueries) throw Error("matrix, library and queries must be set before searching");
   if (p.minscore < 1) throw Error("minscore must be >= 1");
   const double t_begin = now_ms();

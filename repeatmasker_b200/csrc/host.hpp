@@ -53,6 +53,7 @@ int complexity_adjust(int raw, const int64_t counts[kMaxAlpha], const ScoreMatri
 // Owner of the strings an rmgpu_result points to (rmgpu_result::opaque).
 struct ResultArena {
   std::vector<std::unique_ptr<char[]>> blocks;
+  std::vector<std::unique_ptr<ResultArena>> children;  // arenas of merged partial results
   const char* dup(const char* p, size_t n) {
     std::unique_ptr<char[]> b(new char[n + 1]);
     if (n) memcpy(b.get(), p, n);

@@ -1,6 +1,6 @@
 """The fallback paths of the origin pass must give the same hits as the default (windowed, checkpointed) path:
 RMGPU_K2_FULL=1 sweeps every passing triple with origins over the whole fragment; RMGPU_NO_CHECKPOINTS=1 uses the
-score-only / origin mode mask from column 0.  The switches are read once per process, hence the subprocesses."""
+score-only / origin mode mask from column 0; RMGPU_QUERY_CHUNK=2 forces the memory-bounded chunking of query records.  The switches are read once per process, hence the subprocesses."""
 import os
 import subprocess
 import sys
@@ -12,9 +12,9 @@ import util
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("var", ["RMGPU_K2_FULL", "RMGPU_NO_CHECKPOINTS"])
-def test_origin_pass_fallbacks_match_oracle(var):
-    env = dict(os.environ, **{var: "1"})
+@pytest.mark.parametrize("var,val", [("RMGPU_K2_FULL", "1"), ("RMGPU_NO_CHECKPOINTS", "1"), ("RMGPU_QUERY_CHUNK", "2")])
+def test_origin_pass_fallbacks_match_oracle(var, val):
+    env = dict(os.environ, **{var: val})
     res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
                           os.path.join(util.ROOT, "tests", "test_gpu_parity.py"), "-k",
                           "synthetic_genome_full_parity or long_subject_chains or kat_seq1_2 or alphabet"],
