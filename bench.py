@@ -275,7 +275,7 @@ def main():
                     "mbp_per_s": Q * world * args.steps / t_e2e_max / 1e6,
                     "what": "Session.set_library + set_queries (host buffers -> HBM) + search (records back on the host) per step"},
             "gpu_launches": int(sum(s["launches"] for s in st_res)),
-            "roofline": {"bound": "int-simd (DPX VIADDMNMX/VIMNMX3 16x2); not hbm, not tensor", "kernel": "swg_score_kernel<16>",
+            "roofline": {"bound": "int-simd (DPX VIADDMNMX/VIMNMX3 16x2); not hbm, not tensor", "kernel": "swg_score_kernel<16,false>",
                          "achieved": achieved, "peak": peak_cups / 1e9, "unit": "GCUPS", "frac": achieved / (peak_cups / 1e9),
                          "peak_source": "rmgpu_measure_dpx_peak: register-resident loop of the same recurrence, measured live on this GPU",
                          "traffic": traffic_from_profile(cells_step), "k1_ms_per_launch": k1_ms, "dpx_warp_instr_per_s": dpx_ips,
