@@ -78,6 +78,7 @@ struct EventTimer {
   }
 };
 
+constexpr int kPackRunStripes = 4;  // library packing: subjects are laid end to end in runs of at most this many stripes
 constexpr int64_t kCheckpointBudget = 48ll << 30;  // K1 column checkpoints: at most this many bytes per pass
 
 static double now_ms() {
@@ -194,50 +195,49 @@ struct rmgpu_session {
 };
 
 // -------------------------------------------------------------------------------------------------------------
-// Library packing: subjects -> groups of R rows -> stripes of 32 groups.  A subject longer than one stripe owns
-// consecutive stripes starting at lane 0; the free lanes of its last stripe and all remaining stripes are filled
-// first-fit-decreasing with subjects that fit entirely, so only genuinely long subjects create stripe chains.
+// Library packing: subjects -> groups of R rows -> stripes of 32 groups.  Subjects are laid end to end in "runs": a run
+// starts at lane 0 of a fresh stripe and every subject in it starts at the group after the previous one, so a stripe
+// may hold the tail of one subject and the head of the next (the kernel resets the column state at a group that
+// starts a subject; the boundary it reads at lane 0 and the one it writes at lane 31 then belong to different
+// subjects).  Runs are filled best-fit-decreasing up to kPackRunStripes stripes, which leaves < 1 % of padded rows
+// instead of the ~8 % of one-subject-per-chain packing, while the dependency chains (consecutive stripes that
+// share a subject) stay short.  A subject longer than a run is a run of its own; the free lanes of its last
+// stripe are filled with subjects that fit entirely.
 // -------------------------------------------------------------------------------------------------------------
 void rmgpu_session::set_library(SeqSet s) {
   if (!haveMatrix) throw Error("set the matrix before the library");
   lib = std::move(s);
   const int n = (int)lib.seqs.size();
-  std::vector<int> order(n), groups(n);
+  std::vector<int> groups(n);
+  std::multimap<int, int> pool;  // groups -> subject, the subjects not yet placed
   for (int i = 0; i < n; i++) {
     if (lib.seqs[i].size() >= (1u << 20)) throw Error("subject longer than 1,048,575 bases: " + lib.names[i]);
     groups[i] = (int)((lib.seqs[i].size() + R - 1) / R);
+    if (groups[i] > 0) pool.insert({groups[i], -i});  // -i: among equal sizes the lowest index is the last element
   }
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a] > groups[b]; });
+  static const int capStripes = getenv("RMGPU_PACK_RUN") ? std::max(1, atoi(getenv("RMGPU_PACK_RUN"))) : kPackRunStripes;
+  const int cap = capStripes * 32;
   struct Place {
     int subject, firstGroup;
   };
   std::vector<Place> places;
-  std::vector<std::pair<int, int>> open;  // (stripe, free lanes) for stripes with room at the tail
   int stripes = 0;
-  for (int idx : order) {
-    int g = groups[idx];
-    if (g == 0) continue;
-    int found = -1;
-    if (g < 32)
-      for (size_t o = 0; o < open.size(); o++)
-        if (open[o].second >= g) {
-          found = (int)o;
-          break;
-        }
-    if (found >= 0) {
-      int stripe = open[found].first, freeL = open[found].second;
-      places.push_back({idx, stripe * 32 + (32 - freeL)});
-      open[found].second -= g;
-      if (open[found].second == 0) open.erase(open.begin() + found);
-    } else {
-      int ns = (g + 31) / 32;
-      places.push_back({idx, stripes * 32});
-      int rem = ns * 32 - g;
-      if (rem > 0) open.push_back({stripes + ns - 1, rem});
-      stripes += ns;
-      if (open.size() > 4096) open.erase(open.begin());  // bound the first-fit scan
+  while (!pool.empty()) {
+    auto last = std::prev(pool.end());  // largest subject left opens a run
+    int total = last->first;
+    places.push_back({-last->second, stripes * 32});
+    pool.erase(last);
+    for (;;) {
+      // room: up to the run capacity, or (oversize subject) up to the end of its last stripe
+      const int room = total <= cap ? cap - total : (32 - total % 32) % 32;
+      auto it = pool.upper_bound(room);  // first subject that does NOT fit
+      if (it == pool.begin()) break;
+      --it;
+      places.push_back({-it->second, stripes * 32 + total});
+      total += it->first;
+      pool.erase(it);
     }
+    stripes += (total + 31) / 32;
   }
   nStripes = std::max(stripes, 1);
   nGroups = nStripes * 32;
@@ -533,8 +533,8 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   static const bool dbgOn = getenv("RMGPU_DEBUG_K1") != nullptr;
   a.dbg = nullptr;
   if (dbgOn) {
-    a.dbg = d_dbg.ensure(4);
-    CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 32, stream));
+    a.dbg = d_dbg.ensure(8);
+    CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 64, stream));
   }
   CUDA_CHECK(cudaMemsetAsync(a.pairbest, 0, pairbest.size() * sizeof(int32_t), stream));
   CUDA_CHECK(cudaMemsetAsync(a.hotmask, 0, hotmask.size() * sizeof(unsigned long long), stream));
@@ -557,10 +557,15 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   ms = tm.ms();
   launches += 2;
   if (dbgOn) {
-    unsigned long long d[4];
-    CUDA_CHECK(cudaMemcpy(d, a.dbg, 32, cudaMemcpyDeviceToHost));
+    unsigned long long d[8];
+    CUDA_CHECK(cudaMemcpy(d, a.dbg, 64, cudaMemcpyDeviceToHost));
+    int64_t rows = 0;
+    for (auto& sq : lib.seqs) rows += (int64_t)sq.size();
     fprintf(stderr, "[K1 dbg] tasks %llu  producer-wait %.1f%% of task cycles  slot-wait %.2e cyc  mean task %.0f cyc  grid %d nslot %d\n", d[2],
             100.0 * (double)d[0] / (double)std::max(d[3], 1ull), (double)d[1], (double)d[3] / (double)std::max(d[2], 1ull), grid, nslot);
+    fprintf(stderr, "[K1 dbg] stripes %d  padded rows %.2f%%  warp busy until exit: mean %.1f%% of the last warp's (%.2f ms)  kernel %.2f ms\n", nStripes,
+            100.0 * ((double)nStripes * 32 * R - (double)rows) / (double)std::max<int64_t>(rows, 1),
+            100.0 * (double)d[4] / ((double)warps * (double)std::max(d[5], 1ull)), (double)d[5] * 1e-6, ms);
   }
 }
 

@@ -37,6 +37,11 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 }
 // prmt.b32 in its generic form: selector nibble bit 3 replicates the sign of the selected byte.  (__byte_perm masks
 // the selector with 0x7777, which would drop exactly that bit.)
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
 __device__ __forceinline__ uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t sel) {
   uint32_t d;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
@@ -164,7 +169,8 @@ struct ScoreArgs {
   int* abort_flag;            // set by the watchdog
   uint2* ck;                  // optional column checkpoints [(q*64 + cb) * ckRows + g*R + r] = (H, E') before column cb*CB
   int64_t ckRows;             // nGroups * R
-  unsigned long long* dbg;    // optional [4]: cycles waiting on the producer, cycles waiting on a slot, tasks, task cycles
+  unsigned long long* dbg;    // optional [8]: cycles waiting on the producer, cycles waiting on a slot, tasks, task cycles,
+                              // sum and max over warps of (exit time - first warp's start) in ns, -, base time
 };
 
 // Boundary elements are single 64-bit words {H | F' << 32}; every 16-bit half is < 32768, so bit 15 of each half is
@@ -199,6 +205,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
   __shared__ uint2 s_out[kScoreWarps][32];   // last row's (H, F') of the last 32 columns lane 31 finished
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nTickets = a.nQueries * a.nStripes;
+  if (a.dbg && lane == 0) atomicCAS(&a.dbg[7], 0ull, globaltimer_ns());  // time base: the first warp to get here
   for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(a.ticket, 1);
@@ -386,6 +393,11 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
         atomicAdd(&a.dbg[3], (unsigned long long)(clock64() - task0));
       }
     }
+  }
+  if (a.dbg && lane == 0) {
+    const unsigned long long dt = globaltimer_ns() - *(volatile unsigned long long*)&a.dbg[7];
+    atomicAdd(&a.dbg[4], dt);
+    atomicMax(&a.dbg[5], dt);
   }
 }
 
