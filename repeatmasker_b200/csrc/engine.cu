@@ -78,6 +78,7 @@ struct EventTimer {
   }
 };
 
+constexpr int kTraceAttempts = 2;  // band widths K3 tries per launch (W, 2W) before the host reschedules a candidate
 constexpr int kPackRunStripes = 4;  // library packing: subjects are laid end to end in runs of at most this many stripes
 constexpr int64_t kCheckpointBudget = 48ll << 30;  // K1 column checkpoints: at most this many bytes per pass
 
@@ -619,6 +620,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   for (int i = 0; i < 16; i++)
     for (int j = 0; j < 16; j++) h_mat[i][j] = (i < matrix.n && j < matrix.n) ? matrix.score[i][j] : -128;
 
+  static const bool dbgK2 = getenv("RMGPU_DEBUG_K2") != nullptr;
+  const double k2t0 = now_ms();
   int chainCtas = 0;  // CTAs the concurrent fallback sweep needs resident
   std::atomic<int> chainLaunched{0};  // set once the fallback sweep's kernel is in its stream (or there is none)
   // ------------------------------------------------------------------ block-parallel path
@@ -781,13 +784,16 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       int overflow = 0;
       std::vector<int> redoFlag(triples.size(), 0);
       std::vector<unsigned long long> keys(ftableSize), vals(ftableSize);
+      CUDA_CHECK(cudaStreamSynchronize(stream));  // as in run_chain: never block inside a pageable copy while the other path launches
       CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
       CUDA_CHECK(cudaMemcpyAsync(redoFlag.data(), r.redo, triples.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
       CUDA_CHECK(cudaMemcpyAsync(keys.data(), r.fkeys, ftableSize * 8, cudaMemcpyDeviceToHost, stream));
       CUDA_CHECK(cudaMemcpyAsync(vals.data(), r.fvals, ftableSize * 8, cudaMemcpyDeviceToHost, stream));
       CUDA_CHECK(cudaStreamSynchronize(stream));
       check_abort("K2b");
-      (void)tm;
+      if (dbgK2)
+        fprintf(stderr, "[K2 dbg] blocks: %zu triples %zu tasks %d tickets grid %d  kernels %.2f ms (done at +%.2f ms)\n", trIdx.size(),
+                tasks.size(), nTickets, grid, tm.ms(), now_ms() - k2t0);
       st.launches += 2;
       st.d2h_bytes += (int64_t)ftableSize * 16;
       if (overflow) {  // a probe sequence got long in one of the two tables
@@ -924,6 +930,9 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         CUDA_CHECK(cudaGetLastError());
         std::vector<unsigned long long> keys(tableSize), vals(tableSize);
         int overflow = 0;
+        // wait for the sweep BEFORE issuing the downloads: a copy into pageable memory blocks inside the driver until
+        // the stream reaches it, and while it does the other thread's launches are held back (the two paths serialise)
+        CUDA_CHECK(cudaStreamSynchronize(stream2));
         CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream2));
         CUDA_CHECK(cudaMemcpyAsync(leftFlag.data(), a.leftFlag, tasks.size() * sizeof(int), cudaMemcpyDeviceToHost, stream2));
         CUDA_CHECK(cudaMemcpyAsync(keys.data(), a.keys, tableSize * 8, cudaMemcpyDeviceToHost, stream2));
@@ -931,6 +940,9 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         CUDA_CHECK(cudaStreamSynchronize(stream2));
         check_abort_on("K2", a.abort_flag, stream2);
         chainMs += tm.ms();
+        if (dbgK2)
+          fprintf(stderr, "[K2 dbg] chain: %zu triples %d tickets R=%d grid %d round %d  kernel %.2f ms (done at +%.2f ms)\n", trIdx.size(),
+                  nTickets, chainR, grid, round, tm.ms(), now_ms() - k2t0);
         chainLaunches += 1;
         chainD2H += (int64_t)tableSize * 16;
         if (overflow) {
@@ -979,7 +991,6 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   chainCtas = std::min((chainCtas + 3) / 4, numSMs * 2);
   // the fallback sweeps are long and narrow (a few warps busy for tens of ms): run them on a second stream from a
   // second host thread while the block-parallel path fills the machine
-  const double k2t0 = now_ms();
   std::exception_ptr chainErr;
   std::thread chainThread([&] {
     try {
@@ -1062,7 +1073,10 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
         const Candidate& c = cands[todo[at]];
         int n = c.i1 - c.i0 + 1, m = c.j1 - c.j0 + 1, w = W[todo[at]];
         int64_t bw = (int64_t)std::abs(n - m) + 2 * (int64_t)w + 1;
-        int64_t dirBytes = (int64_t)(n + 1) * bw;
+        // the kernel itself retries once with the doubled band (same schedule, no second launch for the few that
+        // need it): the scratch is sized for that last attempt
+        const int64_t bwLast = (int64_t)std::abs(n - m) + 2 * ((int64_t)w << (kTraceAttempts - 1)) + 1;
+        int64_t dirBytes = (int64_t)(n + 1) * bwLast;
         if (!tc.empty() && (dirTot + dirBytes > kDirBudget || (band_of(ids[0]) > 64) != (bw > 64))) break;
         TraceCand t;
         t.q = c.q;
@@ -1074,11 +1088,12 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
         t.j1 = c.j1;
         t.raw = c.raw;
         t.W = w;
+        t.attempts = kTraceAttempts;
         t.dirOff = dirTot;
         t.rowOff = rowTot;
         t.opsOff = opsTot;
         dirTot += dirBytes;
-        rowTot += 3 * bw;
+        rowTot += 3 * bwLast;
         opsTot += n + m;
         tc.push_back(t);
         ids.push_back(todo[at]);
@@ -1106,7 +1121,7 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
       EventTimer tm;
       tm.start(stream);
       if (band_of(ids[0]) > 64)
-        traceback_kernel<true><<<(int)tc.size(), kTraceWarps * 32, 0, stream>>>(a);
+        traceback_kernel<true><<<(int)tc.size(), kTraceBlockThreads, 0, stream>>>(a);
       else
         traceback_kernel<false><<<((int)tc.size() + kTraceWarps - 1) / kTraceWarps, kTraceWarps * 32, 0, stream>>>(a);
       tm.stop(stream);
@@ -1119,6 +1134,19 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
       st.ms_traceback += tm.ms();
       st.launches += 1;
       st.d2h_bytes += opsTot + (int64_t)tc.size() * 4;
+      static const bool dbgK3 = getenv("RMGPU_DEBUG_K3") != nullptr;
+      if (dbgK3) {
+        int maxN = 0, failed = 0;
+        int64_t maxBand = 0, longBand = 0;
+        for (size_t i = 0; i < tc.size(); i++) {
+          const int n = tc[i].i1 - tc[i].i0 + 1;
+          if (n > maxN) maxN = n, longBand = band_of(ids[i]);
+          maxBand = std::max(maxBand, band_of(ids[i]));
+          failed += hlen[i] <= 0;
+        }
+        fprintf(stderr, "[K3 dbg] %s launch: %zu candidates, %.2f ms, longest %d rows (band %lld), widest band %lld, %d to retry, dir bytes %.1f MB\n",
+                band_of(ids[0]) > 64 ? "block" : "warp", tc.size(), tm.ms(), maxN, (long long)longBand, (long long)maxBand, failed, dirTot / 1e6);
+      }
       for (size_t i = 0; i < tc.size(); i++) {
         int id = ids[i];
         if (hlen[i] > 0) {
@@ -1128,7 +1156,7 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
           const Candidate& c = cands[id];
           int full = std::max(c.i1 - c.i0 + 1, c.j1 - c.j0 + 1);
           if (W[id] >= full) throw Error("traceback could not reproduce the forward score");
-          W[id] *= 2;
+          W[id] <<= kTraceAttempts;
           next.push_back(id);
         }
       }

@@ -1091,9 +1091,10 @@ struct TraceCand {
   int32_t q, strand, subject;
   int32_t i0, j0, i1, j1;   // 1-based, strand coordinates
   int32_t raw;
-  int32_t W;                // band half-width for this attempt
+  int32_t W;                // band half-width of the first attempt
+  int32_t attempts;         // attempts made inside the kernel, W doubling each time (scratch is sized for the last)
   int64_t dirOff;           // offset into dir scratch
-  int64_t rowOff;           // offset into row scratch (4 * bw ints)
+  int64_t rowOff;           // offset into row scratch (3 * bw ints)
   int64_t opsOff;           // offset into ops
 };
 
@@ -1111,169 +1112,225 @@ struct TraceArgs {
   int32_t* rows;
   uint8_t* ops;
   int32_t* opsLen;   // [nCand] number of ops, or -1
-  int32_t* status;   // [nCand]
+  int32_t* status;   // [nCand] 1 + index of the attempt that succeeded, 0 if none did
 };
 
 // Band cell (u, k) (k = d - dlo, v = u - dlo - k) depends on (u-1, k-1) [E], (u-1, k) [D] and (u, k+1) [F]; all
-// cells with the same w = 2u - k are independent, so a team of T threads (one warp for narrow bands, a 128-thread
-// block for wide ones) sweeps waves w, thread l owning k = 2l (+parity), 2l + 2T, ...  H/E/F live in place in
-// shared memory (global scratch when the band is wider than the shared buffer); entries of parity w hold wave w-2
-// (the diagonal source), the others wave w-1.
+// cells with the same w = 2u - k are independent, so a team of T threads (one warp for narrow bands, up to 512
+// threads of a block for wide ones: one thread per cell of a wave) sweeps waves w, thread l owning k = 2l (+parity),
+// 2l + 2T, ...  H/E/F live in place in shared memory (global scratch when the band is wider than the shared
+// buffer), even and odd k in separate halves so that a wave's accesses are unit-stride; entries of parity w hold
+// wave w-2 (the diagonal source), the others wave w-1.  The walk back is done by lane 0 of the team's first warp on
+// a 32 x 32 window of direction bytes that the warp refills with 32 independent loads, instead of one dependent
+// global load per step.
 constexpr int kTraceWarpBand = 256;    // ints per array per warp in warp mode
-constexpr int kTraceWarps = 4;
+constexpr int kTraceWarps = 4;         // warps (= candidates) per block in warp mode
+constexpr int kTraceBlockThreads = 512;  // block mode: threads per candidate (the team is sized to the band)
 constexpr int kTraceBlockBand = 2048;  // ints per array in block mode
 constexpr int kTraceSeqBlock = 10240;  // query / subject bytes of a candidate staged in shared memory (block mode)
 constexpr int kTraceSeqWarp = 1024;    // the same per warp in warp mode
 
 template <bool BLOCK>
-__global__ void __launch_bounds__(kTraceWarps * 32) traceback_kernel(TraceArgs a) {
-  constexpr int T = BLOCK ? kTraceWarps * 32 : 32;
+__global__ void __launch_bounds__(BLOCK ? kTraceBlockThreads : kTraceWarps * 32) traceback_kernel(TraceArgs a) {
   constexpr int SB = BLOCK ? kTraceBlockBand : kTraceWarpBand;
   constexpr int SQ = BLOCK ? kTraceSeqBlock : kTraceSeqWarp;
+  constexpr int NT = BLOCK ? 1 : kTraceWarps;  // candidates per block
   __shared__ int32_t smat[16 * 16];
-  __shared__ int32_t sband[BLOCK ? 1 : kTraceWarps][3][SB];
-  __shared__ uint8_t sseq[BLOCK ? 1 : kTraceWarps][2][SQ];
+  __shared__ int32_t sband[NT][3][SB];
+  __shared__ uint8_t sseq[NT][2][SQ];
+  __shared__ uint8_t swin[NT][32][32];
+  __shared__ int s_len[NT];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
   __syncthreads();
   const int tid = BLOCK ? threadIdx.x : (threadIdx.x & 31);
+  const int lane = threadIdx.x & 31;
   const int wib = BLOCK ? 0 : (threadIdx.x >> 5);
   const int c = BLOCK ? blockIdx.x : blockIdx.x * kTraceWarps + wib;
-  if (c >= a.nCand) return;
-  auto team_sync = [&]() {
-    if (BLOCK)
-      __syncthreads();
-    else
-      __syncwarp();
-  };
+  if (c >= a.nCand) return;  // whole block (block mode) or whole warp (warp mode)
+  const int TALL = BLOCK ? kTraceBlockThreads : 32;
   const TraceCand tc = a.cand[c];
   const int NEGI = -(1 << 28);
   const int n = tc.i1 - tc.i0 + 1, m = tc.j1 - tc.j0 + 1;
   const uint8_t* qc = (tc.strand ? a.codes_rc : a.codes_fwd) + a.qoff[tc.q] + (tc.i0 - 1);
   const uint8_t* sc = a.scodes + a.soff[tc.subject] + (tc.j0 - 1);
   if (n <= SQ && m <= SQ) {  // stage both sequences: the waves then never wait on global memory for their residues
-    for (int i = tid; i < n; i += T) sseq[wib][0][i] = qc[i];
-    for (int i = tid; i < m; i += T) sseq[wib][1][i] = sc[i];
+    for (int i = tid; i < n; i += TALL) sseq[wib][0][i] = qc[i];
+    for (int i = tid; i < m; i += TALL) sseq[wib][1][i] = sc[i];
     qc = sseq[wib][0];
     sc = sseq[wib][1];
   }
-  const int dlo = min(0, n - m) - tc.W, dhi = max(0, n - m) + tc.W;
-  const int bw = dhi - dlo + 1;
   uint8_t* dir = a.dir + tc.dirOff;
-  int32_t *Hb, *Eb, *Fb;
-  if (bw <= SB) {
-    Hb = sband[wib][0];
-    Eb = sband[wib][1];
-    Fb = sband[wib][2];
-  } else {
-    Hb = a.rows + tc.rowOff;
-    Eb = Hb + bw;
-    Fb = Eb + bw;
-  }
-  // row u = 0: only (0,0) (d = 0) is reachable
-  for (int k = tid; k < bw; k += T) {
-    Hb[k] = (k == -dlo) ? 0 : NEGI;
-    Eb[k] = NEGI;
-    Fb[k] = NEGI;
-  }
-  team_sync();
-  // waves: u >= 1, 0 <= k < bw  ->  w = 2u - k in [3 - bw, 2n]
-  for (int w = 3 - bw; w <= 2 * n; w++) {
-    // only k with 1 <= (w + k) / 2 <= n matter: k in [2 - w, 2n - w]
-    const int klo = max(0, 2 - w), khi = min(bw - 1, 2 * n - w);
-    for (int k0 = klo & ~1; k0 <= khi; k0 += 2 * T) {
-      const int k = k0 + 2 * tid + (w & 1);
-      const int u = (w + k) >> 1;
-      const int v = u - dlo - k;
-      const bool inBand = k < bw && u >= 1 && u <= n;
-      int hnew = NEGI, enew = NEGI, fnew = NEGI;
-      uint8_t bits = 0;
-      if (inBand && v >= 1 && v <= m) {
-        const int e_src_e = k > 0 ? Eb[k - 1] : NEGI, e_src_h = k > 0 ? Hb[k - 1] : NEGI;
-        const int f_src_f = k + 1 < bw ? Fb[k + 1] : NEGI, f_src_h = k + 1 < bw ? Hb[k + 1] : NEGI;
-        const int hd = Hb[k];
-        int e_ext = e_src_e + a.ins_ext, e_open = e_src_h + a.gap_init;
-        if (e_ext >= e_open) {
-          enew = e_ext;
-          bits |= 4;
-        } else
-          enew = e_open;
-        int f_ext = f_src_f + a.del_ext, f_open = f_src_h + a.gap_init;
-        if (f_ext >= f_open) {
-          fnew = f_ext;
-          bits |= 8;
-        } else
-          fnew = f_open;
-        int D = hd > NEGI / 2 ? hd + smat[(int)sc[v - 1] * 16 + (int)qc[u - 1]] : NEGI;
-        if (u == 1 && v == 1) {
-          enew = NEGI;
-          fnew = NEGI;
-        }
-        hnew = enew;
-        uint8_t ch = 1;
-        if (fnew > hnew) {
-          hnew = fnew;
-          ch = 2;
-        }
-        if (D > hnew) {
-          hnew = D;
-          ch = 3;
-        }
-        if (hnew < NEGI / 2) hnew = NEGI;
-        if (enew < NEGI / 2) enew = NEGI;
-        if (fnew < NEGI / 2) fnew = NEGI;
-        dir[(int64_t)u * bw + k] = bits | ch;
+  int len = -1, used = 0;
+  for (int attempt = 0; attempt < tc.attempts && len <= 0; attempt++) {
+    const int W = tc.W << attempt;
+    const int dlo = min(0, n - m) - W, dhi = max(0, n - m) + W;
+    const int bw = dhi - dlo + 1;
+    const int half = (bw + 1) >> 1;
+    // team: one thread per cell of a wave, whole warps
+    const int T = BLOCK ? min(kTraceBlockThreads, max(32, (half + 31) & ~31)) : 32;
+    auto team_sync = [&]() {
+      if (BLOCK)
+        asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
+      else
+        __syncwarp();
+    };
+    auto ix = [&](int k) { return (k >> 1) + ((k & 1) ? half : 0); };
+    int32_t *Hb, *Eb, *Fb;
+    if (bw <= SB) {
+      Hb = sband[wib][0];
+      Eb = sband[wib][1];
+      Fb = sband[wib][2];
+    } else {
+      Hb = a.rows + tc.rowOff;
+      Eb = Hb + bw;
+      Fb = Eb + bw;
+    }
+    if (tid < T) {
+      // row u = 0: only (0,0) (d = 0) is reachable
+      for (int k = tid; k < bw; k += T) {
+        Hb[ix(k)] = (k == -dlo) ? 0 : NEGI;
+        Eb[ix(k)] = NEGI;
+        Fb[ix(k)] = NEGI;
       }
-      if (inBand) {
-        Hb[k] = hnew;
-        Eb[k] = enew;
-        Fb[k] = fnew;
+      team_sync();
+      // waves: u >= 1, 0 <= k < bw  ->  w = 2u - k in [3 - bw, 2n]
+      for (int w = 3 - bw; w <= 2 * n; w++) {
+        // only k with 1 <= (w + k) / 2 <= n matter: k in [2 - w, 2n - w]
+        const int klo = max(0, 2 - w), khi = min(bw - 1, 2 * n - w);
+        for (int k0 = klo & ~1; k0 <= khi; k0 += 2 * T) {
+          const int k = k0 + 2 * tid + (w & 1);
+          const int u = (w + k) >> 1;
+          const int v = u - dlo - k;
+          const bool inBand = k < bw && u >= 1 && u <= n;
+          int hnew = NEGI, enew = NEGI, fnew = NEGI;
+          uint8_t bits = 0;
+          if (inBand && v >= 1 && v <= m) {
+            const int il = ix(k - 1 < 0 ? 0 : k - 1), ir = ix(k + 1 < bw ? k + 1 : k);
+            const int e_src_e = k > 0 ? Eb[il] : NEGI, e_src_h = k > 0 ? Hb[il] : NEGI;
+            const int f_src_f = k + 1 < bw ? Fb[ir] : NEGI, f_src_h = k + 1 < bw ? Hb[ir] : NEGI;
+            const int hd = Hb[ix(k)];
+            int e_ext = e_src_e + a.ins_ext, e_open = e_src_h + a.gap_init;
+            if (e_ext >= e_open) {
+              enew = e_ext;
+              bits |= 4;
+            } else
+              enew = e_open;
+            int f_ext = f_src_f + a.del_ext, f_open = f_src_h + a.gap_init;
+            if (f_ext >= f_open) {
+              fnew = f_ext;
+              bits |= 8;
+            } else
+              fnew = f_open;
+            int D = hd > NEGI / 2 ? hd + smat[(int)sc[v - 1] * 16 + (int)qc[u - 1]] : NEGI;
+            if (u == 1 && v == 1) {
+              enew = NEGI;
+              fnew = NEGI;
+            }
+            hnew = enew;
+            uint8_t ch = 1;
+            if (fnew > hnew) {
+              hnew = fnew;
+              ch = 2;
+            }
+            if (D > hnew) {
+              hnew = D;
+              ch = 3;
+            }
+            if (hnew < NEGI / 2) hnew = NEGI;
+            if (enew < NEGI / 2) enew = NEGI;
+            if (fnew < NEGI / 2) fnew = NEGI;
+            dir[(int64_t)u * bw + k] = bits | ch;
+          }
+          if (inBand) {
+            const int ik = ix(k);
+            Hb[ik] = hnew;
+            Eb[ik] = enew;
+            Fb[ik] = fnew;
+          }
+        }
+        team_sync();
       }
     }
-    team_sync();
-  }
-  // after the last wave H(n, k) sits in Hb[k] for every k (each k's last in-range wave is row n)
-  const int kend = (n - m) - dlo;
-  int len = -1;
-  if (tid == 0) {
-    if (Hb[kend] == tc.raw && (dir[(int64_t)n * bw + kend] & 3) == 3) {
-      uint8_t* ops = a.ops + tc.opsOff;
+    // after the last wave H(n, k) sits in Hb[k] for every k (each k's last in-range wave is row n)
+    if (tid < 32) {
+      const int kend = (n - m) - dlo;
+      // the direction bytes were written by other threads of the team: make them visible to this warp's loads
+      __threadfence_block();
       int uu = n, vv = m, state = 0, pos = 0;
-      bool ok = true;
-      while (uu > 0 || vv > 0) {
-        if (uu < 1 || vv < 1) {
-          ok = false;
-          break;
+      bool ok = Hb[ix(kend)] == tc.raw && (dir[(int64_t)n * bw + kend] & 3) == 3, done = false;
+      uint8_t* ops = a.ops + tc.opsOff;
+      for (;;) {
+        const int uu0 = __shfl_sync(0xffffffffu, uu, 0), vv0 = __shfl_sync(0xffffffffu, vv, 0);
+        if (__shfl_sync(0xffffffffu, (int)(done || !ok), 0)) break;
+        const int kk0 = (uu0 - vv0) - dlo;
+        const int kbase = max(0, min(kk0 - 16, bw - 32));
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+          const int row = uu0 - r, col = kbase + lane;
+          swin[wib][r][lane] = (row >= 1 && col < bw) ? dir[(int64_t)row * bw + col] : (uint8_t)0;
         }
-        int kk = (uu - vv) - dlo;
-        if (kk < 0 || kk >= bw) {
-          ok = false;
-          break;
+        __syncwarp();
+        if (lane == 0) {
+          for (;;) {
+            if (uu == 0 && vv == 0) {
+              done = true;
+              break;
+            }
+            if (uu < 1 || vv < 1) {
+              ok = false;
+              break;
+            }
+            const int kk = (uu - vv) - dlo;
+            if (kk < 0 || kk >= bw) {
+              ok = false;
+              break;
+            }
+            const int r = uu0 - uu, cc = kk - kbase;
+            if (r > 31 || cc < 0 || cc > 31) break;  // left the window: refill around the current cell
+            const uint8_t bch = swin[wib][r][cc];
+            if (state == 0) {
+              const int ch = bch & 3;
+              if (ch == 3) {
+                ops[pos++] = 0;
+                uu--;
+                vv--;
+              } else if (ch == 1)
+                state = 1;
+              else if (ch == 2)
+                state = 2;
+              else {
+                ok = false;  // a cell the sweep never wrote
+                break;
+              }
+            } else if (state == 1) {
+              ops[pos++] = 1;
+              state = (bch & 4) ? 1 : 0;
+              uu--;
+            } else {
+              ops[pos++] = 2;
+              state = (bch & 8) ? 2 : 0;
+              vv--;
+            }
+          }
         }
-        uint8_t bch = dir[(int64_t)uu * bw + kk];
-        if (state == 0) {
-          int ch = bch & 3;
-          if (ch == 3) {
-            ops[pos++] = 0;
-            uu--;
-            vv--;
-          } else if (ch == 1)
-            state = 1;
-          else
-            state = 2;
-        } else if (state == 1) {
-          ops[pos++] = 1;
-          state = (bch & 4) ? 1 : 0;
-          uu--;
-        } else {
-          ops[pos++] = 2;
-          state = (bch & 8) ? 2 : 0;
-          vv--;
-        }
+        __syncwarp();
       }
-      if (ok) len = pos;
+      if (lane == 0) s_len[wib] = (ok && done) ? pos : -1;
     }
+    if (BLOCK)
+      __syncthreads();
+    else
+      __syncwarp();
+    len = s_len[wib];
+    used = attempt + 1;
+    if (BLOCK)
+      __syncthreads();  // s_len is rewritten by the next attempt
+    else
+      __syncwarp();
+  }
+  if (tid == 0) {
     a.opsLen[c] = len;
-    a.status[c] = len > 0 ? 1 : 0;
+    a.status[c] = len > 0 ? used : 0;
   }
 }
 
