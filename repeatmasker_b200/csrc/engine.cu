@@ -601,7 +601,9 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         t.q = q;
         t.strand = strand;
         t.subject = s;
-        t.dil = m | (m << 1) | (m >> 1);
+        // K1 files a cell under the block its warp is in, which for lanes lagging behind is the block AFTER the cell's
+        // own, and an alignment may start before the block in which it first reaches minscore: add the block before
+        t.dil = m | (m >> 1);
         const int64_t CB = 32ll << h_hotShift[q];
         // checkpoints are exact only when K1 is (no merged residue class, no int16 wrap)
         t.chain = pairbest[idx] >= 32767 || fullMode || !ckEnabled || !classesExact || t.dil == 0 ||
@@ -858,10 +860,23 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       t.c0 = 0;
       t.c1 = h_qlen[T.q];
       t.ckOff = -1;
+      if (pairbest[idx] >= 32767 && t.mode != ~0ull && ckEnabled && classesExact) {
+        // int16 wrap: K1 is exact up to the first hot block (a score passes minscore long before it wraps), so the
+        // sweep starts at the checkpoint before the first block of the mask; to the right of the last one K1 saw
+        // nothing >= minscore, and since a wrap only ever LOWERS K1's values (the wrapped sum is negative and loses
+        // every max) a path it missed there descends from the wrapped alignment and scores below its maximum --
+        // unless it leaves the window at >= minscore, which the kernel reports (then the task is redone in full)
+        const int64_t CB = 32ll << h_hotShift[T.q];
+        const int lo = __builtin_ctzll(fwd), hi = 63 - __builtin_clzll(fwd);
+        t.c0 = (int)std::min<int64_t>(lo * CB, h_qlen[T.q]);
+        if (lo > 0) t.ckOff = ((int64_t)T.q * 64 + lo) * ((int64_t)nGroups * R) + (int64_t)h_subjFirstGroup[T.subject] * R;
+        if (hi < 63) t.c1 = (int)std::min<int64_t>(h_qlen[T.q], (hi + 1) * CB);
+        if (t.c0 >= t.c1) t.c0 = 0, t.c1 = h_qlen[T.q], t.ckOff = -1;
+      }
       t.firstTicket = (int)ticketTask.size();
       for (int k = 0; k < t.nStripes; k++) ticketTask.push_back((int32_t)tasks.size());
       tasks.push_back(t);
-      chainCells += (double)h_qlen[T.q] * (double)lib.seqs[T.subject].size();
+      chainCells += (double)(t.c1 - t.c0) * (double)lib.seqs[T.subject].size();
     }
     int blocksPerSM = 0;
     if (chainR == 2)
@@ -974,11 +989,16 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         if (leftFlag[i]) {
           if (tasks[i].mode == ~0ull) throw Error("origin pass: a fully swept task still reports a left origin");
           tasks[i].mode = ~0ull;
+          tasks[i].c0 = 0;
+          tasks[i].c1 = h_qlen[tasks[i].q];
+          tasks[i].ckOff = -1;
           any = true;
           chainRedo++;
         } else {
           tasks[i].mode = 0;  // done: nothing to sweep with origins, and nothing >= minscore can appear
+          tasks[i].c0 = 0;
           tasks[i].c1 = 0;    // (an empty window makes the ticket a no-op)
+          tasks[i].ckOff = -1;
         }
       }
       if (!any) break;

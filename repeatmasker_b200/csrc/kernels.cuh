@@ -607,6 +607,23 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
       oH[r] = 0;
       oE[r] = 0;
     }
+    int diagH = 0;
+    if (tk.ckOff >= 0) {
+      // window starting at a K1 column checkpoint (exact H, E' before column c0); whatever is alive there comes "from
+      // the left": a hit that carries that origin makes the host redo the task from column 0
+      const uint2* ck = a.ck + tk.ckOff;
+      const int sh = tk.strand ? 16 : 0;
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        if (row0 + r < L) {
+          const uint2 v = ck[row0 + r];
+          H[r] = (int)((v.x >> sh) & 0xffffu);
+          E[r] = (int)((v.y >> sh) & 0xffffu) + a.gap_init;
+          oH[r] = kOriginLeft;
+          oE[r] = kOriginLeft;
+        }
+      if (row0 > 0 && row0 - 1 < L) diagH = (int)((ck[row0 - 1].x >> sh) & 0xffffu);
+    }
     const long long k2t0 = clock64();
     long long k2wait = 0;
     const int W = tk.c1 - tk.c0;  // columns of this task's window
@@ -625,8 +642,8 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
         break;
       }
     }
-    int outH = 0, outF = NEGI, diagH = 0, curQ = -1;
-    uint32_t outOH = 0, outOF = 0, diagO = 0;
+    int outH = 0, outF = NEGI, curQ = -1;
+    uint32_t outOH = 0, outOF = 0, diagO = kOriginLeft;  // only read when the diagonal source is alive (checkpoint start)
     OriginBoundary wb = {0, NEGI, 0, 0};
     uint32_t lastOrigin = kOriginLeft;  // nothing cached
     unsigned long long lastVal = 0;
@@ -670,12 +687,15 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
           inOF = fof;
         }
         curQ = inQ;
-        const int i1 = tk.c0 + b * 32 + j - lane + 1;  // 1-based query column of this lane at this step
+        const int cw = b * 32 + j - lane;  // column inside the window, 0-based
+        const int i1 = tk.c0 + cw + 1;     // 1-based query column of this lane at this step
         const bool mode = (j >= lane) ? modeCur : modeOld;
         int hd = diagH, hu = inH, f = inF;
-        diagH = inH;
         const bool active = curQ >= 0;
-        if (!mode) {
+        if (cw < 0) {
+          // before its first column a lane keeps its (checkpointed) state untouched
+        } else if (!mode) {
+          diagH = inH;
           // ---- score-only sweep: identical H/E/F values, no origins
 #pragma unroll
           for (int r = 0; r < R; r++) {
@@ -699,7 +719,9 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
           diagO = kOriginLeft;
           outOH = kOriginLeft;
           outOF = kOriginLeft;
+          prevMode = false;
         } else {
+          diagH = inH;
           if (!prevMode) {  // entering an origin block: everything alive comes from the left
 #pragma unroll
             for (int r = 0; r < R; r++) {
@@ -741,8 +763,14 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
           }
           outOH = ou;
           outOF = of;
+          prevMode = true;
         }
-        prevMode = mode;
+        if (cw == W - 1 && tk.c1 < Q) {
+          // the window ends before the query does: nothing >= minscore may leave it (the host then redoes the task
+          // over the whole query); everything further right was cold in K1, see run_origin
+#pragma unroll
+          for (int r = 0; r < R; r++) needFull |= H[r] >= a.minscore;
+        }
         outH = hu;
         outF = f;
         if (hasNext) {

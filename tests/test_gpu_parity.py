@@ -112,6 +112,23 @@ def test_long_subject_chains_and_int16_overflow(tmp_path):
     assert_same_hits(got, want)
 
 
+def test_int16_overflow_windows_start_at_a_checkpoint(tmp_path):
+    """Overflowing (> 32767) alignments in the middle of a 50 kbp query, one per strand: the int32 sweep of such a triple
+    starts at the K1 checkpoint before its first hot column block and stops after the last one; no redo is needed."""
+    rng = np.random.default_rng(77)
+    long_s = synth.random_dna(rng, 9000).tobytes().decode()
+    other = synth.random_dna(rng, 700).tobytes().decode()
+    copy1 = synth.mutate(rng, long_s[1000:7400], 0.02, 0.002)
+    copy2 = synth.revcomp(synth.mutate(rng, long_s[2000:8600], 0.03, 0.002))
+    bg = synth.random_dna(rng, 38000).tobytes().decode()
+    q = (bg[:12000] + copy1 + bg[12000:13000] + synth.mutate(rng, other, 0.12, 0.01) + bg[13000:22000] + copy2 +
+         bg[22000:30000] + synth.mutate(rng, long_s[4000:4600], 0.2, 0.02) + bg[30000:])
+    got, want, st = both(tmp_path, ["q1"], [q], ["longS#LINE/L1", "short#SINE/x"], [long_s, other])
+    assert sum(h["score"] > 32767 for h in want) == 2
+    assert_same_hits(got, want)
+    assert st["n_origin_redo"] == 0
+
+
 def test_alphabet_edge_cases(tmp_path):
     """N runs, X (masked), lower-case x (excision sentinel), IUPAC codes incl. B/D/H/V, >7 residue classes."""
     rng = np.random.default_rng(9)
