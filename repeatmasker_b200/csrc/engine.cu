@@ -101,6 +101,30 @@ struct HitRec {
   std::string qaln, saln;
 };
 
+// Static split of [0, n) over a few host threads (post-processing of independent records).
+template <typename F>
+void parallel_for(int n, F&& f) {
+  static const int hw = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const int nt = std::min(hw, std::max(1, n / 8));
+  if (nt <= 1) {
+    for (int i = 0; i < n; i++) f(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err(nt);
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([&, t] {
+      try {
+        for (int i = t; i < n; i += nt) f(i);
+      } catch (...) {
+        err[t] = std::current_exception();
+      }
+    });
+  for (auto& x : th) x.join();
+  for (auto& e : err)
+    if (e) std::rethrow_exception(e);
+}
+
 }  // namespace rmgpu
 
 using namespace rmgpu;
@@ -1311,36 +1335,51 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
 
   std::vector<int32_t> pairbest;
   std::vector<unsigned long long> hotmask;
+  const double w0 = now_ms();
   run_score(p, pairbest, hotmask, st.ms_score, st.launches, /*exact=*/false);
   st.score_launches = 1;
   st.d2h_bytes += (int64_t)pairbest.size() * 12;
+  const double w1 = now_ms();
   std::vector<Candidate> cands;
   run_origin(p, pairbest, hotmask, cands, st);
+  const double w2 = now_ms();
   std::vector<std::vector<uint8_t>> ops;
   run_traceback(p, cands, ops, st);
+  const double w3 = now_ms();
 
   const double t_post = now_ms();
-  std::vector<HitRec> hits;
+  // one record per candidate, built by a few host threads (candidates are independent; the order is restored below)
   std::vector<std::string> rcCache(nQ);
-  for (size_t ci = 0; ci < cands.size(); ci++) {
+  {
+    std::vector<char> needRc(nQ, 0);
+    for (const Candidate& c : cands)
+      if (c.strand) needRc[c.q] = 1;
+    parallel_for(nQ, [&](int q) {
+      if (needRc[q]) rcCache[q] = revcomp_letters(queries.seqs[q]);
+    });
+  }
+  std::vector<HitRec> built(cands.size());
+  std::vector<char> keepRec(cands.size(), 0);
+  parallel_for((int)cands.size(), [&](int ci) {
     const Candidate& c = cands[ci];
     const std::string& qf = queries.seqs[c.q];
     const std::string& sj = lib.seqs[c.subject];
-    if (c.strand && rcCache[c.q].empty()) rcCache[c.q] = revcomp_letters(qf);
     const std::string& ql = c.strand ? rcCache[c.q] : qf;
     const int Q = (int)qf.size(), L = (int)sj.size();
-    HitRec h;
-    h.qaln.reserve(ops[ci].size());
-    h.saln.reserve(ops[ci].size());
+    HitRec& h = built[ci];
+    const std::vector<uint8_t>& op_list = ops[ci];
+    h.qaln.resize(op_list.size());
+    h.saln.resize(op_list.size());
     int64_t counts[kMaxAlpha] = {};
     long nsub = 0, ndel = 0, nins = 0;
     h.ti = h.tv = h.amb = h.gap_inits = h.gap_bases = 0;
     int qi = c.i0 - 1, si = c.j0 - 1, prev = 0;
-    for (uint8_t op : ops[ci]) {
+    size_t col = 0;
+    for (uint8_t op : op_list) {
       if (op == 0) {
         char a = ql[qi++], b = sj[si++];
-        h.qaln.push_back(a);
-        h.saln.push_back(b);
+        h.qaln[col] = a;
+        h.saln[col] = b;
         counts[matrix.code_of[(unsigned char)a]]++;
         if (a != b) {
           nsub++;
@@ -1353,23 +1392,24 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
             h.tv++;
         }
       } else if (op == 1) {
-        h.qaln.push_back(ql[qi++]);
-        h.saln.push_back('-');
+        h.qaln[col] = ql[qi++];
+        h.saln[col] = '-';
         nins++;
         h.gap_bases++;
         if (prev != 1) h.gap_inits++;
       } else {
-        h.qaln.push_back('-');
-        h.saln.push_back(sj[si++]);
+        h.qaln[col] = '-';
+        h.saln[col] = sj[si++];
         ndel++;
         h.gap_bases++;
         if (prev != 2) h.gap_inits++;
       }
       prev = op;
+      col++;
     }
     h.raw = c.raw;
     h.score = p.raw ? c.raw : complexity_adjust(c.raw, counts, matrix);
-    if (h.score < p.minscore) continue;
+    if (h.score < p.minscore) return;
     h.qidx = c.q;
     h.sidx = c.subject;
     h.strand = c.strand;
@@ -1388,8 +1428,12 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
     fmt_pct(h.div, nsub, span);
     fmt_pct(h.del, ndel, span);
     fmt_pct(h.ins, nins, span);
-    hits.push_back(std::move(h));
-  }
+    keepRec[ci] = 1;
+  });
+  std::vector<HitRec> hits;
+  hits.reserve(cands.size());
+  for (size_t ci = 0; ci < cands.size(); ci++)
+    if (keepRec[ci]) hits.push_back(std::move(built[ci]));
   // output order: query order, ascending query start, DESCENDING subject order, then subject start, query end, strand
   std::sort(hits.begin(), hits.end(), [](const HitRec& x, const HitRec& y) {
     if (x.qidx != y.qidx) return x.qidx < y.qidx;
@@ -1477,12 +1521,15 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
     o.gap_inits = h.gap_inits;
     o.gap_bases = h.gap_bases;
     if (p.want_alignments) {
-      o.qaln = arena->dup(h.qaln);
-      o.saln = arena->dup(h.saln);
+      o.qaln = arena->keep(std::move(hits[k].qaln));
+      o.saln = arena->keep(std::move(hits[k].saln));
     }
   }
   st.ms_host_post = now_ms() - t_post;
   st.ms_total = now_ms() - t_begin + ms_h2d_queries;
+  if (getenv("RMGPU_DEBUG_HOST"))
+    fprintf(stderr, "[host dbg] search_batch wall: setup %.2f  score %.2f (kernel %.2f)  origin %.2f  traceback %.2f (kernels %.2f)  post %.2f ms\n",
+            w0 - t_begin, w1 - w0, st.ms_score, w2 - w1, w3 - w2, st.ms_traceback, st.ms_host_post);
   return res;
 }
 
@@ -1558,8 +1605,12 @@ int rmgpu_session_set_matrix_file(rmgpu_session* s, const char* f) {
 int rmgpu_session_set_library(rmgpu_session* s, int32_t n, const char* const* names, const char* const* seqs,
                               const int32_t* lens) {
   return guarded([&] {
+    const double t0 = now_ms();
     CUDA_CHECK(cudaSetDevice(s->device));
-    s->set_library(SeqSet::from_arrays(n, names, seqs, lens));
+    SeqSet ss = SeqSet::from_arrays(n, names, seqs, lens);
+    const double t1 = now_ms();
+    s->set_library(std::move(ss));
+    if (getenv("RMGPU_DEBUG_HOST")) fprintf(stderr, "[host dbg] set_library: copy %.2f ms, pack+upload %.2f ms\n", t1 - t0, now_ms() - t1);
   });
 }
 int rmgpu_session_set_library_fasta(rmgpu_session* s, const char* f) {
@@ -1571,8 +1622,12 @@ int rmgpu_session_set_library_fasta(rmgpu_session* s, const char* f) {
 int rmgpu_session_set_queries(rmgpu_session* s, int32_t n, const char* const* names, const char* const* seqs,
                               const int32_t* lens) {
   return guarded([&] {
+    const double t0 = now_ms();
     CUDA_CHECK(cudaSetDevice(s->device));
-    s->set_queries(SeqSet::from_arrays(n, names, seqs, lens));
+    SeqSet ss = SeqSet::from_arrays(n, names, seqs, lens);
+    const double t1 = now_ms();
+    s->set_queries(std::move(ss));
+    if (getenv("RMGPU_DEBUG_HOST")) fprintf(stderr, "[host dbg] set_queries: copy %.2f ms, pack+upload %.2f ms\n", t1 - t0, now_ms() - t1);
   });
 }
 int rmgpu_session_set_queries_fasta(rmgpu_session* s, const char* f) {

@@ -62,6 +62,11 @@ struct ResultArena {
     return blocks.back().get();
   }
   const char* dup(const std::string& s) { return dup(s.data(), s.size()); }
+  std::vector<std::unique_ptr<std::string>> strings;  // strings handed over without a copy
+  const char* keep(std::string&& s) {
+    strings.emplace_back(new std::string(std::move(s)));
+    return strings.back()->c_str();
+  }
 };
 
 }  // namespace rmgpu

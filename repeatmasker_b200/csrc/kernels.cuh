@@ -193,6 +193,10 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 }
 
 constexpr int kScoreWarps = 8;
+#ifndef K1_UNROLL
+#define K1_UNROLL 4
+#endif
+constexpr int kK1Unroll = K1_UNROLL;  // columns per trip of K1's inner loop
 
 // EXACT: the running best is folded in at every cell (rmgpu_session_score_only, tests).  !EXACT (the search path, where
 // K1 is only a filter): the best is sampled from E' every 8th column.  E'[i][j] = max_k (H[i-k][j] + (k-1)*ins_ext), so
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
       __syncwarp();  // everyone is done reading the previous block's feed
       s_feed[wib][lane] = make_uint4(selv, (uint32_t)raw, (uint32_t)(raw >> 32), 0u);
       __syncwarp();
-#pragma unroll 2
+#pragma unroll kK1Unroll
       for (int j = 0; j < 32; j++) {
         uint32_t inSel = __shfl_up_sync(0xffffffffu, curSel, 1);
         uint32_t inH = __shfl_up_sync(0xffffffffu, outH, 1);

@@ -7,9 +7,11 @@ plug-in that RepeatMasker itself loads is repeatmasker_b200/perl/GpuSearchEngine
 """
 import ctypes as C
 import os
+import sys
+import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librmgpu.so")
+LIB_PATH = os.environ.get("RMGPU_LIB") or os.path.join(HERE, "librmgpu.so")
 
 
 class RmgpuError(RuntimeError):
@@ -159,11 +161,17 @@ class Session:
 
     def search(self, params):
         res = C.POINTER(Result)()
+        dbg = "RMGPU_DEBUG_HOST" in os.environ
+        t0 = time.perf_counter()
         _check(lib().rmgpu_session_search(self._h, C.byref(params), C.byref(res)))
+        t1 = time.perf_counter()
         try:
             return _hits_to_dicts(res)
         finally:
             lib().rmgpu_free(res)
+            if dbg:
+                print(f"[host dbg] Session.search: C call {1e3 * (t1 - t0):.2f} ms, records -> dicts + free {1e3 * (time.perf_counter() - t1):.2f} ms",
+                      file=sys.stderr)
 
     def score_only(self, params):
         """K1 only: (best[nq][ns][2] as a flat list, kernel ms)."""
