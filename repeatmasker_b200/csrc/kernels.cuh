@@ -9,6 +9,7 @@
 // Scoring convention (SearchResult.pm:1829-1852, :1894-1917): score = M[subject][query]; the first base of a gap
 // costs gap_init, further bases ins_gap_ext (gap in the subject row, "E") or del_gap_ext (gap in the query row, "F").
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -194,9 +195,15 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 
 constexpr int kScoreWarps = 8;
 #ifndef K1_UNROLL
-#define K1_UNROLL 4
+#define K1_UNROLL 8
 #endif
-constexpr int kK1Unroll = K1_UNROLL;  // columns per trip of K1's inner loop
+constexpr int kK1Unroll = K1_UNROLL;
+#ifndef K1_IMAD_SELECT
+#define K1_IMAD_SELECT 1
+#endif
+#ifndef K1_SPLIT_CK
+#define K1_SPLIT_CK 1
+#endif  // columns per trip of K1's inner loop
 
 // EXACT: the running best is folded in at every cell (rmgpu_session_score_only, tests).  !EXACT (the search path, where
 // K1 is only a filter): the best is sampled from E' every 8th column.  E'[i][j] = max_k (H[i-k][j] + (k-1)*ins_ext), so
@@ -205,7 +212,8 @@ constexpr int kK1Unroll = K1_UNROLL;  // columns per trip of K1's inner loop
 // 6 of the 104 integer-pipe instructions per lane-column.
 template <int R, bool EXACT>
 __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArgs a) {
-  __shared__ uint4 s_feed[kScoreWarps][32];  // (selector, H above, F' above) for the 32 columns of the current block
+  __shared__ uint4 s_feed[kScoreWarps][33];  // (selector, H above, F' above) for the 32 columns of the current block
+                                             // + the selector of the next block's first column
   __shared__ uint2 s_out[kScoreWarps][32];   // last row's (H, F') of the last 32 columns lane 31 finished
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nTickets = a.nQueries * a.nStripes;
@@ -258,6 +266,12 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     const int ckBlkMask = (1 << hotShift) - 1;
     const int sj = a.gsubject[g];
     uint32_t best = 0, bestBlk = 0, outH = 0, outF = 0, diag = 0, curSel = kPadSel;
+    uint32_t nextSel = lane == 0 ? (uint32_t)sel[0] : kPadSel;  // selector of this lane's next column, one step ahead
+#if K1_IMAD_SELECT
+    // 0/1 factors, made opaque so that they stay multiplications
+    uint32_t keepSel = lane != 0, feedSel = lane == 0, keepHF = lane != 0 && !startFlag, feedHF = lane == 0 && !startFlag;
+    asm volatile("" : "+r"(keepSel), "+r"(feedSel), "+r"(keepHF), "+r"(feedHF));
+#endif
     unsigned long long nextRaw = 0;
     if (hasPrev) nextRaw = ld_relaxed_u64(&bndIn[lane]);
     for (int b = 0; b < nBlocks; b++) {
@@ -304,63 +318,88 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
       const bool ckBlock = a.ck != nullptr && b > 0 && (b & ckBlkMask) == 0 && b * 32 < Q;
       __syncwarp();  // everyone is done reading the previous block's feed
       s_feed[wib][lane] = make_uint4(selv, (uint32_t)raw, (uint32_t)(raw >> 32), 0u);
+      if (lane == 0) s_feed[wib][32].x = b + 1 < nBlocks ? (uint32_t)sel[(b + 1) * 32] : kPadSel;
       __syncwarp();
+      // The 32 columns of the block.  CK: this block starts a checkpointed column block (rare) -- a separate
+      // instantiation keeps the test out of the common loop.
+      auto columns = [&](auto ckTag) {
+        constexpr bool CK = decltype(ckTag)::value;
 #pragma unroll kK1Unroll
-      for (int j = 0; j < 32; j++) {
-        uint32_t inSel = __shfl_up_sync(0xffffffffu, curSel, 1);
-        uint32_t inH = __shfl_up_sync(0xffffffffu, outH, 1);
-        uint32_t inF = __shfl_up_sync(0xffffffffu, outF, 1);
-        const uint4 fd = s_feed[wib][j];  // broadcast read
-        if (lane == 0) {
-          inSel = fd.x;
-          inH = fd.y;
-          inF = fd.z;
-        }
-        if (startFlag) {
-          inH = 0;
-          inF = 0;
-        }
-        curSel = inSel;
-        if (ckBlock && j == lane) {
-          // column checkpoint for the origin pass: the (H, E') this lane holds before it starts column b*32 = cb*CB
-          uint2* dst = a.ck + ((int64_t)q * 64 + (b >> hotShift)) * a.ckRows + (int64_t)g * R;
+        for (int j = 0; j < 32; j++) {
+          // the selector does not depend on the sweep: it is passed down the lanes one step AHEAD, so a step never starts
+          // by waiting for a shuffle
+          curSel = nextSel;
+          uint32_t inSel = __shfl_up_sync(0xffffffffu, curSel, 1);
+          uint32_t inH = __shfl_up_sync(0xffffffffu, outH, 1);
+          uint32_t inF = __shfl_up_sync(0xffffffffu, outF, 1);
+          const uint4 fd = s_feed[wib][j];  // broadcast read
+          const uint32_t fdSelNext = s_feed[wib][j + 1].x;
+#if K1_IMAD_SELECT
+          // lane 0 takes the feed, a lane that starts a subject takes zeros: as multiply-adds by 0/1 factors, which
+          // issue on the FMA pipe instead of five SELs on the (saturated) integer pipe
+          nextSel = inSel * keepSel + fdSelNext * feedSel;
+          inH = inH * keepHF + fd.y * feedHF;
+          inF = inF * keepHF + fd.z * feedHF;
+#else
+          nextSel = lane == 0 ? fdSelNext : inSel;
+          if (lane == 0) {
+            inH = fd.y;
+            inF = fd.z;
+          }
+          if (startFlag) {
+            inH = 0;
+            inF = 0;
+          }
+#endif
+          if (CK && (K1_SPLIT_CK || ckBlock) && j == lane) {
+            // column checkpoint for the origin pass: the (H, E') this lane holds before it starts column b*32 = cb*CB
+            uint2* dst = a.ck + ((int64_t)q * 64 + (b >> hotShift)) * a.ckRows + (int64_t)g * R;
 #pragma unroll
-          for (int r = 0; r < R; r++) dst[r] = make_uint2(H[r], E[r]);
-        }
-        uint32_t hd = diag, f = inF, h = 0;
-        diag = inH;
+            for (int r = 0; r < R; r++) dst[r] = make_uint2(H[r], E[r]);
+          }
+          uint32_t hd = diag, f = inF, h = 0;
+          diag = inH;
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const uint32_t s = prmt(Plo[r], Phi[r], curSel);
-          const uint32_t hl = H[r];
-          E[r] = __viaddmax_s16x2(E[r], a.ie2, hl);                  // E'[i][j]
-          const uint32_t d = __vadd2(hd, s);                         // H[i-1][j-1] + s
-          const uint32_t tt = __viaddmax_s16x2_relu(E[r], a.gi2, d);  // T = max(0, diag, E'+gi): H without F
-          h = __viaddmax_s16x2(f, a.gi2, tt);                        // H = max(T, F'+gi)          (off the chain)
-          f = __viaddmax_s16x2(f, a.df2, tt);                        // F' of the next row         (the only chain)
-          hd = hl;
-          H[r] = h;
-          if (EXACT) bestBlk = __vmaxs2(bestBlk, h);
-        }
-        if (!EXACT && (j & 7) == 7) {
+          for (int r = 0; r < R; r++) {
+            const uint32_t s = prmt(Plo[r], Phi[r], curSel);
+            const uint32_t hl = H[r];
+            E[r] = __viaddmax_s16x2(E[r], a.ie2, hl);                  // E'[i][j]
+            const uint32_t d = __vadd2(hd, s);                         // H[i-1][j-1] + s
+            const uint32_t tt = __viaddmax_s16x2_relu(E[r], a.gi2, d);  // T = max(0, diag, E'+gi): H without F
+            h = __viaddmax_s16x2(f, a.gi2, tt);                        // H = max(T, F'+gi)          (off the chain)
+            f = __viaddmax_s16x2(f, a.df2, tt);                        // F' of the next row         (the only chain)
+            hd = hl;
+            H[r] = h;
+            if (EXACT) bestBlk = __vmaxs2(bestBlk, h);
+          }
+          if (!EXACT && (j & 7) == 7) {
 #pragma unroll
-          for (int r = 0; r < R; r++) bestBlk = __vmaxs2(bestBlk, E[r]);
-        }
-        outH = h;
-        outF = f;
-        if (hasNext) {
-          // lane 31 has just finished column c = b*32 + j - 31
-          const int c = b * 32 + j - 31;
-          if (lane == 31) s_out[wib][c & 31] = make_uint2(outH, outF);
-          if (c >= 0 && (c & 31) == 31) {  // column block complete: one coalesced, tagged 64-bit store per lane
-            __syncwarp();
-            const uint2 o = s_out[wib][lane];
-            st_relaxed_u64(&bndOut[(c & ~31) + lane],
-                           ((((unsigned long long)o.y << 32) | o.x) & ~kTagMask) | tagOut);
-            __syncwarp();
+            for (int r = 0; r < R; r++) bestBlk = __vmaxs2(bestBlk, E[r]);
+          }
+          outH = h;
+          outF = f;
+          if (hasNext) {
+            // lane 31 has just finished column c = b*32 + j - 31
+            const int c = b * 32 + j - 31;
+            if (lane == 31) s_out[wib][c & 31] = make_uint2(outH, outF);
+            if (c >= 0 && (c & 31) == 31) {  // column block complete: one coalesced, tagged 64-bit store per lane
+              __syncwarp();
+              const uint2 o = s_out[wib][lane];
+              st_relaxed_u64(&bndOut[(c & ~31) + lane],
+                             ((((unsigned long long)o.y << 32) | o.x) & ~kTagMask) | tagOut);
+              __syncwarp();
+            }
           }
         }
-      }
+      };
+#if K1_SPLIT_CK
+      if (ckBlock)
+        columns(std::true_type{});
+      else
+        columns(std::false_type{});
+#else
+      if (ckBlock || true) columns(std::true_type{});
+#endif
       // column-block bookkeeping for the origin pass: which blocks hold a cell >= minscore
       if ((((b + 1) >> hotShift) != (b >> hotShift)) || b == nBlocks - 1) {
         if (sj >= 0) {
