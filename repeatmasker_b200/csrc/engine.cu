@@ -35,20 +35,29 @@ namespace rmgpu {
 
 static thread_local std::string g_last_error;
 
+// bytes held by all DevBufs of this process: lets a session track free HBM without asking the driver on every call
+static std::atomic<long long> g_devbuf_bytes{0};
+
 template <typename T>
 struct DevBuf {  // grow-only device buffer
   T* p = nullptr;
   size_t cap = 0;
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaFree(p);
+      g_devbuf_bytes -= (long long)(cap * sizeof(T));
+    }
   }
   T* ensure(size_t n) {
     if (n > cap) {
       if (p) cudaFree(p);
       p = nullptr;
+      g_devbuf_bytes -= (long long)(cap * sizeof(T));
+      cap = 0;
       size_t want = std::max(n, cap + cap / 2);
       CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
       cap = want;
+      g_devbuf_bytes += (long long)(cap * sizeof(T));
     }
     return p;
   }
@@ -217,6 +226,7 @@ struct rmgpu_session {
   rmgpu_result* search(const rmgpu_params& p);        // whole resident batch, in memory-bounded chunks of queries
   rmgpu_result* search_batch(const rmgpu_params& p);  // one chunk: K1 -> K2 -> K3 -> host post
   int query_capacity() const;
+  long long freeAtOpen = 0, devbufAtOpen = 0;  // free HBM and this process's DevBuf bytes when the session opened
 };
 
 // -------------------------------------------------------------------------------------------------------------
@@ -1260,10 +1270,12 @@ struct IntervalUnion {  // disjoint, merged closed intervals
 // How many query records one pass may hold: the K1 column checkpoints (64 x rows x 8 B per query) and the stripe
 // boundary ring (up to stripes x columns x 8 B per query) must fit in a share of the free HBM.
 int rmgpu_session::query_capacity() const {
-  size_t freeB = 0, totalB = 0;
-  if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) return 1 << 30;
   static const char* capEnv = getenv("RMGPU_QUERY_CHUNK");
   if (capEnv && atoi(capEnv) > 0) return atoi(capEnv);
+  // free HBM = what was free when the session opened less what this process has allocated since (cudaMemGetInfo
+  // itself costs up to milliseconds per call)
+  const long long freeNow = freeAtOpen - (g_devbuf_bytes.load() - devbufAtOpen);
+  const size_t freeB = (size_t)std::max<long long>(freeNow, 0);
   const double budget = 0.45 * (double)(freeB + d_ck.cap * sizeof(uint2) + d_bnd1.cap * 8);
   const double perQuery = 64.0 * nGroups * R * 8.0 + (double)nStripes * ((double)maxQ + 64.0) * 8.0;
   const double byCk = (double)kCheckpointBudget / std::max(64.0 * nGroups * R * 8.0, 1.0);
@@ -1570,6 +1582,12 @@ rmgpu_session* rmgpu_session_open(int device) {
     s->device = device;
     s->numSMs = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    {
+      size_t freeB = 0, totalB = 0;
+      CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
+      s->freeAtOpen = (long long)freeB;
+      s->devbufAtOpen = g_devbuf_bytes.load();
+    }
     {
       int lo = 0, hi = 0;
       CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
