@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RMGPU_ABI_VERSION 1
+#define RMGPU_ABI_VERSION 2
 
 /* Search parameters.  Replaces the argv that CrossmatchSearchEngine.pm:277-363 (getParameters) builds from the
  * SearchEngineI.pm:132-681 setters:
@@ -58,6 +58,11 @@ typedef struct rmgpu_hit {
   const char *qaln, *saln; /* NUL-terminated gapped rows in cross_match DISPLAY orientation: for strand C the
                               query row is reverse-complemented (descending coordinates), subject row forward.
                               NULL when want_alignments == 0.                                           */
+  char pct_kimura[8];      /* sprintf("%4.2f") of SearchResult::calcKimuraDivergence(divCpGMod => 1)
+                              (SearchResult.pm:1607-1683), as CrossmatchSearchEngine.pm:509-511 stores it; computed
+                              on the rows as SearchResult holds them (strand C: both reversed and complemented).
+                              "" when want_alignments == 0.                                             */
+  int32_t cpg_sites, well_characterized; /* by-products of the same pass                                */
 } rmgpu_hit;
 
 /* Device-side accounting of one search (all times from CUDA events on the engine's stream). */
@@ -136,6 +141,13 @@ int rmgpu_server_quit(const char *socket_path);
 /* Measured integer-SIMD ("DPX") peak of this GPU: a register-resident loop of the bare recurrence.
  * Returns 16-bit-lane cell updates per second (GCUPS*1e9) in *cups and raw VIADDMNMX.S16x2 warp-instructions/s. */
 int rmgpu_measure_dpx_peak(int device, double *cups, double *dpx_instr_per_s);
+
+/* Host-only helper behind rmgpu_hit::pct_kimura, exported so that it can be checked against the reference's Perl
+ * (SearchResult.pm:1607-1683) without a GPU: rows in the orientation of rmgpu_hit::qaln/saln, strand as in rmgpu_hit.
+ * Writes the "%4.2f" text; the optional outputs are transitions (fractional with the CpG rule), transversions,
+ * well-characterised pairs and CpG sites. */
+void rmgpu_kimura_divergence(const char *qaln, const char *saln, int strand, char text[8], double *transitions,
+                             int32_t *transversions, int32_t *well_characterized, int32_t *cpg_sites);
 
 #ifdef __cplusplus
 }

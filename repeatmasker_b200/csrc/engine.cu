@@ -106,7 +106,8 @@ struct HitRec {
   int qstart, qend, qleft, sstart, send, sleft;
   int ti, tv, amb, gap_inits, gap_bases;
   bool star = false;
-  char div[8], del[8], ins[8];
+  char div[8], del[8], ins[8], kimura[8];
+  int cpg = 0, wcb = 0;
   std::string qaln, saln;
 };
 
@@ -1440,6 +1441,13 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
     fmt_pct(h.div, nsub, span);
     fmt_pct(h.del, ndel, span);
     fmt_pct(h.ins, nins, span);
+    h.kimura[0] = 0;
+    if (p.want_alignments) {
+      const KimuraResult k = kimura_divergence(h.qaln.data(), h.saln.data(), h.qaln.size(), c.strand != 0);
+      snprintf(h.kimura, sizeof(h.kimura), "%4.2f", k.kimura);
+      h.cpg = k.cpgSites;
+      h.wcb = k.wellCharacterized;
+    }
     keepRec[ci] = 1;
   });
   std::vector<HitRec> hits;
@@ -1527,6 +1535,9 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
     memcpy(o.pct_div, h.div, 8);
     memcpy(o.pct_del, h.del, 8);
     memcpy(o.pct_ins, h.ins, 8);
+    memcpy(o.pct_kimura, h.kimura, 8);
+    o.cpg_sites = h.cpg;
+    o.well_characterized = h.wcb;
     o.transitions = h.ti;
     o.transversions = h.tv;
     o.ambiguous = h.amb;
@@ -1564,6 +1575,17 @@ extern "C" {
 
 const char* rmgpu_version(void) { return "rmgpu version 0.1.0 (B200 sm_100a exhaustive Smith-Waterman-Gotoh)"; }
 int rmgpu_abi_version(void) { return RMGPU_ABI_VERSION; }
+
+void rmgpu_kimura_divergence(const char* qaln, const char* saln, int strand, char text[8], double* transitions,
+                             int32_t* transversions, int32_t* well_characterized, int32_t* cpg_sites) {
+  const size_t len = std::min(strlen(qaln), strlen(saln));
+  const KimuraResult k = kimura_divergence(qaln, saln, len, strand != 0);
+  snprintf(text, 8, "%4.2f", k.kimura);
+  if (transitions) *transitions = k.transitions;
+  if (transversions) *transversions = k.transversions;
+  if (well_characterized) *well_characterized = k.wellCharacterized;
+  if (cpg_sites) *cpg_sites = k.cpgSites;
+}
 const char* rmgpu_last_error(void) { return g_last_error.c_str(); }
 
 rmgpu_session* rmgpu_session_open(int device) {

@@ -47,6 +47,14 @@ struct SeqSet {
 char complement_letter(char c);  // table of CrossmatchSearchEngine.pm:833
 std::string revcomp_letters(const std::string& s);
 
+// SearchResult.pm:1607-1683 (calcKimuraDivergence with divCpGMod): rows as the engine reports them; for strand C they
+// are read back to front through the complement table, i.e. as CrossmatchSearchEngine.pm:824-837 stores them.
+struct KimuraResult {
+  double kimura, transitions;
+  int transversions, wellCharacterized, cpgSites;
+};
+KimuraResult kimura_divergence(const char* qaln, const char* saln, size_t len, bool strandC);
+
 // SearchResult.pm:2111-2150 in double precision, perl int() truncation.
 int complexity_adjust(int raw, const int64_t counts[kMaxAlpha], const ScoreMatrix& m);
 

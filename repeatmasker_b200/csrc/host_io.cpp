@@ -182,6 +182,52 @@ SeqSet SeqSet::from_arrays(int32_t n, const char* const* names, const char* cons
   return s;
 }
 
+KimuraResult kimura_divergence(const char* qaln, const char* saln, size_t len, bool strandC) {
+  // mutation classes of SearchResult.pm:179-217: only pairs of A/C/G/T are "well characterised"; CT TC AG GA are
+  // transitions, every other unequal pair a transversion
+  auto base = [](char c) { return c == 'A' ? 0 : c == 'G' ? 1 : c == 'C' ? 2 : c == 'T' ? 3 : -1; };
+  double transitions = 0, prevTrans = 0;
+  int transversions = 0, cpg = 0, wcb = 0;
+  char pS = 0;
+  for (size_t i = 0; i < len; i++) {
+    const size_t at = strandC ? len - 1 - i : i;
+    const char sb = strandC ? complement_letter(saln[at]) : saln[at];
+    const char qb = strandC ? complement_letter(qaln[at]) : qaln[at];
+    if (sb == '-') continue;
+    const int bq = base(qb), bs = base(sb);
+    const bool wc = bq >= 0 && bs >= 0;
+    if (wc) wcb++;
+    const int mt = (!wc || bq == bs) ? 0 : ((bq >> 1) == (bs >> 1) ? 1 : 2);  // purine<->purine, pyrimidine<->pyrimidine
+    if (pS == 'C' && sb == 'G') {
+      cpg++;
+      if (mt == 1)
+        prevTrans += 1;
+      else if (mt == 2)
+        transversions++;
+      if (prevTrans == 2)
+        prevTrans = 1;  // two transitions in a CpG count as one
+      else if (prevTrans == 1)
+        prevTrans = 1.0 / 10;  // a single one as a tenth
+    } else {
+      transitions += prevTrans;
+      prevTrans = 0;
+      if (mt == 1)
+        prevTrans = 1;  // held back for the CpG accounting
+      else if (mt == 2)
+        transversions++;
+    }
+    pS = sb;
+  }
+  transitions += prevTrans;
+  double kimura = 100.00;
+  if (wcb >= 1) {
+    const double p = transitions / wcb, q = (double)transversions / wcb;
+    const double logOperand = (1 - (2 * p) - q) * std::pow(1 - (2 * q), 0.5);
+    if (logOperand > 0) kimura = std::fabs(-0.5 * std::log(logOperand)) * 100;
+  }
+  return {kimura, transitions, transversions, wcb, cpg};
+}
+
 int complexity_adjust(int raw, const int64_t counts[kMaxAlpha], const ScoreMatrix& m) {
   double t_factor = 0, t_sum = 0, t_counts = 0;
   for (int c = 0; c < m.n; c++) {

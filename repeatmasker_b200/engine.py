@@ -33,7 +33,8 @@ class Hit(C.Structure):
                 ("pad_", C.c_uint8 * 2), ("pct_div", C.c_char * 8), ("pct_del", C.c_char * 8),
                 ("pct_ins", C.c_char * 8), ("transitions", C.c_int32), ("transversions", C.c_int32),
                 ("ambiguous", C.c_int32), ("gap_inits", C.c_int32), ("gap_bases", C.c_int32), ("qaln", C.c_char_p),
-                ("saln", C.c_char_p)]
+                ("saln", C.c_char_p), ("pct_kimura", C.c_char * 8), ("cpg_sites", C.c_int32),
+                ("well_characterized", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -55,7 +56,7 @@ EXPORTS = ["rmgpu_version", "rmgpu_abi_version", "rmgpu_last_error", "rmgpu_sear
            "rmgpu_session_open", "rmgpu_session_close", "rmgpu_session_set_matrix_file", "rmgpu_session_set_library",
            "rmgpu_session_set_library_fasta", "rmgpu_session_set_queries", "rmgpu_session_set_queries_fasta",
            "rmgpu_session_search", "rmgpu_session_score_only", "rmgpu_session_counts", "rmgpu_measure_dpx_peak",
-           "rmgpu_server_ping", "rmgpu_server_quit"]
+           "rmgpu_server_ping", "rmgpu_server_quit", "rmgpu_kimura_divergence"]
 
 
 def lib():
@@ -105,9 +106,23 @@ def _hits_to_dicts(res):
                         qleft=h.qleft, strand="C" if h.strand else "+", sname=h.subject_name.decode(),
                         sstart=h.sstart, send=h.send, sleft=h.sleft, star=bool(h.overlap_star),
                         qaln=(h.qaln or b"").decode(), saln=(h.saln or b"").decode(), ti=h.transitions,
-                        tv=h.transversions, query_index=h.query_index, subject_index=h.subject_index))
+                        tv=h.transversions, query_index=h.query_index, subject_index=h.subject_index,
+                        kimura=h.pct_kimura.decode(), cpg=h.cpg_sites))
     st = {k: getattr(r.stats, k) for k, _ in Stats._fields_}
     return out, st
+
+
+def kimura_divergence(qaln, saln, strand_c=False):
+    """rmgpu_kimura_divergence(): (text "%4.2f", transitions, transversions, well-characterised pairs, CpG sites) of one
+    alignment in the orientation of rmgpu_hit::qaln/saln (SearchResult.pm:1607-1683).  Host-only, needs no GPU."""
+    text = C.create_string_buffer(8)
+    ti, tv, wcb, cpg = C.c_double(), C.c_int32(), C.c_int32(), C.c_int32()
+    f = lib().rmgpu_kimura_divergence
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                  C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    f.restype = None
+    f(qaln.encode(), saln.encode(), 1 if strand_c else 0, text, C.byref(ti), C.byref(tv), C.byref(wcb), C.byref(cpg))
+    return text.value.decode(), ti.value, tv.value, wcb.value, cpg.value
 
 
 def make_params(gap_init=-30, ins_gap_ext=-6, del_gap_ext=-5, minscore=225, masklevel=101, minmatch=9, bandwidth=14,

@@ -305,7 +305,12 @@ sub recordsToCollection {
       my $deletions = ( $result->getPctDelete() / 100 ) * $qryLen;
       $result->setPctDelete( sprintf( "%4.2f", ( $deletions * 100 ) / $sbjLen ) );
     }
-    if ( defined $rec->{'queryString'} ) {
+    if ( defined $rec->{'pctKimuraDiverge'} ) {
+      # computed by the library with the arithmetic of SearchResult::calcKimuraDivergence( divCpGMod => 1 ):
+      # at GPU search rates the per-character Perl loop would cost more than the search itself
+      $result->setPctKimuraDiverge( $rec->{'pctKimuraDiverge'} );
+    }
+    elsif ( defined $rec->{'queryString'} ) {
       my ( $div, $transi, $transv, $wellCharBases, $numCpGs ) =
           $result->calcKimuraDivergence( divCpGMod => 1 );
       $result->setPctKimuraDiverge( sprintf( "%4.2f", $div ) );

@@ -78,6 +78,7 @@ search(query, subject, matrix, gap_init, ins_gap_ext, del_gap_ext, minscore, mas
         (void)hv_stores(hv, "star", newSViv(h->overlap_star));
         (void)hv_stores(hv, "transitions", newSViv(h->transitions));
         (void)hv_stores(hv, "transversions", newSViv(h->transversions));
+        if (h->pct_kimura[0]) (void)hv_stores(hv, "pctKimuraDiverge", newSVpv(h->pct_kimura, 0));
         if (h->qaln) (void)hv_stores(hv, "queryString", newSVpv(h->qaln, 0));
         if (h->saln) (void)hv_stores(hv, "subjString", newSVpv(h->saln, 0));
         av_push(hits, newRV_noinc((SV *)hv));

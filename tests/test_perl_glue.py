@@ -25,7 +25,8 @@ def test_xs_glue_builds_and_loads():
     assert out.startswith("rmgpu version")
 
 
-def test_records_to_collection_equals_reference_parse(tmp_path):
+@pytest.mark.parametrize("library_kimura", [False, True])
+def test_records_to_collection_equals_reference_parse(tmp_path, library_kimura):
     subprocess.run(["make", "-C", PERL_DIR], check=True, capture_output=True)
     snames, sseqs = synth.make_library(21, n_families=20, lo=80, hi=900)
     genome, _ = synth.make_genome(22, 9000, sseqs, coverage=0.5)
@@ -40,6 +41,10 @@ def test_records_to_collection_equals_reference_parse(tmp_path):
                  orientation="C" if h["strand"] == "C" else "", subjName=h["sname"], subjStart=h["sstart"],
                  subjEnd=h["send"], subjRemaining=h["sleft"], star=int(h["star"]), queryString=h["qaln"],
                  subjString=h["saln"]) for h in hits]
+    if library_kimura:  # the fast path: the text computed by librmgpu (host code) instead of the Perl loop
+        from repeatmasker_b200 import engine
+        for r, h in zip(recs, hits):
+            r["pctKimuraDiverge"] = engine.kimura_divergence(h["qaln"], h["saln"], h["strand"] == "C")[0]
     (tmp_path / "recs.json").write_text(json.dumps(recs))
     res = subprocess.run(["perl", f"-I{REF}", f"-I{PERL_DIR}", os.path.join(util.ROOT, "tests", "perl", "compare_collections.pl"),
                           util.ORACLE_BIN, m, q, s, str(tmp_path / "recs.json")], capture_output=True, text=True)
