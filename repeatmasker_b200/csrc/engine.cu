@@ -659,7 +659,6 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
 
   static const bool dbgK2 = getenv("RMGPU_DEBUG_K2") != nullptr;
   const double k2t0 = now_ms();
-  int chainCtas = 0;  // CTAs the concurrent fallback sweep needs resident
   std::atomic<int> chainLaunched{0};  // set once the fallback sweep's kernel is in its stream (or there is none)
   // ------------------------------------------------------------------ block-parallel path
   auto run_blocks = [&](const std::vector<int>& trIdx, bool allBlocks, std::vector<int>& redoOut) {
@@ -709,8 +708,11 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       if (sorted[i].prevTask >= 0) sorted[i].prevTask = inv[sorted[i].prevTask];
     }
     tasks.swap(sorted);
-    // tickets go stripe level by stripe level over all tasks (all first stripes, then all second stripes, ...): a
-    // consumer stripe is claimed after (nearly) a whole level of other tickets, so it does not poll its producer
+    // tickets go stripe level by stripe level over all tasks, the levels aligned at the LAST stripe: a task with n
+    // stripes has its stripe k in level (maxStripes - n) + k.  The long tasks -- the critical path, one dependent
+    // ticket per stripe -- start first and run as systolic pipelines while the machine is still filling; the wide
+    // levels, where a consumer stripe is claimed (nearly) a whole level after its producer and never polls, come last,
+    // so the kernel ends on plenty of parallel work instead of a thin tail of long tasks
     std::vector<int32_t> ticketTask, ticketStripe, prodTicket, consTicket;
     int maxStripes = 0;
     for (auto& t : tasks) {
@@ -720,10 +722,11 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     {
       std::vector<int32_t> prevOf(tasks.size(), -1);
       size_t levelWidthMax = 0;
-      for (int level = 0; level < maxStripes; level++) {
+      for (int key = 0; key < maxStripes; key++) {
         size_t before = ticketTask.size();
         for (size_t i = 0; i < tasks.size(); i++) {
-          if (level >= tasks[i].nStripes) continue;
+          const int level = key - (maxStripes - tasks[i].nStripes);
+          if (level < 0) continue;
           const int32_t tkt = (int32_t)ticketTask.size();
           ticketTask.push_back((int32_t)i);
           ticketStripe.push_back(level);
@@ -740,8 +743,10 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     int blocksPerSM = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_origin_block_kernel, 128, 0));
     if (blocksPerSM < 1) throw Error("K2b does not fit on an SM");
-    // leave room for the CTAs of the concurrent fallback sweep (persistent grids: what is not resident cannot start)
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)numSMs * blocksPerSM - chainCtas, ((int64_t)nTickets + 3) / 4));
+    // the fallback sweep is launched first (high-priority stream) and takes the SM slots it needs; this grid is sized
+    // for the whole machine: CTAs that do not fit next to the sweep start when it ends (tickets are claimed
+    // dynamically and a ticket's producer is always an older ticket, so CTAs waiting to become resident are harmless)
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)numSMs * blocksPerSM, ((int64_t)nTickets + 3) / 4));
     const int warps = grid * 4;
     // a slot's reader is at most one level (blockLevelWidth tickets) after its writer
     const int nslot = (int)std::min<int64_t>(nTickets, std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)blockLevelWidth + 2));
@@ -787,6 +792,11 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       a.vals = d_vals.ensure(tableSize);
       a.tableMask = (uint32_t)tableSize - 1;
       a.overflow = d_overflow.ensure(1);
+      a.dbg = nullptr;
+      if (dbgK2) {
+        a.dbg = d_dbg.ensure(72);
+        CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 72 * 8, stream));
+      }
       CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream));
       CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream));
       CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream));
@@ -828,9 +838,18 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       CUDA_CHECK(cudaMemcpyAsync(vals.data(), r.fvals, ftableSize * 8, cudaMemcpyDeviceToHost, stream));
       CUDA_CHECK(cudaStreamSynchronize(stream));
       check_abort("K2b");
-      if (dbgK2)
+      if (dbgK2) {
         fprintf(stderr, "[K2 dbg] blocks: %zu triples %zu tasks %d tickets grid %d  kernels %.2f ms (done at +%.2f ms)\n", trIdx.size(),
                 tasks.size(), nTickets, grid, tm.ms(), now_ms() - k2t0);
+        unsigned long long d[72];
+        CUDA_CHECK(cudaMemcpy(d, a.dbg, 72 * 8, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[K2 dbg] blocks: last ticket of stripe level k ended at (ms):");
+        for (int k = 0; k < std::min(maxStripes, 64); k++) fprintf(stderr, " %.1f", (double)d[8 + k] * 1e-6);
+        fprintf(stderr, "\n");
+        fprintf(stderr, "[K2 dbg] blocks: mean ticket %.0f cyc, producer-wait %.1f%% of ticket cycles, slot-wait %.2e cyc, warps busy until exit: mean %.1f%% of the last warp's (%.2f ms), levels %d, widest level %d\n",
+                (double)d[3] / (double)std::max(d[2], 1ull), 100.0 * (double)d[0] / (double)std::max(d[3], 1ull), (double)d[1],
+                100.0 * (double)d[4] / ((double)warps * (double)std::max(d[5], 1ull)), (double)d[5] * 1e-6, maxStripes, blockLevelWidth);
+      }
       st.launches += 2;
       st.d2h_bytes += (int64_t)ftableSize * 16;
       if (overflow) {  // a probe sequence got long in one of the two tables
@@ -1042,8 +1061,6 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
 
   std::vector<int> blockTr, chainTr, redo;
   for (size_t i = 0; i < triples.size(); i++) (triples[i].chain ? chainTr : blockTr).push_back((int)i);
-  for (int tr : chainTr) chainCtas += (int)((lib.seqs[triples[tr].subject].size() + 63) / 64);
-  chainCtas = std::min((chainCtas + 3) / 4, numSMs * 2);
   // the fallback sweeps are long and narrow (a few warps busy for tens of ms): run them on a second stream from a
   // second host thread while the block-parallel path fills the machine
   std::exception_ptr chainErr;
@@ -1057,6 +1074,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     chainLaunched.store(1);
   });
   std::exception_ptr blockErr;
+  static const bool serialK2 = getenv("RMGPU_K2_SERIAL") != nullptr;  // experiment: no overlap of the two paths
+  if (serialK2) chainThread.join();
   try {
     run_blocks(blockTr, false, redo);
     if (!redo.empty()) {
@@ -1067,7 +1086,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   } catch (...) {
     blockErr = std::current_exception();
   }
-  chainThread.join();
+  if (chainThread.joinable()) chainThread.join();
   if (blockErr) std::rethrow_exception(blockErr);
   if (chainErr) std::rethrow_exception(chainErr);
   found.insert(found.end(), foundChain.begin(), foundChain.end());

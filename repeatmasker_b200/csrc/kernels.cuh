@@ -743,18 +743,14 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
 #pragma unroll
           for (int r = 0; r < R; r++) {
             const int hl = H[r];
-            int hnew = 0;
-            if (active && srow[r] >= 0) {
-              const int e = max(E[r] + a.ins_ext, hl + a.gap_init);
-              f = max(f + a.del_ext, hu + a.gap_init);
-              const int d = hd + smat[srow[r] + curQ];
-              hnew = max(max(e, f), max(d, 0));
-              E[r] = e;
-              needFull |= hnew >= a.minscore;
-            } else {
-              E[r] = NEGI;
-              f = NEGI;
-            }
+            const bool valid = active && srow[r] >= 0;
+            const int e = max(E[r] + a.ins_ext, hl + a.gap_init);
+            const int fn = max(f + a.del_ext, hu + a.gap_init);
+            const int d = hd + smat[(srow[r] + curQ) & 255];
+            const int hnew = valid ? max(max(e, fn), max(d, 0)) : 0;
+            E[r] = valid ? e : NEGI;
+            f = valid ? fn : NEGI;
+            needFull |= hnew >= a.minscore;
             hd = hl;
             H[r] = hnew;
             hu = hnew;
@@ -774,35 +770,41 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
           }
           uint32_t od = diagO, ou = inOH, of = inOF;
           diagO = inOH;
+          uint32_t ends = 0;  // candidate ends of this column, handled after the straight-line cells (see K2b)
 #pragma unroll
           for (int r = 0; r < R; r++) {
             const int hl = H[r];
             const uint32_t ol = oH[r];
             const bool valid = active && srow[r] >= 0;
-            const int sc_ = valid ? smat[srow[r] + curQ] : 0;
+            const int sc_ = smat[(srow[r] + curQ) & 255];
             const OriginCell c = origin_cell(valid, hl, ol, hu, ou, hd, od, sc_, (uint32_t)i1 * Lp1 + (uint32_t)(row0 + r + 1),
                                              E[r], oE[r], f, of, a.gap_init, a.ins_ext, a.del_ext);
-            if (c.viaDiag && c.h >= a.minscore) {
-              if (c.o == kOriginLeft) {
-                needFull = true;
-              } else {
-                // per-thread cache: one table update per (origin, lane crossing) instead of one per cell
-                const unsigned long long val = cand_val(c.h, i1, row0 + r + 1);
-                if (c.o == lastOrigin) {
-                  lastVal = val > lastVal ? val : lastVal;
-                } else {
-                  if (lastOrigin != kOriginLeft) origin_emit(a, ti, lastOrigin, lastVal);
-                  lastOrigin = c.o;
-                  lastVal = val;
-                }
-              }
-            }
+            ends |= (c.viaDiag && c.h >= a.minscore) ? (1u << r) : 0u;
             hd = hl;
             od = ol;
             H[r] = c.h;
             oH[r] = c.o;
             hu = c.h;
             ou = c.o;
+          }
+          if (ends) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+              if (ends & (1u << r)) {
+                if (oH[r] == kOriginLeft) {
+                  needFull = true;
+                } else {
+                  // per-thread cache: one table update per (origin, lane crossing) instead of one per cell
+                  const unsigned long long val = cand_val(H[r], i1, row0 + r + 1);
+                  if (oH[r] == lastOrigin) {
+                    lastVal = val > lastVal ? val : lastVal;
+                  } else {
+                    if (lastOrigin != kOriginLeft) origin_emit(a, ti, lastOrigin, lastVal);
+                    lastOrigin = oH[r];
+                    lastVal = val;
+                  }
+                }
+              }
           }
           outOH = ou;
           outOF = of;
@@ -861,6 +863,9 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
 // pseudo origins through those snapshots back to the real origin cell.  Origins are encoded relative to the task,
 // (i0 - c0) * (L + 1) + j0, which must stay below 2^31 (bit 31 marks pseudo origins).
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef K2B_MIN_CTAS
+#define K2B_MIN_CTAS 4
+#endif
 constexpr uint32_t kPseudoBit = 0x80000000u;
 constexpr uint32_t kPseudoEBit = 1u << 20;  // pseudo origin of the E state (else H) of boundary row (bits 0..19, 1-based)
 
@@ -902,6 +907,8 @@ struct BlockArgs {
   unsigned long long* vals;
   uint32_t tableMask;
   int* overflow;
+  unsigned long long* dbg;     // optional [8]: producer-wait cycles, slot-wait cycles, tickets, ticket cycles, sum and max of
+                               // (warp exit - first warp start) in ns, -, time base
 };
 
 __device__ __forceinline__ void table_emit(unsigned long long* keys, unsigned long long* vals, uint32_t mask, int* overflow,
@@ -918,18 +925,21 @@ __device__ __forceinline__ void table_emit(unsigned long long* keys, unsigned lo
   atomicExch(overflow, 1);
 }
 
-__global__ void __launch_bounds__(128) swg_origin_block_kernel(BlockArgs a) {
+__global__ void __launch_bounds__(128, K2B_MIN_CTAS) swg_origin_block_kernel(BlockArgs a) {
   __shared__ int32_t smat[16 * 16];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   constexpr int R = kR2;
   const int NEGI = -(1 << 28);
+  if (a.dbg && lane == 0) atomicCAS(&a.dbg[7], 0ull, globaltimer_ns());
   for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(a.ticket, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= a.nTickets) break;
+    const long long tk0 = clock64();
+    long long waitCyc = 0;
     const int ti = a.ticketTask[t];
     const BlockTask tk = a.tasks[ti];
     const int st = a.ticketStripe[t];  // stripe of this ticket
@@ -949,8 +959,10 @@ __global__ void __launch_bounds__(128) swg_origin_block_kernel(BlockArgs a) {
       for (int tOld = t - a.nslot; tOld >= 0; tOld -= a.nslot) {
         const int cOld = a.consTicket[tOld];
         if (cOld < 0) continue;  // that ticket had no stripe below: it wrote nothing
+        const long long g0 = clock64();
         if (lane == 0) wait_ge(&a.finished[cOld], 1, a.abort_flag);
         __syncwarp();
+        if (a.dbg && lane == 0) atomicAdd(&a.dbg[1], (unsigned long long)(clock64() - g0));
         break;
       }
     }
@@ -993,8 +1005,10 @@ __global__ void __launch_bounds__(128) swg_origin_block_kernel(BlockArgs a) {
       const int qv = (col < W) ? (int)qc[tk.c0 + col] : -1;
       OriginBoundary bv = {0, NEGI, 0, 0};
       if (hasPrev && b < qBlocks) {
+        const long long w0 = clock64();
         if (lane == 0 && ld_acquire(&a.progress[tProd]) < b + 1) wait_ge(&a.progress[tProd], b + 1, a.abort_flag);
         __syncwarp();
+        waitCyc += clock64() - w0;
         const int4 raw = __ldcg(reinterpret_cast<const int4*>(&bndIn[col]));
         bv.h = raw.x;
         bv.f = raw.y;
@@ -1028,31 +1042,40 @@ __global__ void __launch_bounds__(128) swg_origin_block_kernel(BlockArgs a) {
         if (cw >= 0) {  // before its first column a lane must keep the checkpointed state untouched
           diagH = inH;
           diagO = inOH;
+          // the R cells of the column are straight-line code (the score lookup is unconditional, candidate ends are only
+          // marked in a bit mask), so the compiler can overlap the parts of different rows that do not depend on the
+          // cell above; the rare candidate ends are handled after the column
+          uint32_t ends = 0;
 #pragma unroll
           for (int r = 0; r < R; r++) {
             const int hl = H[r];
             const uint32_t ol = oH[r];
             const bool valid = active && srow[r] >= 0;
-            const int sc_ = valid ? smat[srow[r] + curQ] : 0;
+            const int sc_ = smat[(srow[r] + curQ) & 255];
             const OriginCell c = origin_cell(valid, hl, ol, hu, ou, hd, od, sc_, (uint32_t)(cw + 1) * Lp1 + (uint32_t)(row0 + r + 1),
                                              E[r], oE[r], f, of, a.gap_init, a.ins_ext, a.del_ext);
-            if (c.viaDiag && c.h >= a.minscore) {
-              const unsigned long long val = cand_val(c.h, i1, row0 + r + 1);
-              if (c.o == lastOrigin) {
-                lastVal = val > lastVal ? val : lastVal;
-              } else {
-                if (lastOrigin != 0xFFFFFFFFu)
-                  table_emit(a.keys, a.vals, a.tableMask, a.overflow, ((unsigned long long)(uint32_t)ti << 32) | lastOrigin, lastVal);
-                lastOrigin = c.o;
-                lastVal = val;
-              }
-            }
+            ends |= (c.viaDiag && c.h >= a.minscore) ? (1u << r) : 0u;
             hd = hl;
             od = ol;
             H[r] = c.h;
             oH[r] = c.o;
             hu = c.h;
             ou = c.o;
+          }
+          if (ends) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+              if (ends & (1u << r)) {
+                const unsigned long long val = cand_val(H[r], i1, row0 + r + 1);
+                if (oH[r] == lastOrigin) {
+                  lastVal = val > lastVal ? val : lastVal;
+                } else {
+                  if (lastOrigin != 0xFFFFFFFFu)
+                    table_emit(a.keys, a.vals, a.tableMask, a.overflow, ((unsigned long long)(uint32_t)ti << 32) | lastOrigin, lastVal);
+                  lastOrigin = oH[r];
+                  lastVal = val;
+                }
+              }
           }
         }
         outH = hu;
@@ -1092,7 +1115,21 @@ __global__ void __launch_bounds__(128) swg_origin_block_kernel(BlockArgs a) {
     if (lastOrigin != 0xFFFFFFFFu)
       table_emit(a.keys, a.vals, a.tableMask, a.overflow, ((unsigned long long)(uint32_t)ti << 32) | lastOrigin, lastVal);
     __syncwarp();
-    if (lane == 0) st_release(&a.finished[t], 1);
+    if (lane == 0) {
+      st_release(&a.finished[t], 1);
+      if (a.dbg) {
+        atomicAdd(&a.dbg[0], (unsigned long long)waitCyc);
+        atomicAdd(&a.dbg[2], 1ull);
+        atomicAdd(&a.dbg[3], (unsigned long long)(clock64() - tk0));
+        // per stripe level (first 64): when its last ticket ended, relative to the first warp's start
+        if (st < 64) atomicMax(&a.dbg[8 + st], globaltimer_ns() - *(volatile unsigned long long*)&a.dbg[7]);
+      }
+    }
+  }
+  if (a.dbg && lane == 0) {
+    const unsigned long long dt = globaltimer_ns() - *(volatile unsigned long long*)&a.dbg[7];
+    atomicAdd(&a.dbg[4], dt);
+    atomicMax(&a.dbg[5], dt);
   }
 }
 
