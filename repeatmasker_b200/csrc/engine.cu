@@ -6,6 +6,7 @@
 //   queries   qpacked (4 bit/base, what crosses PCIe), sel (2 B/column, both strands), codes_fwd/codes_rc (1 B/base)
 //   scratch   stripe boundary ring (K1 8 B/column, K2 16 B/column), candidate table, traceback direction bytes
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstring>
 #include <map>
@@ -110,30 +111,6 @@ struct HitRec {
   int cpg = 0, wcb = 0;
   std::string qaln, saln;
 };
-
-// Static split of [0, n) over a few host threads (post-processing of independent records).
-template <typename F>
-void parallel_for(int n, F&& f) {
-  static const int hw = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  const int nt = std::min(hw, std::max(1, n / 8));
-  if (nt <= 1) {
-    for (int i = 0; i < n; i++) f(i);
-    return;
-  }
-  std::vector<std::thread> th;
-  std::vector<std::exception_ptr> err(nt);
-  for (int t = 0; t < nt; t++)
-    th.emplace_back([&, t] {
-      try {
-        for (int i = t; i < n; i += nt) f(i);
-      } catch (...) {
-        err[t] = std::current_exception();
-      }
-    });
-  for (auto& x : th) x.join();
-  for (auto& e : err)
-    if (e) std::rethrow_exception(e);
-}
 
 }  // namespace rmgpu
 
@@ -280,7 +257,8 @@ void rmgpu_session::set_library(SeqSet s) {
   std::vector<uint8_t> rowcode((size_t)nGroups * R, 0xFF), gflags(nGroups, 1), sflags(nStripes, 0);
   h_gsubject.assign(nGroups, -1);
   h_subjFirstGroup.assign(n, -1);
-  for (auto& pl : places) {
+  parallel_for((int)places.size(), [&](int pi) {  // subjects own disjoint groups
+    const Place& pl = places[pi];
     h_subjFirstGroup[pl.subject] = pl.firstGroup;
     const std::string& sq = lib.seqs[pl.subject];
     for (int gi = 0; gi < groups[pl.subject]; gi++) {
@@ -292,7 +270,7 @@ void rmgpu_session::set_library(SeqSet s) {
         if (pos < sq.size()) rowcode[(size_t)g * R + r] = matrix.code_of[(unsigned char)sq[pos]];
       }
     }
-  }
+  }, 32);
   for (int k = 0; k < nStripes; k++) {
     bool prev = !(gflags[k * 32] & 1);
     if (prev) {
@@ -310,9 +288,9 @@ void rmgpu_session::set_library(SeqSet s) {
     h_soff[i + 1] = h_soff[i] + slen[i];
   }
   std::vector<uint8_t> scodes((size_t)std::max<int64_t>(h_soff[n], 1));
-  for (int i = 0; i < n; i++)
-    for (size_t k = 0; k < lib.seqs[i].size(); k++)
-      scodes[h_soff[i] + k] = matrix.code_of[(unsigned char)lib.seqs[i][k]];
+  parallel_for(n, [&](int i) {
+    for (size_t k = 0; k < lib.seqs[i].size(); k++) scodes[h_soff[i] + k] = matrix.code_of[(unsigned char)lib.seqs[i][k]];
+  }, 32);
   d_rowcode.upload(rowcode, stream);
   d_gflags.upload(gflags, stream);
   d_sflags.upload(sflags, stream);
@@ -350,15 +328,25 @@ void rmgpu_session::set_queries(SeqSet s) {
   selTotal = h_selOff[n];
   std::vector<uint8_t> packed((size_t)(h_qoff[n] / 2 + 1), 0);
   int64_t counts[16] = {};
-  for (int i = 0; i < n; i++) {
-    const std::string& q = queries.seqs[i];
-    for (size_t k = 0; k < q.size(); k++) {
-      uint8_t c = matrix.code_of[(unsigned char)q[k]];
-      counts[c]++;
-      counts[matrix.comp_code[c]]++;
-      int64_t nib = h_qoff[i] + (int64_t)k;
-      packed[nib >> 1] |= (uint8_t)(c << ((nib & 1) * 4));
-    }
+  {
+    // every record starts on a byte of `packed` (even nibble offsets), so records are packed independently
+    std::vector<std::array<int64_t, 16>> cnt(n);
+    parallel_for(n, [&](int i) {
+      const std::string& q = queries.seqs[i];
+      std::array<int64_t, 16>& cc = cnt[i];
+      cc.fill(0);
+      for (size_t k = 0; k < q.size(); k++) {
+        uint8_t c = matrix.code_of[(unsigned char)q[k]];
+        cc[c]++;
+        int64_t nib = h_qoff[i] + (int64_t)k;
+        packed[nib >> 1] |= (uint8_t)(c << ((nib & 1) * 4));
+      }
+    }, 1);
+    for (int i = 0; i < n; i++)
+      for (int c = 0; c < 16; c++) {
+        counts[c] += cnt[i][c];
+        counts[matrix.comp_code[c]] += cnt[i][c];
+      }
   }
   // residue classes: up to 7 exact; beyond that the rarest codes share class 6 with row-wise max scores, which
   // makes K1 an upper bound (still an exact filter: K2 recomputes every passing pair with the full alphabet)

@@ -1,6 +1,9 @@
 // host.hpp -- host-side data model of librmgpu (C++17).  No oracle code is used anywhere in this directory.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <exception>
+#include <thread>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -8,6 +11,31 @@
 #include <vector>
 
 namespace rmgpu {
+
+// Static split of [0, n) over a few host threads (independent records: packing on the way in, post-processing on the
+// way out); at least `grain` items per thread.
+template <typename F>
+void parallel_for(int n, F&& f, int grain = 8) {
+  static const int hw = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const int nt = std::min(hw, std::max(1, n / std::max(grain, 1)));
+  if (nt <= 1) {
+    for (int i = 0; i < n; i++) f(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err(nt);
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([&, t] {
+      try {
+        for (int i = t; i < n; i += nt) f(i);
+      } catch (...) {
+        err[t] = std::current_exception();
+      }
+    });
+  for (auto& x : th) x.join();
+  for (auto& e : err)
+    if (e) std::rethrow_exception(e);
+}
 
 constexpr int kMaxAlpha = 16;  // 4-bit residue codes on the device
 

@@ -173,12 +173,24 @@ SeqSet SeqSet::from_fasta(const std::string& path) {
 
 SeqSet SeqSet::from_arrays(int32_t n, const char* const* names, const char* const* seqs, const int32_t* lens) {
   SeqSet s;
+  s.seqs.resize(n);
+  int64_t total = 0;
   for (int i = 0; i < n; i++) {
     s.names.emplace_back(names && names[i] ? names[i] : ("seq" + std::to_string(i)));
-    std::string q(seqs[i], (size_t)lens[i]);
-    for (auto& c : q) c = (char)std::toupper((unsigned char)c);
-    s.seqs.push_back(std::move(q));
+    total += lens[i];
   }
+  static const struct Upper {
+    char t[256];
+    Upper() {
+      for (int i = 0; i < 256; i++) t[i] = (char)std::toupper(i);
+    }
+  } upper;
+  parallel_for(n, [&](int i) {
+    std::string& q = s.seqs[i];
+    q.resize((size_t)lens[i]);
+    const char* src = seqs[i];
+    for (int32_t k = 0; k < lens[i]; k++) q[k] = upper.t[(unsigned char)src[k]];
+  }, total > (1 << 18) ? 1 : n + 1);
   return s;
 }
 
