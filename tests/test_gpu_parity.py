@@ -129,6 +129,44 @@ def test_int16_overflow_windows_start_at_a_checkpoint(tmp_path):
     assert st["n_origin_redo"] == 0
 
 
+def test_int16_overflow_at_both_ends_of_the_query(tmp_path):
+    """Two overflowing alignments of the same (query, subject, strand) triple, one starting at the first base of the
+    query and one ending at its last base: the int32 window has no checkpoint to start from and reaches the end."""
+    rng = np.random.default_rng(78)
+    long_s = synth.random_dna(rng, 8200).tobytes().decode()
+    copy1 = synth.mutate(rng, long_s[500:7000], 0.02, 0.002)
+    copy2 = synth.mutate(rng, long_s[1200:8000], 0.03, 0.003)
+    bg = synth.random_dna(rng, 12000).tobytes().decode()
+    q = copy1 + bg + copy2
+    got, want, st = both(tmp_path, ["q1"], [q], ["longS#LINE/L1"], [long_s])
+    assert sum(h["score"] > 32767 for h in want) == 2
+    assert_same_hits(got, want)
+
+
+def test_library_packing_edge_lengths(tmp_path):
+    """Subject lengths around the packing units (16-row groups, 512-row stripes, 4-stripe runs): subjects that end
+    exactly on a group / stripe / run boundary, one-base and 15-base subjects, a subject longer than a run whose last
+    stripe is topped up, and enough small ones to share stripes with the tails of longer ones."""
+    rng = np.random.default_rng(123)
+    lengths = [1, 15, 16, 17, 31, 32, 100, 511, 512, 513, 1024, 1040, 2047, 2048, 2049, 2560, 3000, 5000, 240, 250, 260, 270]
+    seqs = [synth.random_dna(rng, n).tobytes().decode() for n in lengths]
+    names = [f"s{i}_{n}#DNA/x" for i, n in enumerate(lengths)]
+    bg = synth.random_dna(rng, 30000).tobytes().decode()
+    parts, at = [], 0
+    for i, sq in enumerate(seqs):
+        if len(sq) < 60:
+            continue
+        copy = synth.mutate(rng, sq, 0.08 + 0.01 * (i % 5), 0.01)
+        if i % 2:
+            copy = synth.revcomp(copy)
+        parts.append(bg[at:at + 600] + copy)
+        at += 600
+    q = "".join(parts) + bg[at:at + 3000]
+    got, want, st = both(tmp_path, ["qpack"], [q], names, seqs)
+    assert len(want) >= 15
+    assert_same_hits(got, want)
+
+
 def test_alphabet_edge_cases(tmp_path):
     """N runs, X (masked), lower-case x (excision sentinel), IUPAC codes incl. B/D/H/V, >7 residue classes."""
     rng = np.random.default_rng(9)
