@@ -102,6 +102,47 @@ struct Candidate {
   int i0, j0, i1, j1, raw;
 };
 
+// Host view of a hot mask (kHotBlocks bits, bit c = column block c).
+struct HotMask {
+  unsigned long long w[kHotWords] = {};
+  static HotMask all() {
+    HotMask m;
+    for (auto& x : m.w) x = ~0ull;
+    return m;
+  }
+  bool none() const {
+    for (auto x : w)
+      if (x) return false;
+    return true;
+  }
+  bool test(int c) const { return (w[c >> 6] >> (c & 63)) & 1ull; }
+  HotMask operator|(const HotMask& o) const {
+    HotMask m;
+    for (int k = 0; k < kHotWords; k++) m.w[k] = w[k] | o.w[k];
+    return m;
+  }
+  HotMask shr1() const {  // bit c -> c - 1
+    HotMask m;
+    for (int k = 0; k < kHotWords; k++) m.w[k] = (w[k] >> 1) | (k + 1 < kHotWords ? w[k + 1] << 63 : 0ull);
+    return m;
+  }
+  HotMask shl1() const {  // bit c -> c + 1
+    HotMask m;
+    for (int k = 0; k < kHotWords; k++) m.w[k] = (w[k] << 1) | (k > 0 ? w[k - 1] >> 63 : 0ull);
+    return m;
+  }
+  int lowest() const {
+    for (int k = 0; k < kHotWords; k++)
+      if (w[k]) return 64 * k + __builtin_ctzll(w[k]);
+    return -1;
+  }
+  int highest() const {
+    for (int k = kHotWords - 1; k >= 0; k--)
+      if (w[k]) return 64 * k + 63 - __builtin_clzll(w[k]);
+    return -1;
+  }
+};
+
 struct HitRec {
   int score, raw, qidx, sidx, strand;
   int qstart, qend, qleft, sstart, send, sleft;
@@ -322,7 +363,7 @@ void rmgpu_session::set_queries(SeqSet s) {
     h_selOff[i + 1] = h_selOff[i] + h_selLen[i];
     maxQ = std::max<int>(maxQ, (int)Q);
     int sh = 0;
-    while ((((Q + 31) >> 5) + 1) >> sh > 63) sh++;  // at most 64 column blocks per query for the hot mask
+    while ((((Q + 31) >> 5) + 1) >> sh > kHotBlocks - 1) sh++;  // at most kHotBlocks column blocks per query (hot mask bits)
     h_hotShift.push_back(sh);
   }
   selTotal = h_selOff[n];
@@ -493,7 +534,7 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
                               std::vector<unsigned long long>& hotmask, double& ms, int& launches, bool exact) {
   const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
   pairbest.assign((size_t)nQ * nS * 2, 0);
-  hotmask.assign((size_t)nQ * nS * 2, 0);
+  hotmask.assign((size_t)nQ * nS * 2 * kHotWords, 0);
   ms = 0;
   if (nQ == 0 || nS == 0) return;
   if (p.gap_init >= 0 || p.ins_gap_ext > 0 || p.del_gap_ext > 0 || p.gap_init < -20000)
@@ -545,10 +586,10 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   a.minscore = std::max(1, std::min(p.minscore, ovfThresh) - scoreSlack);
   a.ovfThresh = ovfThresh;
   a.abort_flag = d_abort.ensure(1);
-  // column checkpoints for the origin pass (64 per query): only when they fit the budget
+  // column checkpoints for the origin pass (kHotBlocks per query): only when they fit the budget
   {
     static const bool noCk = getenv("RMGPU_NO_CHECKPOINTS") != nullptr;
-    const int64_t ckElems = (int64_t)nQ * 64 * nGroups * R;
+    const int64_t ckElems = (int64_t)nQ * kHotBlocks * nGroups * R;
     ckEnabled = !noCk && ckElems * (int64_t)sizeof(uint2) <= kCheckpointBudget;
     a.ck = ckEnabled ? d_ck.ensure((size_t)ckElems) : nullptr;
     a.ckRows = (int64_t)nGroups * R;
@@ -606,7 +647,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   static const bool fullMode = getenv("RMGPU_K2_FULL") != nullptr;
   struct Triple {
     int q, strand, subject;
-    unsigned long long dil;
+    HotMask dil;
     bool chain;
   };
   std::vector<Triple> triples;
@@ -619,17 +660,18 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         if ((Q + 1) * (L + 1) >= (1ll << 32))
           throw Error("query x subject too large for one origin pass (" + queries.names[q] + " x " + lib.names[s] +
                       "): fragment the query as SimpleBatcher does");
-        const unsigned long long m = hotmask[idx];
+        HotMask m;
+        for (int k = 0; k < kHotWords; k++) m.w[k] = hotmask[idx * kHotWords + k];
         Triple t;
         t.q = q;
         t.strand = strand;
         t.subject = s;
         // K1 files a cell under the block its warp is in, which for lanes lagging behind is the block AFTER the cell's
         // own, and an alignment may start before the block in which it first reaches minscore: add the block before
-        t.dil = m | (m >> 1);
+        t.dil = m | m.shr1();
         const int64_t CB = 32ll << h_hotShift[q];
         // checkpoints are exact only when K1 is (no merged residue class, no int16 wrap)
-        t.chain = pairbest[idx] >= 32767 || fullMode || !ckEnabled || !classesExact || t.dil == 0 ||
+        t.chain = pairbest[idx] >= 32767 || fullMode || !ckEnabled || !classesExact || t.dil.none() ||
                   (CB + 2) * (L + 1) >= (1ll << 31);
         triples.push_back(t);
       }
@@ -658,9 +700,9 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       const int64_t CB = 32ll << h_hotShift[T.q];
       const int nblk = (int)((Q + CB - 1) / CB);
       int prev = -1;
-      for (int c = 0; c < nblk && c < 64; c++) {
-        // bit 63 stands for every block >= 63
-        const bool on = allBlocks || ((T.dil >> std::min(c, 63)) & 1ull);
+      for (int c = 0; c < nblk && c < kHotBlocks; c++) {
+        // the last bit stands for every block from there on
+        const bool on = allBlocks || T.dil.test(std::min(c, kHotBlocks - 1));
         if (!on) {
           prev = -1;
           continue;
@@ -672,9 +714,9 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         t.subject = T.subject;
         t.triple = tr;
         t.c0 = (int)(c * CB);
-        t.c1 = (c == 63) ? (int)Q : (int)std::min<int64_t>(Q, (c + 1) * CB);
+        t.c1 = (c == kHotBlocks - 1) ? (int)Q : (int)std::min<int64_t>(Q, (c + 1) * CB);
         t.prevTask = prev;
-        t.ckOff = c > 0 ? ((int64_t)T.q * 64 + c) * ((int64_t)nGroups * R) + (int64_t)h_subjFirstGroup[T.subject] * R : -1;
+        t.ckOff = c > 0 ? ((int64_t)T.q * kHotBlocks + c) * ((int64_t)nGroups * R) + (int64_t)h_subjFirstGroup[T.subject] * R : -1;
         t.snapOff = snapTot;
         snapTot += 2 * L;
         prev = (int)tasks.size();
@@ -880,6 +922,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     for (int tr : trIdx) stripes8 += (int64_t)(lib.seqs[triples[tr].subject].size() + 255) / 256;
     const int chainR = (stripes8 * 4 <= (int64_t)numSMs * 16) ? 2 : 8;
     std::vector<OriginTask> tasks;
+    std::vector<char> taskFull;  // swept with origins over the whole query
     std::vector<int32_t> ticketTask;
     for (int tr : trIdx) {
       const Triple& T = triples[tr];
@@ -894,25 +937,35 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       // after an int16 wrap K1 under-reports the blocks that follow (true scores decay by only ~5-6 per column along
       // a gap), so the mask is stretched 8 blocks forward; a cell >= minscore met in a score-only block still forces
       // a full redo of the task, so exactness never depends on this guess
-      unsigned long long fwd = T.dil;
-      if (pairbest[idx] >= 32767)
-        for (int k = 1; k <= 8; k++) fwd |= T.dil << k;
-      t.mode = (fullMode || T.dil == 0) ? ~0ull : fwd;
+      HotMask fwd = T.dil;
+      const int64_t CBq = 32ll << h_hotShift[T.q];
+      if (pairbest[idx] >= 32767) {
+        const int stretch = (int)std::max<int64_t>(8, (8192 + CBq - 1) / CBq);  // at least 8 blocks and 8192 columns
+        HotMask sh = T.dil;
+        for (int k = 1; k <= stretch; k++) {
+          sh = sh.shl1();
+          fwd = fwd | sh;
+        }
+      }
+      const bool fullSweep = fullMode || T.dil.none();
+      const HotMask modeMask = fullSweep ? HotMask::all() : fwd;
+      for (int k = 0; k < kHotWords; k++) t.mode[k] = modeMask.w[k];
+      taskFull.push_back(fullSweep ? 1 : 0);
       t.hotShift = h_hotShift[T.q];
       t.c0 = 0;
       t.c1 = h_qlen[T.q];
       t.ckOff = -1;
-      if (pairbest[idx] >= 32767 && t.mode != ~0ull && ckEnabled && classesExact) {
+      if (pairbest[idx] >= 32767 && !fullSweep && ckEnabled && classesExact) {
         // int16 wrap: K1 is exact up to the first hot block (a score passes minscore long before it wraps), so the
         // sweep starts at the checkpoint before the first block of the mask; to the right of the last one K1 saw
         // nothing >= minscore, and since a wrap only ever LOWERS K1's values (the wrapped sum is negative and loses
         // every max) a path it missed there descends from the wrapped alignment and scores below its maximum --
         // unless it leaves the window at >= minscore, which the kernel reports (then the task is redone in full)
-        const int64_t CB = 32ll << h_hotShift[T.q];
-        const int lo = __builtin_ctzll(fwd), hi = 63 - __builtin_clzll(fwd);
+        const int64_t CB = CBq;
+        const int lo = fwd.lowest(), hi = fwd.highest();
         t.c0 = (int)std::min<int64_t>(lo * CB, h_qlen[T.q]);
-        if (lo > 0) t.ckOff = ((int64_t)T.q * 64 + lo) * ((int64_t)nGroups * R) + (int64_t)h_subjFirstGroup[T.subject] * R;
-        if (hi < 63) t.c1 = (int)std::min<int64_t>(h_qlen[T.q], (hi + 1) * CB);
+        if (lo > 0) t.ckOff = ((int64_t)T.q * kHotBlocks + lo) * ((int64_t)nGroups * R) + (int64_t)h_subjFirstGroup[T.subject] * R;
+        if (hi < kHotBlocks - 1) t.c1 = (int)std::min<int64_t>(h_qlen[T.q], (hi + 1) * CB);
         if (t.c0 >= t.c1) t.c0 = 0, t.c1 = h_qlen[T.q], t.ckOff = -1;
       }
       t.firstTicket = (int)ticketTask.size();
@@ -1029,15 +1082,16 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       bool any = false;
       for (size_t i = 0; i < tasks.size(); i++) {
         if (leftFlag[i]) {
-          if (tasks[i].mode == ~0ull) throw Error("origin pass: a fully swept task still reports a left origin");
-          tasks[i].mode = ~0ull;
+          if (taskFull[i]) throw Error("origin pass: a fully swept task still reports a left origin");
+          taskFull[i] = 1;
+          for (int k = 0; k < kHotWords; k++) tasks[i].mode[k] = ~0ull;
           tasks[i].c0 = 0;
           tasks[i].c1 = h_qlen[tasks[i].q];
           tasks[i].ckOff = -1;
           any = true;
           chainRedo++;
         } else {
-          tasks[i].mode = 0;  // done: nothing to sweep with origins, and nothing >= minscore can appear
+          for (int k = 0; k < kHotWords; k++) tasks[i].mode[k] = 0;  // done: nothing to sweep with origins, and nothing >= minscore can appear
           tasks[i].c0 = 0;
           tasks[i].c1 = 0;    // (an empty window makes the ticket a no-op)
           tasks[i].ckOff = -1;
@@ -1275,7 +1329,7 @@ struct IntervalUnion {  // disjoint, merged closed intervals
 
 }  // namespace
 
-// How many query records one pass may hold: the K1 column checkpoints (64 x rows x 8 B per query) and the stripe
+// How many query records one pass may hold: the K1 column checkpoints (kHotBlocks x rows x 8 B per query) and the stripe
 // boundary ring (up to stripes x columns x 8 B per query) must fit in a share of the free HBM.
 int rmgpu_session::query_capacity() const {
   static const char* capEnv = getenv("RMGPU_QUERY_CHUNK");
@@ -1285,8 +1339,8 @@ int rmgpu_session::query_capacity() const {
   const long long freeNow = freeAtOpen - (g_devbuf_bytes.load() - devbufAtOpen);
   const size_t freeB = (size_t)std::max<long long>(freeNow, 0);
   const double budget = 0.45 * (double)(freeB + d_ck.cap * sizeof(uint2) + d_bnd1.cap * 8);
-  const double perQuery = 64.0 * nGroups * R * 8.0 + (double)nStripes * ((double)maxQ + 64.0) * 8.0;
-  const double byCk = (double)kCheckpointBudget / std::max(64.0 * nGroups * R * 8.0, 1.0);
+  const double perQuery = (double)kHotBlocks * nGroups * R * 8.0 + (double)nStripes * ((double)maxQ + 64.0) * 8.0;
+  const double byCk = (double)kCheckpointBudget / std::max((double)kHotBlocks * nGroups * R * 8.0, 1.0);
   return (int)std::max(1.0, std::floor(std::min(budget / std::max(perQuery, 1.0), byCk)));
 }
 

@@ -19,6 +19,15 @@ namespace rmgpu {
 constexpr int kPadClass = 7;            // residue class whose score is very negative: columns outside the query
 constexpr uint32_t kPadSel = 0xF7F7u;   // PRMT selector picking class 7 for both strands (sign-replicated)
 constexpr int kWarp = 32;
+#ifndef K2_LAG
+#define K2_LAG 2
+#endif
+constexpr int kLagSweep = K2_LAG;  // the same for the (latency-bound) int32 sweeps, whose pipelines are ~100 stripes deep: the fill is lag x depth
+#ifndef RMGPU_HOT_WORDS
+#define RMGPU_HOT_WORDS 2
+#endif
+constexpr int kHotWords = RMGPU_HOT_WORDS;   // 64-bit words of a hot mask
+constexpr int kHotBlocks = 64 * kHotWords;  // column blocks per query record: hot-mask bits = K1 column checkpoints
 constexpr int kLag = 4;                 // blocks of slack a consumer stripe rebuilds whenever it catches its producer
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -168,7 +177,7 @@ struct ScoreArgs {
   int minscore;               // hot-mask threshold (already lowered by the sampling slack in the search path)
   int ovfThresh;              // a best at or above this is reported as 32767 = "int16 may have wrapped, redo in int32"
   int* abort_flag;            // set by the watchdog
-  uint2* ck;                  // optional column checkpoints [(q*64 + cb) * ckRows + g*R + r] = (H, E') before column cb*CB
+  uint2* ck;                  // optional column checkpoints [(q*kHotBlocks + cb) * ckRows + g*R + r] = (H, E') before column cb*CB
   int64_t ckRows;             // nGroups * R
   unsigned long long* dbg;    // optional [8]: cycles waiting on the producer, cycles waiting on a slot, tasks, task cycles,
                               // sum and max over warps of (exit time - first warp's start) in ns, -, base time
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
 #endif
           if (CK && (K1_SPLIT_CK || ckBlock) && j == lane) {
             // column checkpoint for the origin pass: the (H, E') this lane holds before it starts column b*32 = cb*CB
-            uint2* dst = a.ck + ((int64_t)q * 64 + (b >> hotShift)) * a.ckRows + (int64_t)g * R;
+            uint2* dst = a.ck + ((int64_t)q * kHotBlocks + (b >> hotShift)) * a.ckRows + (int64_t)g * R;
 #pragma unroll
             for (int r = 0; r < R; r++) dst[r] = make_uint2(H[r], E[r]);
           }
@@ -407,10 +416,11 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           const bool hf = (int)(int16_t)(bestBlk & 0xffffu) >= a.minscore;
           const bool hr = (int)(int16_t)(bestBlk >> 16) >= a.minscore;
           if (hf | hr) {
-            unsigned long long* hm = a.hotmask + ((int64_t)q * a.nSubjects + sj) * 2;
-            const unsigned long long bit = 1ull << min(b >> hotShift, 63);
-            if (hf) atomicOr(hm, bit);
-            if (hr) atomicOr(hm + 1, bit);
+            unsigned long long* hm = a.hotmask + ((int64_t)q * a.nSubjects + sj) * 2 * kHotWords;  // [strand][word]
+            const int blk = min(b >> hotShift, kHotBlocks - 1);
+            const unsigned long long bit = 1ull << (blk & 63);
+            if (hf) atomicOr(hm + (blk >> 6), bit);
+            if (hr) atomicOr(hm + kHotWords + (blk >> 6), bit);
           }
         }
         best = __vmaxs2(best, bestBlk);
@@ -510,8 +520,8 @@ constexpr uint32_t kOriginLeft = 0xFFFFFFFFu;  // "the origin lies in a part of 
 struct OriginTask {
   int32_t q, strand, subject;
   int32_t firstTicket, nStripes;  // stripes of kR2*32 rows
-  unsigned long long mode;        // bit c: sweep column block c with origin propagation (else score only)
-  int32_t hotShift;               // column block c = ((column >> 5) >> hotShift), capped at 63
+  unsigned long long mode[kHotWords];  // bit c: sweep column block c with origin propagation (else score only)
+  int32_t hotShift;               // column block c = ((column >> 5) >> hotShift), capped at kHotBlocks - 1
   int32_t c0, c1;                 // query columns [c0, c1) swept by this task (0-based)
   int32_t pad_;
   int64_t ckOff;                  // offset of the subject's first row in the K1 checkpoint taken before column c0, or -1
@@ -698,7 +708,7 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
       if (hasPrev && b < qBlocks) {
         // hysteresis: when the producer is not ahead, let it get kLag blocks ahead so that later blocks need no sleep
         const long long w0 = clock64();
-        if (lane == 0 && ld_acquire(&a.progress[t - 1]) < b + 1) wait_ge(&a.progress[t - 1], min(b + kLag, qBlocks), a.abort_flag);
+        if (lane == 0 && ld_acquire(&a.progress[t - 1]) < b + 1) wait_ge(&a.progress[t - 1], min(b + kLagSweep, qBlocks), a.abort_flag);
         __syncwarp();
         k2wait += clock64() - w0;
         const int4 raw = __ldcg(reinterpret_cast<const int4*>(&bndIn[col]));
@@ -709,8 +719,15 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
       }
       // mode of this lane's column: lanes lag the block by `lane` columns, so two 32-column blocks are involved
       const int b0 = tk.c0 >> 5;  // windows start on 32-column boundaries
-      const bool modeCur = (tk.mode >> min((b0 + b) >> tk.hotShift, 63)) & 1ull;
-      const bool modeOld = b > 0 ? (bool)((tk.mode >> min((b0 + b - 1) >> tk.hotShift, 63)) & 1ull) : modeCur;
+      auto mode_bit = [&](int blk32) {
+        const int blk = min(blk32 >> tk.hotShift, kHotBlocks - 1);
+        unsigned long long w = tk.mode[0];
+#pragma unroll
+        for (int k = 1; k < kHotWords; k++) w = (blk >> 6) == k ? tk.mode[k] : w;
+        return (bool)((w >> (blk & 63)) & 1ull);
+      };
+      const bool modeCur = mode_bit(b0 + b);
+      const bool modeOld = b > 0 ? mode_bit(b0 + b - 1) : modeCur;
       for (int j = 0; j < 32; j++) {
         int inQ = __shfl_up_sync(0xffffffffu, curQ, 1);
         int inH = __shfl_up_sync(0xffffffffu, outH, 1);
