@@ -279,6 +279,8 @@ def main():
                          "achieved": achieved, "peak": peak_cups / 1e9, "unit": "GCUPS", "frac": achieved / (peak_cups / 1e9),
                          "peak_source": "rmgpu_measure_dpx_peak: register-resident loop of the same recurrence, measured live on this GPU",
                          "traffic": traffic_from_profile(cells_step), "k1_ms_per_launch": k1_ms, "dpx_warp_instr_per_s": dpx_ips,
+                         # SURVEY 8(d)'s alternative denominator: raw DPX issue rate x 32 lanes x 2 cells / 5 instructions per cell pair
+                         "frac_of_dpx_issue_bound": achieved * 1e9 / (dpx_ips * 32 * 2 / 5) if dpx_ips else None,
                          "hbm_algorithmic_gbs": (Q / 2 + sum(len(x) for x in sseqs) * 8) / (k1_ms * 1e-3) / 1e9,
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},
             "stage_ms": {k: sum(s[k] for s in st_res) / len(st_res) for k in ("ms_score", "ms_origin", "ms_traceback", "ms_host_post", "ms_total")},
