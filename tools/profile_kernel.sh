@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu --set full of one origin-pass kernel on the bench workload, after the same command ran plain.
-# usage: profile_k2b.sh [kernel regex, default swg_origin_block_kernel] [output name]
+# usage: profile_kernel.sh [kernel regex, default swg_origin_block_kernel] [output name]
 cd /root/repo; mkdir -p gpurun_out
 K=${1:-swg_origin_block_kernel}; O=${2:-k2b_full}
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
