@@ -269,8 +269,7 @@ void rmgpu_session::set_library(SeqSet s) {
     groups[i] = (int)((lib.seqs[i].size() + R - 1) / R);
     if (groups[i] > 0) pool.insert({groups[i], -i});  // -i: among equal sizes the lowest index is the last element
   }
-  static const int capStripes = getenv("RMGPU_PACK_RUN") ? std::max(1, atoi(getenv("RMGPU_PACK_RUN"))) : kPackRunStripes;
-  const int cap = capStripes * 32;
+  const int cap = kPackRunStripes * 32;
   struct Place {
     int subject, firstGroup;
   };
@@ -1116,8 +1115,6 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     chainLaunched.store(1);
   });
   std::exception_ptr blockErr;
-  static const bool serialK2 = getenv("RMGPU_K2_SERIAL") != nullptr;  // experiment: no overlap of the two paths
-  if (serialK2) chainThread.join();
   try {
     run_blocks(blockTr, false, redo);
     if (!redo.empty()) {

@@ -2,9 +2,12 @@
 //
 //   K0 build_streams      packed 4-bit query -> per-column PRMT selector stream (both strands) + 1-byte code streams
 //   K0 build_profile      packed library rows -> 8-byte per-row score profile for the batch's residue classes
-//   K1 swg_score_kernel   strand-paired int16x2 Smith-Waterman-Gotoh score pass (DPX: VIADDMNMX/VIMNMX3/VIADD.16x2)
-//   K2 swg_origin_kernel  int32 Smith-Waterman-Gotoh with alignment-origin propagation -> candidate table
-//   K3 traceback_kernel   banded global traceback between origin and end cell
+//   K1 swg_score_kernel        strand-paired int16x2 Smith-Waterman-Gotoh score pass (DPX: VIADDMNMX/VIMNMX3/VIADD.16x2):
+//                              best per (query, subject, strand), hot column blocks, column checkpoints
+//   K2b swg_origin_block_kernel int32 Smith-Waterman-Gotoh with alignment-origin propagation over the hot column blocks
+//                              only, started from K1's checkpoints; resolve_candidates_kernel -> candidate table
+//   K2 swg_origin_kernel       the same as one sweep over a window of the query (triples K1 cannot checkpoint exactly)
+//   K3 traceback_kernel        banded global traceback between origin and end cell
 //
 // Scoring convention (SearchResult.pm:1829-1852, :1894-1917): score = M[subject][query]; the first base of a gap
 // costs gap_init, further bases ins_gap_ext (gap in the subject row, "E") or del_gap_ext (gap in the query row, "F").
@@ -19,16 +22,11 @@ namespace rmgpu {
 constexpr int kPadClass = 7;            // residue class whose score is very negative: columns outside the query
 constexpr uint32_t kPadSel = 0xF7F7u;   // PRMT selector picking class 7 for both strands (sign-replicated)
 constexpr int kWarp = 32;
-#ifndef K2_LAG
-#define K2_LAG 2
-#endif
-constexpr int kLagSweep = K2_LAG;  // the same for the (latency-bound) int32 sweeps, whose pipelines are ~100 stripes deep: the fill is lag x depth
-#ifndef RMGPU_HOT_WORDS
-#define RMGPU_HOT_WORDS 2
-#endif
-constexpr int kHotWords = RMGPU_HOT_WORDS;   // 64-bit words of a hot mask
-constexpr int kHotBlocks = 64 * kHotWords;  // column blocks per query record: hot-mask bits = K1 column checkpoints
-constexpr int kLag = 4;                 // blocks of slack a consumer stripe rebuilds whenever it catches its producer
+constexpr int kLag = 4;                 // blocks of slack a K1 consumer stripe rebuilds whenever it catches its producer
+constexpr int kLagSweep = 2;            // the same for the latency-bound int32 sweeps of K2, whose pipelines are ~100
+                                        // stripes deep: their fill time is lag x depth
+constexpr int kHotWords = 2;                // 64-bit words of a hot mask
+constexpr int kHotBlocks = 64 * kHotWords;  // column blocks per query record = hot-mask bits = K1 column checkpoints
 
 // ---------------------------------------------------------------------------------------------------------------
 // Inter-warp systolic pipeline through global memory.
@@ -150,8 +148,8 @@ __global__ void build_profile_kernel(ProfileArgs a) {
 // (the last line is F'[j+1] = max(F'[j]+del_ext, H[j]) with H expanded; it makes the F' recurrence the ONLY serial
 // dependency down a column -- one instruction per row -- so a single warp keeps the DPX pipe busy)
 // Lane t works on column (step - t): an anti-diagonal wavefront; the last row's (H, F') and the column's selector
-// move one lane down per step by warp shuffle.  int16 overflow: a pair whose best reaches 32000 is re-done by K2 in
-// int32 like every pair with best >= minscore, so wrapped values never reach a result.
+// move one lane down per step by warp shuffle.  int16 overflow: a triple whose best comes near 32767 is reported as
+// 32767 and swept in int32 by K2 like every triple with best >= minscore, so wrapped values never reach a result.
 // ---------------------------------------------------------------------------------------------------------------
 struct ScoreArgs {
   const uint2* prof;          // [nGroups * R]
@@ -203,16 +201,7 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 }
 
 constexpr int kScoreWarps = 8;
-#ifndef K1_UNROLL
-#define K1_UNROLL 8
-#endif
-constexpr int kK1Unroll = K1_UNROLL;
-#ifndef K1_IMAD_SELECT
-#define K1_IMAD_SELECT 1
-#endif
-#ifndef K1_SPLIT_CK
-#define K1_SPLIT_CK 1
-#endif  // columns per trip of K1's inner loop
+constexpr int kK1Unroll = 8;  // columns per trip of K1's inner loop (4: +3 % time, 16: the loop outgrows the instruction cache)  // columns per trip of K1's inner loop
 
 // EXACT: the running best is folded in at every cell (rmgpu_session_score_only, tests).  !EXACT (the search path, where
 // K1 is only a filter): the best is sampled from E' every 8th column.  E'[i][j] = max_k (H[i-k][j] + (k-1)*ins_ext), so
@@ -276,11 +265,9 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     const int sj = a.gsubject[g];
     uint32_t best = 0, bestBlk = 0, outH = 0, outF = 0, diag = 0, curSel = kPadSel;
     uint32_t nextSel = lane == 0 ? (uint32_t)sel[0] : kPadSel;  // selector of this lane's next column, one step ahead
-#if K1_IMAD_SELECT
     // 0/1 factors, made opaque so that they stay multiplications
     uint32_t keepSel = lane != 0, feedSel = lane == 0, keepHF = lane != 0 && !startFlag, feedHF = lane == 0 && !startFlag;
     asm volatile("" : "+r"(keepSel), "+r"(feedSel), "+r"(keepHF), "+r"(feedHF));
-#endif
     unsigned long long nextRaw = 0;
     if (hasPrev) nextRaw = ld_relaxed_u64(&bndIn[lane]);
     for (int b = 0; b < nBlocks; b++) {
@@ -343,24 +330,12 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           uint32_t inF = __shfl_up_sync(0xffffffffu, outF, 1);
           const uint4 fd = s_feed[wib][j];  // broadcast read
           const uint32_t fdSelNext = s_feed[wib][j + 1].x;
-#if K1_IMAD_SELECT
           // lane 0 takes the feed, a lane that starts a subject takes zeros: as multiply-adds by 0/1 factors, which
           // issue on the FMA pipe instead of five SELs on the (saturated) integer pipe
           nextSel = inSel * keepSel + fdSelNext * feedSel;
           inH = inH * keepHF + fd.y * feedHF;
           inF = inF * keepHF + fd.z * feedHF;
-#else
-          nextSel = lane == 0 ? fdSelNext : inSel;
-          if (lane == 0) {
-            inH = fd.y;
-            inF = fd.z;
-          }
-          if (startFlag) {
-            inH = 0;
-            inF = 0;
-          }
-#endif
-          if (CK && (K1_SPLIT_CK || ckBlock) && j == lane) {
+          if (CK && j == lane) {
             // column checkpoint for the origin pass: the (H, E') this lane holds before it starts column b*32 = cb*CB
             uint2* dst = a.ck + ((int64_t)q * kHotBlocks + (b >> hotShift)) * a.ckRows + (int64_t)g * R;
 #pragma unroll
@@ -401,14 +376,10 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           }
         }
       };
-#if K1_SPLIT_CK
       if (ckBlock)
         columns(std::true_type{});
       else
         columns(std::false_type{});
-#else
-      if (ckBlock || true) columns(std::true_type{});
-#endif
       // column-block bookkeeping for the origin pass: which blocks hold a cell >= minscore
       if ((((b + 1) >> hotShift) != (b >> hotShift)) || b == nBlocks - 1) {
         if (sj >= 0) {
@@ -880,9 +851,6 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
 // pseudo origins through those snapshots back to the real origin cell.  Origins are encoded relative to the task,
 // (i0 - c0) * (L + 1) + j0, which must stay below 2^31 (bit 31 marks pseudo origins).
 // ---------------------------------------------------------------------------------------------------------------
-#ifndef K2B_MIN_CTAS
-#define K2B_MIN_CTAS 4
-#endif
 constexpr uint32_t kPseudoBit = 0x80000000u;
 constexpr uint32_t kPseudoEBit = 1u << 20;  // pseudo origin of the E state (else H) of boundary row (bits 0..19, 1-based)
 
@@ -942,7 +910,7 @@ __device__ __forceinline__ void table_emit(unsigned long long* keys, unsigned lo
   atomicExch(overflow, 1);
 }
 
-__global__ void __launch_bounds__(128, K2B_MIN_CTAS) swg_origin_block_kernel(BlockArgs a) {
+__global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
   __shared__ int32_t smat[16 * 16];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
   __syncthreads();
