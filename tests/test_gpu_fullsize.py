@@ -148,3 +148,112 @@ def test_many_family_library_against_oracle(tmp_path):
         for k in ("score", "div", "dele", "ins", "qname", "qstart", "qend", "strand", "sname", "sstart", "send", "star",
                   "qaln", "saln"):
             assert g[k] == w[k], (k, g, w)
+
+
+def _gc_block_genome(seed, sseqs, block_bp):
+    """BASELINE configuration 4's query: blocks at 37/41/45/51 % GC with implanted copies, 15 % of the length in planted
+    (CA)n / (A)n / (GAA)n tracts and AT-rich low-complexity runs."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    blocks = []
+    for k, gc in enumerate((0.37, 0.41, 0.45, 0.51)):
+        g, _ = synth.make_genome(seed + 17 * k, block_bp, sseqs, coverage=0.35, gc=gc)
+        g = list(g)
+        planted = 0
+        while planted < 0.15 * block_bp:
+            n = int(rng.integers(40, 260))
+            kind = int(rng.integers(4))
+            if kind == 0:
+                tract = ("CA" * n)[:n]
+            elif kind == 1:
+                tract = "A" * n
+            elif kind == 2:
+                tract = ("GAA" * n)[:n]
+            else:
+                tract = "".join("AT"[int(x)] if rng.random() < 0.9 else "ACGT"[int(rng.integers(4))] for x in rng.integers(0, 2, n))
+            tract = "".join(c if rng.random() > 0.03 else "ACGT"[int(rng.integers(4))] for c in tract)  # a little decay
+            at = int(rng.integers(0, block_bp - n))
+            g[at:at + n] = tract
+            planted += n
+        blocks.append("".join(g))
+    return "".join(blocks)
+
+
+@pytest.mark.parametrize("matrix,gi,ie,de,raw,minscore", [("14p41g.matrix", -35, -7, -6, False, 225),
+                                                          ("25p41g.matrix", -27, -6, -5, True, 300),
+                                                          ("18p41g.matrix", -30, -6, -5, False, 180)])
+def test_config4_scale_low_complexity_properties(tmp_path, matrix, gi, ie, de, raw, minscore):
+    """BASELINE configuration 4 at a size the oracle cannot do in a test (240 kbp x 0.6 Mbp library + simple-repeat
+    consensi, ~2.9e11 cells, tens of thousands of hits from the planted tracts): every reported alignment re-scores
+    exactly (raw and complexity-adjusted, checked with the oracle's scoring function under the same matrix and gap
+    penalties), output order holds, one hit per origin, and a second run is identical."""
+    snames, sseqs = synth.make_library(1001, n_families=500)
+    snames = snames + ["(CA)n#Simple_repeat", "(A)n#Simple_repeat", "(GAA)n#Simple_repeat", "AT_rich#Low_complexity"]
+    sseqs = sseqs + ["CA" * 90, "A" * 150, "GAA" * 60, "AT" * 50 + "A" * 20 + "TA" * 40]
+    genome = _gc_block_genome(1003, sseqs[:500], 60000)
+    qn, qs = synth.fragment(genome, "gcblocks", frag=60000, overlap=2000)
+    m = util.write_matrix(matrix, str(tmp_path / matrix))
+    s = engine.Session()
+    s.set_matrix(m)
+    s.set_library(sseqs, snames)
+    s.set_queries(qs, qn)
+    p = engine.make_params(gap_init=gi, ins_gap_ext=ie, del_gap_ext=de, minscore=minscore, raw=raw)
+    hits, st = s.search(p)
+    assert len(hits) > 2000 and sum(h["sname"].endswith("Simple_repeat") for h in hits) > 1000
+    om = util.parse_matrix(m)
+    op = util.OraParams(gap_init=gi, ins_gap_ext=ie, del_gap_ext=de)
+    lib = util.oracle_lib()
+    for h in hits:
+        r, adj = C.c_int(), C.c_int()
+        lib.ora_rescore(h["qaln"].encode(), h["saln"].encode(), C.byref(om), C.byref(op), C.byref(r), C.byref(adj))
+        assert r.value == h["raw_score"], h
+        assert h["score"] == (r.value if raw else adj.value) >= minscore, h
+    qi = {n: i for i, n in enumerate(qn)}
+    si = {n: i for i, n in enumerate(snames)}
+    key = lambda h: (qi[h["qname"]], h["qstart"], -si[h["sname"]], h["sstart"], h["qend"], h["strand"] == "C", h["send"])
+    assert [key(h) for h in hits] == sorted(key(h) for h in hits)
+    seen = set()
+    for h in hits:
+        k = (h["qname"], h["strand"], h["sname"], h["qstart"] if h["strand"] == "+" else h["qend"], h["sstart"])
+        assert k not in seen, k
+        seen.add(k)
+    again, _ = s.search(p)
+    assert again == hits
+    s.close()
+
+
+def test_config5_scale_library_properties(tmp_path):
+    """BASELINE configuration 5's library scale (20,000 families, 23.9 Mbp, 46,700 stripes; 24 GB of column checkpoints
+    per query record, so two records are searched in two chunks) against two fragments: alignments re-score exactly,
+    order holds, and the chunked result equals the per-record results."""
+    snames, sseqs = synth.make_library(1005, n_families=20000)
+    genome, _ = synth.make_genome(1005, 100000, sseqs, coverage=0.45)
+    qn, qs = synth.fragment(genome, "chr", frag=60000, overlap=2000)
+    assert len(qs) == 2
+    m = util.write_matrix("20p41g.matrix", str(tmp_path / "20p41g.matrix"))
+    s = engine.Session()
+    s.set_matrix(m)
+    s.set_library(sseqs, snames)
+    s.set_queries(qs, qn)
+    p = engine.make_params()
+    hits, st = s.search(p)
+    assert len(hits) > 50 and st["cells"] == 2.0 * sum(map(len, qs)) * sum(map(len, sseqs))
+    om = util.parse_matrix(m)
+    op = util.OraParams(gap_init=-30, ins_gap_ext=-6, del_gap_ext=-5)
+    lib = util.oracle_lib()
+    for h in hits:
+        r, adj = C.c_int(), C.c_int()
+        lib.ora_rescore(h["qaln"].encode(), h["saln"].encode(), C.byref(om), C.byref(op), C.byref(r), C.byref(adj))
+        assert r.value == h["raw_score"] and adj.value == h["score"] >= 225, h
+    qi = {n: i for i, n in enumerate(qn)}
+    si = {n: i for i, n in enumerate(snames)}
+    key = lambda h: (qi[h["qname"]], h["qstart"], -si[h["sname"]], h["sstart"], h["qend"], h["strand"] == "C", h["send"])
+    assert [key(h) for h in hits] == sorted(key(h) for h in hits)
+    single = []
+    for k in range(2):
+        s.set_queries([qs[k]], [qn[k]])
+        part, _ = s.search(p)
+        single += [{kk: v for kk, v in h.items() if kk != "query_index"} for h in part]
+    assert single == [{kk: v for kk, v in h.items() if kk != "query_index"} for h in hits]
+    s.close()
