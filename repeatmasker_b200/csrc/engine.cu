@@ -36,29 +36,36 @@ namespace rmgpu {
 
 static thread_local std::string g_last_error;
 
-// bytes held by all DevBufs of this process: lets a session track free HBM without asking the driver on every call
-static std::atomic<long long> g_devbuf_bytes{0};
+// bytes held by the DevBufs of this process, per device: lets a session track free HBM without asking the driver on
+// every call
+static std::atomic<long long> g_devbuf_bytes[64];
 
 template <typename T>
 struct DevBuf {  // grow-only device buffer
   T* p = nullptr;
   size_t cap = 0;
+  int dev = 0;  // device the current allocation lives on
   ~DevBuf() {
     if (p) {
       cudaFree(p);
-      g_devbuf_bytes -= (long long)(cap * sizeof(T));
+      g_devbuf_bytes[dev & 63] -= (long long)(cap * sizeof(T));
     }
   }
   T* ensure(size_t n) {
     if (n > cap) {
-      if (p) cudaFree(p);
+      const size_t oldCap = cap;
+      if (p) {
+        cudaFree(p);
+        g_devbuf_bytes[dev & 63] -= (long long)(cap * sizeof(T));
+      }
       p = nullptr;
-      g_devbuf_bytes -= (long long)(cap * sizeof(T));
       cap = 0;
-      size_t want = std::max(n, cap + cap / 2);
+      // geometric growth for buffers that creep up, but never more than 256 MB beyond what was asked for
+      const size_t want = std::max(n, std::min(oldCap + oldCap / 2, n + (size_t)(256u << 20) / sizeof(T)));
+      cudaGetDevice(&dev);
       CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
       cap = want;
-      g_devbuf_bytes += (long long)(cap * sizeof(T));
+      g_devbuf_bytes[dev & 63] += (long long)(cap * sizeof(T));
     }
     return p;
   }
@@ -1333,7 +1340,7 @@ int rmgpu_session::query_capacity() const {
   if (capEnv && atoi(capEnv) > 0) return atoi(capEnv);
   // free HBM = what was free when the session opened less what this process has allocated since (cudaMemGetInfo
   // itself costs up to milliseconds per call)
-  const long long freeNow = freeAtOpen - (g_devbuf_bytes.load() - devbufAtOpen);
+  const long long freeNow = freeAtOpen - (g_devbuf_bytes[device & 63].load() - devbufAtOpen);
   const size_t freeB = (size_t)std::max<long long>(freeNow, 0);
   const double budget = 0.45 * (double)(freeB + d_ck.cap * sizeof(uint2) + d_bnd1.cap * 8);
   const double perQuery = (double)kHotBlocks * nGroups * R * 8.0 + (double)nStripes * ((double)maxQ + 64.0) * 8.0;
@@ -1666,7 +1673,7 @@ rmgpu_session* rmgpu_session_open(int device) {
       size_t freeB = 0, totalB = 0;
       CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
       s->freeAtOpen = (long long)freeB;
-      s->devbufAtOpen = g_devbuf_bytes.load();
+      s->devbufAtOpen = g_devbuf_bytes[device & 63].load();
     }
     {
       int lo = 0, hi = 0;
