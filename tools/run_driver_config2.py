@@ -11,6 +11,7 @@ from repeatmasker_b200 import engine, synth
 ap = argparse.ArgumentParser(); ap.add_argument("--mbp", type=float, default=1.0); ap.add_argument("--pa", type=int, default=4)
 ap.add_argument("--families", type=int, default=500); ap.add_argument("--seed", type=int, default=1001)
 ap.add_argument("--extra", default="", help="extra driver flags, e.g. -s")
+ap.add_argument("--server-gpus", default="0", help="GPU ordinals of the rmgpu_server workers, e.g. 0,1 (0,0 = two sessions on one GPU)")
 ap.add_argument("--also-crossmatch", type=int, default=0, metavar="PA",
                 help="also run `-engine crossmatch -pa PA` (the CPU oracle as cross_match) on the same input and compare the outputs")
 a = ap.parse_args()
@@ -26,7 +27,7 @@ while left > 0:  # generated 1 Mbp at a time, one sequence in the end
 genome = "".join(parts)
 synth.write_fasta(os.path.join(d, "lib.fa"), snames, sseqs)
 synth.write_fasta(os.path.join(d, "genome.fa"), ["synth0"], [genome], width=60)
-with engine.Server(os.path.join(d, "rmgpu.sock")) as srv:
+with engine.Server(os.path.join(d, "rmgpu.sock"), gpus=[int(x) for x in a.server_gpus.split(",")]) as srv:
     cmd = f"source {H}/env.sh && cd {d} && perl $RM_HOME/RepeatMasker -engine gpu -lib lib.fa -gc 41 -pa {a.pa} {a.extra} genome.fa"
     t0 = time.perf_counter()
     res = subprocess.run(["bash", "-c", cmd], capture_output=True, text=True)
@@ -39,7 +40,7 @@ masked = open(os.path.join(d, "genome.fa.masked")).read()
 nN = sum(l.count("N") for l in masked.splitlines() if not l.startswith(">"))
 print(f"RepeatMasker -engine gpu -pa {a.pa} {a.extra}: {len(genome)} bp x {len(sseqs)} families: wall {wall:.1f} s, {len(out) - 3} annotation lines, "
       f"{100.0 * nN / len(genome):.1f} % masked")
-print(srv.log.strip().splitlines()[-1] if srv.log else "")
+print("\n".join(l for l in (srv.log or "").splitlines() if "served" in l))
 print(open(os.path.join(d, "genome.fa.tbl")).read()[:700])
 if a.also_crossmatch:
     d2 = tempfile.mkdtemp()
