@@ -643,9 +643,10 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
 // K2 over every (query, strand, subject) triple whose K1 best reached minscore.
 //   common path  (run_blocks): one task per hot column block, started from K1's column checkpoint, all blocks in
 //                parallel, pseudo origins resolved through per-block snapshots (swg_origin_block_kernel);
-//   fallback     (run_chain):  one sweep from column 0 with the stripe pipeline (swg_origin_kernel) for triples whose
-//                K1 values wrapped (int16), that are too large for the 31-bit relative origin, or when checkpoints
-//                are disabled.
+//   fallback     (run_chain):  one sweep with the stripe pipeline (swg_origin_kernel) for triples whose K1 values
+//                wrapped (int16: swept from the checkpoint before their first hot block to their last one), that are
+//                too large for the 31-bit relative origin or hold merged residue classes, or when checkpoints are
+//                disabled (those from column 0); runs concurrently on a second stream.
 void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest,
                                const std::vector<unsigned long long>& hotmask, std::vector<Candidate>& cands,
                                rmgpu_stats& st) {
@@ -731,7 +732,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       }
     }
     if (tasks.empty()) return;
-    // longest subjects first (one warp sweeps a whole task): remap prevTask through the permutation
+    // longest subjects first: remap prevTask through the permutation
     std::vector<int> perm(tasks.size()), inv(tasks.size());
     std::iota(perm.begin(), perm.end(), 0);
     std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) {
@@ -1182,7 +1183,7 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
   const int64_t kDirBudget = 4ll << 30;  // direction bytes per launch
   while (!todo.empty()) {
     std::vector<int> next;
-    // narrow bands first (one warp each), then wide bands (one 128-thread block each)
+    // narrow bands first (one warp each), then wide bands (a team of up to 512 threads of a block each)
     std::stable_sort(todo.begin(), todo.end(), [&](int x, int y) { return (band_of(x) > 64) < (band_of(y) > 64); });
     size_t at = 0;
     while (at < todo.size()) {

@@ -844,9 +844,9 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 // K2b: block-parallel origin pass (the common path).  A task = one (query, strand, subject) triple x one hot column
 // block [c0, c1) (CB columns, CB = the K1 checkpoint spacing).  Every task starts from K1's exact (H, E') column
-// checkpoint, so all blocks of a triple run in parallel and one warp does a whole task by itself, sweeping the
-// subject's 256-row stripes one after the other (the stripe boundary lives in a private scratch line; no inter-warp
-// pipeline, no flags).  Paths that are alive at the left edge carry a PSEUDO origin naming the boundary cell
+// checkpoint, so all blocks of a triple run in parallel; the subject's 256-row stripes of a task are tickets that
+// different warps pipeline through a boundary ring with progress flags (same protocol as swg_origin_kernel; the
+// host orders the tickets so that long tasks start first).  Paths that are alive at the left edge carry a PSEUDO origin naming the boundary cell
 // (row, H-or-E state); each task snapshots the origins of its last column, and resolve_candidates_kernel follows
 // pseudo origins through those snapshots back to the real origin cell.  Origins are encoded relative to the task,
 // (i0 - c0) * (L + 1) + j0, which must stay below 2^31 (bit 31 marks pseudo origins).
