@@ -664,9 +664,6 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         const size_t idx = ((size_t)q * nS + s) * 2 + strand;
         if (pairbest[idx] < std::max(1, std::min(p.minscore, ovfThresh) - scoreSlack)) continue;
         const int64_t Q = h_qlen[q], L = (int64_t)lib.seqs[s].size();
-        if ((Q + 1) * (L + 1) >= (1ll << 32))
-          throw Error("query x subject too large for one origin pass (" + queries.names[q] + " x " + lib.names[s] +
-                      "): fragment the query as SimpleBatcher does");
         HotMask m;
         for (int k = 0; k < kHotWords; k++) m.w[k] = hotmask[idx * kHotWords + k];
         Triple t;
@@ -928,6 +925,11 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     int64_t stripes8 = 0;
     for (int tr : trIdx) stripes8 += (int64_t)(lib.seqs[triples[tr].subject].size() + 255) / 256;
     const int chainR = (stripes8 * 4 <= (int64_t)numSMs * 16) ? 2 : 8;
+    auto origin_range_check = [&](const OriginTask& t) {
+      if (((int64_t)(t.c1 - t.c0) + 2) * ((int64_t)lib.seqs[t.subject].size() + 1) >= (1ll << 32) - 1)
+        throw Error("query x subject too large for one origin sweep (" + queries.names[t.q] + " x " + lib.names[t.subject] +
+                    "): fragment the query as SimpleBatcher does");
+    };
     std::vector<OriginTask> tasks;
     std::vector<char> taskFull;  // swept with origins over the whole query
     std::vector<int32_t> ticketTask;
@@ -975,6 +977,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         if (hi < kHotBlocks - 1) t.c1 = (int)std::min<int64_t>(h_qlen[T.q], (hi + 1) * CB);
         if (t.c0 >= t.c1) t.c0 = 0, t.c1 = h_qlen[T.q], t.ckOff = -1;
       }
+      // a sweep carries origins as (column in window + 1) * (L + 1) + row in 32 bits (all ones = "from the left")
+      origin_range_check(t);
       t.firstTicket = (int)ticketTask.size();
       for (int k = 0; k < t.nStripes; k++) ticketTask.push_back((int32_t)tasks.size());
       tasks.push_back(t);
@@ -1078,7 +1082,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
           c.strand = t.strand;
           c.subject = t.subject;
           const uint32_t Lp1 = (uint32_t)lib.seqs[t.subject].size() + 1u;
-          c.i0 = (int)(origin / Lp1);
+          c.i0 = (int)(origin / Lp1) + t.c0;  // origins are carried relative to the task's window
           c.j0 = (int)(origin % Lp1);
           decode_val(vals[i], c);
           foundChain.push_back({trIdx[ti], c});
@@ -1095,6 +1099,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
           tasks[i].c0 = 0;
           tasks[i].c1 = h_qlen[tasks[i].q];
           tasks[i].ckOff = -1;
+          origin_range_check(tasks[i]);
           any = true;
           chainRedo++;
         } else {

@@ -532,8 +532,9 @@ struct OriginArgs {
   int* overflow;
 };
 
-// An origin (i0, j0) is carried as one 32-bit word i0 * (L + 1) + j0 (L = subject length); the host checks
-// (Q + 1) * (L + 1) < 2^32 per task (any SimpleBatcher fragment, <= 75 kbp, against subjects up to 57 kbp).
+// An origin (i0, j0) is carried as one 32-bit word (i0 - c0) * (L + 1) + j0 (L = subject length, c0 = first column of the
+// task's window); the host checks (Q + 2) * (L + 1) < 2^32 - 1 per sweep (any SimpleBatcher fragment, <= 75 kbp, against
+// subjects up to 57 kbp).
 // value of a candidate end: larger = better score, then smaller i, then smaller j
 __device__ __forceinline__ unsigned long long cand_val(int h, int i, int j) {
   return ((unsigned long long)(uint32_t)h << 40) | ((unsigned long long)(0xFFFFFu - (uint32_t)i) << 20) |
@@ -765,7 +766,7 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
             const uint32_t ol = oH[r];
             const bool valid = active && srow[r] >= 0;
             const int sc_ = smat[(srow[r] + curQ) & 255];
-            const OriginCell c = origin_cell(valid, hl, ol, hu, ou, hd, od, sc_, (uint32_t)i1 * Lp1 + (uint32_t)(row0 + r + 1),
+            const OriginCell c = origin_cell(valid, hl, ol, hu, ou, hd, od, sc_, (uint32_t)(cw + 1) * Lp1 + (uint32_t)(row0 + r + 1),
                                              E[r], oE[r], f, of, a.gap_init, a.ins_ext, a.del_ext);
             ends |= (c.viaDiag && c.h >= a.minscore) ? (1u << r) : 0u;
             hd = hl;
