@@ -9,6 +9,7 @@ result is checked through size-independent properties, with the oracle's scoring
   * searching the fragments in two halves (two "ranks") returns the same hits as one batch.
 Also a many-family library (BASELINE configuration 5 in miniature) against the oracle."""
 import ctypes as C
+import os
 
 import pytest
 
@@ -257,3 +258,47 @@ def test_config5_scale_library_properties(tmp_path):
         single += [{kk: v for kk, v in h.items() if kk != "query_index"} for h in part]
     assert single == [{kk: v for kk, v in h.items() if kk != "query_index"} for h in hits]
     s.close()
+
+
+def _rescoring_holds(snames, sseqs, qn, qs):
+    import tempfile
+
+    m = util.write_matrix("20p41g.matrix", os.path.join(tempfile.mkdtemp(), "20p41g.matrix"))
+    s = engine.Session()
+    s.set_matrix(m)
+    s.set_library(sseqs, snames)
+    s.set_queries(qs, qn)
+    p = engine.make_params()
+    hits, st = s.search(p)
+    om = util.parse_matrix(m)
+    op = util.OraParams(gap_init=-30, ins_gap_ext=-6, del_gap_ext=-5)
+    lib = util.oracle_lib()
+    for h in hits:
+        r, adj = C.c_int(), C.c_int()
+        lib.ora_rescore(h["qaln"].encode(), h["saln"].encode(), C.byref(om), C.byref(op), C.byref(r), C.byref(adj))
+        assert r.value == h["raw_score"] and adj.value == h["score"] >= 225, h
+    again, _ = s.search(p)
+    assert again == hits
+    s.close()
+    return hits, st
+
+
+def test_extreme_record_and_subject_lengths():
+    """Far beyond a SimpleBatcher fragment: one 900 kbp query record (8,192-column hot blocks, an int16-overflowing triple
+    swept in a window) and 30 / 50 kbp subjects with 20-30 kbp alignments (raw scores > 200,000, stripe chains of ~100
+    stripes, band-doubling traceback): every alignment re-scores exactly and the result is deterministic."""
+    import numpy as np
+
+    snames, sseqs = synth.make_library(501, n_families=100)
+    g, _ = synth.make_genome(502, 900000, sseqs, coverage=0.4)
+    hits, st = _rescoring_holds(snames, sseqs, ["big"], [g])
+    assert len(hits) > 300 and max(h["raw_score"] for h in hits) > 32767
+    rng = np.random.default_rng(5)
+    long1 = synth.random_dna(rng, 30000).tobytes().decode()
+    long2 = synth.random_dna(rng, 50000).tobytes().decode()
+    bg = synth.random_dna(rng, 20000).tobytes().decode()
+    q = (bg[:3000] + synth.mutate(rng, long1[2000:22000], 0.05, 0.005) + bg[3000:6000] +
+         synth.revcomp(synth.mutate(rng, long2[10000:40000], 0.1, 0.01)) + bg[6000:])
+    hits, st = _rescoring_holds(["L30k#LINE/L1", "L50k#Satellite/x"] + snames[:20], [long1, long2] + sseqs[:20], ["q"], [q[:74000]])
+    assert sorted(h["sname"] for h in hits)[:2] == ["L30k#LINE/L1", "L50k#Satellite/x"]
+    assert max(h["raw_score"] for h in hits) > 200000
