@@ -149,6 +149,12 @@ int rmgpu_measure_dpx_peak(int device, double *cups, double *dpx_instr_per_s);
 void rmgpu_kimura_divergence(const char *qaln, const char *saln, int strand, char text[8], double *transitions,
                              int32_t *transversions, int32_t *well_characterized, int32_t *cpg_sites);
 
+/* Host-only views of the two other double-precision pieces of the path, exported for the same reason:
+ * the matrix reader (grammar of Matrix.pm:308-364, lambda of Matrix.pm:397-464) and the complexity adjustment of a
+ * raw score over the aligned query letters of one alignment (SearchResult.pm:2111-2150).  Both return 0 on success. */
+int rmgpu_matrix_info(const char *matrix_file, int32_t *n, char alphabet[17], double *lambda, double freqs[16]);
+int rmgpu_adjusted_score(const char *matrix_file, int32_t raw, const char *qaln, const char *saln, int32_t *adjusted);
+
 #ifdef __cplusplus
 }
 #endif

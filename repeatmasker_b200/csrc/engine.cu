@@ -1822,6 +1822,28 @@ void rmgpu_free(rmgpu_result* r) {
   delete r;
 }
 
+int rmgpu_matrix_info(const char* matrix_file, int32_t* n, char alphabet[17], double* lambda, double freqs[16]) {
+  return guarded([&] {
+    const ScoreMatrix m = ScoreMatrix::from_file(matrix_file);
+    if (n) *n = m.n;
+    if (alphabet) snprintf(alphabet, 17, "%s", m.alphabet.c_str());
+    if (lambda) *lambda = m.lambda;
+    if (freqs)
+      for (int i = 0; i < kMaxAlpha; i++) freqs[i] = i < m.n ? m.freq[i] : 0.0;
+  });
+}
+
+int rmgpu_adjusted_score(const char* matrix_file, int32_t raw, const char* qaln, const char* saln, int32_t* adjusted) {
+  return guarded([&] {
+    const ScoreMatrix m = ScoreMatrix::from_file(matrix_file);
+    int64_t counts[kMaxAlpha] = {};
+    const size_t len = std::min(strlen(qaln), strlen(saln));
+    for (size_t i = 0; i < len; i++)
+      if (qaln[i] != '-' && saln[i] != '-') counts[m.code_of[(unsigned char)qaln[i]]]++;  // aligned pairs, query letter
+    *adjusted = complexity_adjust(raw, counts, m);
+  });
+}
+
 int rmgpu_measure_dpx_peak(int device, double* cups, double* dpx_instr_per_s) {
   return guarded([&] {
     if (device >= 0) CUDA_CHECK(cudaSetDevice(device));

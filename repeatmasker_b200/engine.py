@@ -56,7 +56,8 @@ EXPORTS = ["rmgpu_version", "rmgpu_abi_version", "rmgpu_last_error", "rmgpu_sear
            "rmgpu_session_open", "rmgpu_session_close", "rmgpu_session_set_matrix_file", "rmgpu_session_set_library",
            "rmgpu_session_set_library_fasta", "rmgpu_session_set_queries", "rmgpu_session_set_queries_fasta",
            "rmgpu_session_search", "rmgpu_session_score_only", "rmgpu_session_counts", "rmgpu_measure_dpx_peak",
-           "rmgpu_server_ping", "rmgpu_server_quit", "rmgpu_kimura_divergence"]
+           "rmgpu_server_ping", "rmgpu_server_quit", "rmgpu_kimura_divergence", "rmgpu_matrix_info",
+           "rmgpu_adjusted_score"]
 
 
 def lib():
@@ -123,6 +124,26 @@ def kimura_divergence(qaln, saln, strand_c=False):
     f.restype = None
     f(qaln.encode(), saln.encode(), 1 if strand_c else 0, text, C.byref(ti), C.byref(tv), C.byref(wcb), C.byref(cpg))
     return text.value.decode(), ti.value, tv.value, wcb.value, cpg.value
+
+
+def matrix_info(path):
+    """rmgpu_matrix_info(): (n, alphabet, lambda, freqs) as the library's matrix reader sees the file.  Host-only."""
+    n, lam = C.c_int32(), C.c_double()
+    alpha = C.create_string_buffer(17)
+    fr = (C.c_double * 16)()
+    f = lib().rmgpu_matrix_info
+    f.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _check(f(path.encode(), C.byref(n), alpha, C.byref(lam), fr))
+    return n.value, alpha.value.decode(), lam.value, list(fr)[: n.value]
+
+
+def adjusted_score(matrix_path, raw, qaln, saln):
+    """rmgpu_adjusted_score(): complexity-adjusted score of one alignment (SearchResult.pm:2111-2150).  Host-only."""
+    adj = C.c_int32()
+    f = lib().rmgpu_adjusted_score
+    f.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32)]
+    _check(f(matrix_path.encode(), raw, qaln.encode(), saln.encode(), C.byref(adj)))
+    return adj.value
 
 
 def make_params(gap_init=-30, ins_gap_ext=-6, del_gap_ext=-5, minscore=225, masklevel=101, minmatch=9, bandwidth=14,
