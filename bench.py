@@ -272,7 +272,9 @@ def main():
             "dtype": "int16x2 (DPX) score pass, int32 origin/traceback, f64 complexity adjustment", "data": "synthetic",
             "config": config_dict(args, snames, sseqs, qn, qs, world),
             "mbp_per_s": Q * world * args.steps / t_res_max / 1e6,
-            "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": int(st_e2e[0]["h2d_bytes"]) + sum(len(x) for x in sseqs) * 10,
+            "e2e": {"value": e2e, "unit": "GCUPS", # query records: 4-bit packed (counted by the library); library: 1 B/row codes in 16-row groups + 1 B/base codes
+                    # for K2/K3 + 5 B of flags per group = 2.33 B/base (the 8 B/row profiles are built on the device)
+                    "h2d_bytes_per_step": int(st_e2e[0]["h2d_bytes"]) + int(2.33 * sum(len(x) for x in sseqs)),
                     "d2h_bytes_per_step": int(st_e2e[0]["d2h_bytes"]), "ms_per_step": 1e3 * t_e2e_max / args.steps,
                     "mbp_per_s": Q * world * args.steps / t_e2e_max / 1e6,
                     "what": "Session.set_library + set_queries (host buffers -> HBM) + search (records back on the host) per step"},
