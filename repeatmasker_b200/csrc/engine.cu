@@ -411,6 +411,7 @@ void rmgpu_session::set_queries(SeqSet s) {
     if (sc >= matrix.n) continue;
     auto clampv = [&](int v) {
       if (v > 127) throw Error("matrix score > 127 is not supported by the int8 profile");
+      if (v < -128) classesExact = false;  // clamped: K1 becomes an upper bound, its checkpoints are not exact
       return (int8_t)std::max(v, -128);
     };
     for (int k = 0; k < nExact; k++) class_score[sc][k] = clampv(matrix.score[sc][present[k]]);
@@ -562,7 +563,11 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   const int warps = grid * kScoreWarps;
   build_order(nQ, warps);
   // ring slots: a slot is rewritten nslot tickets later; its reader is at most orderGroup * nQ tickets after its writer
-  const int nslot = (int)std::min<int64_t>(nTickets, std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)orderGroup * nQ + 2));
+  // ... and a boundary's 4-bit tag (generation = ticket / nslot, 15 values) must be unique within a launch: a slot keeps
+  // the boundary of its last WRITER, which may be many generations old when the tickets in between had no stripe below
+  const int nslot = (int)std::min<int64_t>(
+      nTickets, std::max<int64_t>(std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)orderGroup * nQ + 2), nTickets / 14 + 1));
+  if ((nTickets + nslot - 1) / nslot > 15) throw Error("K1 boundary ring: more than 15 tag generations in one launch");
   const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
   ScoreArgs a;
   a.prof = d_prof.p;
@@ -682,6 +687,14 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   st.n_pairs_passed = (int)triples.size();
   cands.clear();
   if (triples.empty()) return;
+  // the candidate tables carry the triple and the raw score in 24-bit fields (cand_val, resolve_candidates_kernel)
+  if (triples.size() >= (1u << 24)) throw Error("origin pass: more than 2^24 passing (query, strand, subject) triples in one pass");
+  {
+    int64_t maxL = 0;
+    for (auto& sq : lib.seqs) maxL = std::max<int64_t>(maxL, (int64_t)sq.size());
+    if (std::min<int64_t>(maxQ, maxL) * std::max(matrix.max_score(), 1) >= (1ll << 24))
+      throw Error("origin pass: raw scores of 2^24 or more are possible with these sequence lengths");
+  }
   std::vector<std::pair<int, Candidate>> found;  // (triple, candidate)
   auto decode_val = [](unsigned long long v, Candidate& c) {
     c.raw = (int)(v >> 40);
@@ -1351,7 +1364,9 @@ int rmgpu_session::query_capacity() const {
   const double budget = 0.45 * (double)(freeB + d_ck.cap * sizeof(uint2) + d_bnd1.cap * 8);
   const double perQuery = (double)kHotBlocks * nGroups * R * 8.0 + (double)nStripes * ((double)maxQ + 64.0) * 8.0;
   const double byCk = (double)kCheckpointBudget / std::max((double)kHotBlocks * nGroups * R * 8.0, 1.0);
-  return (int)std::max(1.0, std::floor(std::min(budget / std::max(perQuery, 1.0), byCk)));
+  // (query, strand, subject) triples are numbered in 24 bits by the origin pass
+  const double byTriples = std::floor(((double)(1u << 24) - 1.0) / std::max(2.0 * (double)lib.seqs.size(), 1.0));
+  return (int)std::max(1.0, std::floor(std::min(std::min(budget / std::max(perQuery, 1.0), byCk), byTriples)));
 }
 
 rmgpu_result* rmgpu_session::search(const rmgpu_params& p) {
@@ -1670,7 +1685,10 @@ rmgpu_session* rmgpu_session_open(int device) {
     CUDA_CHECK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 9) throw Error("librmgpu needs DPX instructions (built for sm_100a)");
+    // the library carries sm_100a SASS only (build.py: -gencode arch=compute_100a,code=sm_100a)
+    if (prop.major != 10)
+      throw Error("librmgpu is built for sm_100a (B200) only; device " + std::to_string(device) + " is sm_" +
+                  std::to_string(prop.major) + std::to_string(prop.minor));
     s = new rmgpu_session();
     s->device = device;
     s->numSMs = prop.multiProcessorCount;

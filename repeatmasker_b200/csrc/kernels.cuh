@@ -1253,6 +1253,12 @@ __global__ void __launch_bounds__(BLOCK ? kTraceBlockThreads : kTraceWarps * 32)
     qc = sseq[wib][0];
     sc = sseq[wib][1];
   }
+  // every thread of the block (warp) staged residues, but a narrow band's team is only its first T threads and
+  // team_sync() only covers those: the staged bytes must be visible to the team before its first wave
+  if (BLOCK)
+    __syncthreads();
+  else
+    __syncwarp();
   uint8_t* dir = a.dir + tc.dirOff;
   int len = -1, used = 0;
   for (int attempt = 0; attempt < tc.attempts && len <= 0; attempt++) {

@@ -115,77 +115,11 @@ sub getDevice {
 }
 
 ##---------------------------------------------------------------------------##
-## getParameters(): the driver interpolates this into its error messages
-## (RepeatMasker:2076, :2101).  Same flag spelling as
-## CrossmatchSearchEngine.pm:277-363 and the same croaks on missing files.
+## getParameters() is inherited (CrossmatchSearchEngine.pm:277-363): pathToEngine
+## names an existing file (librmgpu.so), so its engine check passes and the
+## driver's error messages (RepeatMasker:2076, :2101) read
+## "<path>/librmgpu.so -alignments -gap_init ...".
 ##---------------------------------------------------------------------------##
-sub getParameters {
-  my $this = shift;
-
-  my $parameters = "";
-  my $value;
-  if ( ( $value = $this->getScoreMode() ) ) {
-    $parameters .= " -raw" if ( $value == SearchEngineI::basicScoreMode );
-  }
-  if ( ( $value = $this->getWordRaw() ) ) {
-    $parameters .= " -word_raw" if ( $value > 0 );
-  }
-  if ( ( $value = $this->getGenerateAlignments() ) ) {
-    $parameters .= " -alignments" if ( $value > 0 );
-  }
-  if ( defined( $value = $this->getGapInit() ) && $value =~ /\d+/ ) {
-    $parameters .= " -gap_init $value";
-  }
-  if ( defined( $value = $this->getInsGapExt() ) && $value =~ /\d+/ ) {
-    $parameters .= " -ins_gap_ext $value";
-  }
-  if ( defined( $value = $this->getDelGapExt() ) && $value =~ /\d+/ ) {
-    $parameters .= " -del_gap_ext $value";
-  }
-  if ( ( $value = $this->getMinMatch() ) ) {
-    $parameters .= " -minmatch $value" if ( $value > 0 );
-  }
-  if ( ( $value = $this->getMinScore() ) ) {
-    $parameters .= " -minscore $value" if ( $value > 0 );
-  }
-  if ( ( $value = $this->getBandwidth() ) ) {
-    $parameters .= " -bandwidth $value" if ( $value > 0 );
-  }
-  if ( ( $value = $this->getMaskLevel() ) ) {
-    $parameters .= " -masklevel $value" if ( $value > 0 );
-  }
-  if ( ( $value = $this->getMatrix() ) ) {
-    if ( -f $value ) {
-      $parameters .= " -matrix $value";
-    }
-    else {
-      croak $CLASS. "::getParameters: Error...matrix ($value) does not exist!\n";
-    }
-  }
-  if ( ( $value = $this->getQuery() ) ) {
-    if ( -f $value ) {
-      $parameters .= " $value";
-    }
-    else {
-      croak $CLASS. "::getParameters: Error...query ($value) does not exist!\n";
-    }
-  }
-  else {
-    croak $CLASS. "::getParameters: Error query undefined!\n";
-  }
-  if ( ( $value = $this->getSubject() ) ) {
-    if ( -f $value ) {
-      $parameters .= " $value";
-    }
-    else {
-      croak $CLASS. "::getParameters: Error...subject ($value) does not exist!\n";
-    }
-  }
-  else {
-    croak $CLASS. "::getParameters: Error subject undefined!\n";
-  }
-  return ( "rmgpu" . $parameters );
-}
 
 ##---------------------------------------------------------------------------##
 ## search(): same contract as CrossmatchSearchEngine.pm:381-524 --
@@ -207,7 +141,7 @@ sub search {
     }
   }
 
-  my $cmdLine = $this->getParameters();    # croaks on missing inputs like the parent class
+  my $cmdLine = $this->getParameters();    # inherited: croaks on missing inputs
 
   my $matrixName;
   {
