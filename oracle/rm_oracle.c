@@ -293,6 +293,72 @@ int ora_sw_score(const unsigned char *q, int Q, const unsigned char *s, int L, c
   return best;
 }
 
+/* The same score-only pass over up to 16 subjects at once, one int16 lane per subject (inter-sequence SIMD, AVX2).
+   Saturating arithmetic: a lane whose best reaches `cap` is reported as cap ("at least cap"), so the caller may only
+   use the result as the boolean best >= minscore with minscore <= cap.  Lanes shorter than the longest subject are
+   padded with rows that score PADSC against everything, which cannot raise a lane's best (every value in a pad row
+   descends from a real cell through penalties).  ora_search() uses it when the CPU has AVX2 and RM_ORACLE_SCALAR is
+   not set; tests/test_oracle_golden.py checks it against ora_sw_score(). */
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define ORA_HAVE_AVX2 1
+#define ORA_LANES 16
+#define ORA_CAP 32000
+__attribute__((target("avx2"))) void ora_sw_score_batch(const unsigned char *q, int Q, const unsigned char *const *s,
+                                                        const int *L, int nsub, const ora_matrix *m,
+                                                        const ora_params *p, int *best_out) {
+  const short PADSC = -100;
+  int Lmax = 0, l, j, c, i;
+  __m256i *prof, *Hc, *Ec, best;
+  const __m256i vgi = _mm256_set1_epi16((short)p->gap_init), vie = _mm256_set1_epi16((short)p->ins_gap_ext),
+                vde = _mm256_set1_epi16((short)p->del_gap_ext), vzero = _mm256_setzero_si256(),
+                vcap = _mm256_set1_epi16(ORA_CAP), vneg = _mm256_set1_epi16(-32768);
+  short tmp[ORA_LANES];
+  for (l = 0; l < nsub; l++)
+    if (L[l] > Lmax) Lmax = L[l];
+  if (Lmax == 0 || Q == 0) {
+    for (l = 0; l < nsub; l++) best_out[l] = 0;
+    return;
+  }
+  prof = (__m256i *)aligned_alloc(32, (size_t)m->n * (size_t)Lmax * sizeof(__m256i));
+  Hc = (__m256i *)aligned_alloc(32, (size_t)(Lmax + 1) * sizeof(__m256i));
+  Ec = (__m256i *)aligned_alloc(32, (size_t)(Lmax + 1) * sizeof(__m256i));
+  for (c = 0; c < m->n; c++)
+    for (j = 0; j < Lmax; j++) {
+      for (l = 0; l < ORA_LANES; l++) tmp[l] = (l < nsub && j < L[l]) ? (short)m->score[s[l][j]][c] : PADSC;
+      prof[(size_t)c * Lmax + j] = _mm256_loadu_si256((const __m256i *)tmp);
+    }
+  for (j = 0; j <= Lmax; j++) {
+    Hc[j] = vzero;
+    Ec[j] = vneg;
+  }
+  best = vzero;
+  for (i = 1; i <= Q; i++) {
+    const __m256i *prow = prof + (size_t)q[i - 1] * Lmax;
+    __m256i hdiag = vzero, hup = vzero, F = vneg;
+    for (j = 1; j <= Lmax; j++) {
+      const __m256i hl = Hc[j];
+      const __m256i E = _mm256_max_epi16(_mm256_adds_epi16(Ec[j], vie), _mm256_adds_epi16(hl, vgi));
+      const __m256i d = _mm256_adds_epi16(hdiag, prow[j - 1]);
+      __m256i h;
+      F = _mm256_max_epi16(_mm256_adds_epi16(F, vde), _mm256_adds_epi16(hup, vgi));
+      h = _mm256_max_epi16(_mm256_max_epi16(E, F), _mm256_max_epi16(d, vzero));
+      h = _mm256_min_epi16(h, vcap);
+      hdiag = hl;
+      Hc[j] = h;
+      Ec[j] = E;
+      hup = h;
+      best = _mm256_max_epi16(best, h);
+    }
+  }
+  _mm256_storeu_si256((__m256i *)tmp, best);
+  for (l = 0; l < nsub; l++) best_out[l] = tmp[l];
+  free(prof);
+  free(Hc);
+  free(Ec);
+}
+#endif
+
 /* ------------------------------------------------------------------------------------------ */
 /* Origin-tracking pass                                                                        */
 /* ------------------------------------------------------------------------------------------ */
@@ -347,6 +413,9 @@ static void candmap_update(candmap *c, uint64_t origin, int score, int i, int j)
   }
 }
 
+#define SELI(c, a, b) ((b) ^ (((a) ^ (b)) & -(int)(c)))
+#define SELO(c, a, b) ((b) ^ (((a) ^ (b)) & (uint64_t) - (int64_t)(c)))
+
 static void origin_pass(const unsigned char *q, int Q, const unsigned char *s, int L, const ora_matrix *m,
                         const ora_params *p, candmap *cm) {
   int *Hc = (int *)malloc((size_t)(L + 1) * sizeof(int));
@@ -360,44 +429,36 @@ static void origin_pass(const unsigned char *q, int Q, const unsigned char *s, i
     Ec[j] = NEG;
   }
   for (i = 1; i <= Q; i++) {
-    int qi = q[i - 1];
-    int hdiag = 0, hup = 0, F = NEG;
+    int mrow[ORA_MAXA]; /* scores of every subject residue against this query residue */
+    const uint64_t irow = (uint64_t)(uint32_t)i << 32;
+    int hdiag = 0, hup = 0, F = NEG, c;
     uint64_t odiag = 0, oup = 0, oF = 0;
+    for (c = 0; c < ORA_MAXA; c++) mrow[c] = m->score[c][q[i - 1]];
     for (j = 1; j <= L; j++) {
-      int e_ext = Ec[j] + ie, e_open = Hc[j] + gi;
-      int f_ext = F + de, f_open = hup + gi;
-      int E, d, h;
-      uint64_t oe, od, oh;
-      if (e_ext >= e_open) { /* extension preferred on ties */
-        E = e_ext;
-        oe = oE[j];
-      } else {
-        E = e_open;
-        oe = oH[j];
-      }
-      if (f_ext >= f_open) {
-        F = f_ext;
-      } else {
-        F = f_open;
-        oF = oup;
-      }
-      d = hdiag + m->score[s[j - 1]][qi];
-      od = hdiag > 0 ? odiag : (((uint64_t)(uint32_t)i << 32) | (uint32_t)j);
+      /* written with selects instead of branches: in unrelated sequence every one of these comparisons is a coin flip */
+      const int e_ext = Ec[j] + ie, e_open = Hc[j] + gi;
+      const int f_ext = F + de, f_open = hup + gi;
+      /* SELI/SELO(c, a, b) = c ? a : b as mask arithmetic (gcc turns ?: back into branches here) */
+      const int e_opens = e_open > e_ext; /* extension preferred on ties */
+      const int f_opens = f_open > f_ext;
+      const int E = SELI(e_opens, e_open, e_ext);
+      const uint64_t oe = SELO(e_opens, oH[j], oE[j]);
+      const int d = hdiag + mrow[s[j - 1]];
+      const uint64_t od = SELO(hdiag > 0, odiag, irow | (uint32_t)j);
+      int h, c1, c2, pos;
+      uint64_t oh;
+      F = SELI(f_opens, f_open, f_ext);
+      oF = SELO(f_opens, oup, oF);
       /* priority E > F > diagonal */
-      h = E;
-      oh = oe;
-      if (F > h) {
-        h = F;
-        oh = oF;
-      }
-      if (d > h) {
-        h = d;
-        oh = od;
-      }
-      if (h <= 0) {
-        h = 0;
-        oh = 0;
-      }
+      c1 = F > E;
+      h = SELI(c1, F, E);
+      oh = SELO(c1, oF, oe);
+      c2 = d > h;
+      h = SELI(c2, d, h);
+      oh = SELO(c2, od, oh);
+      pos = h > 0;
+      h = SELI(pos, h, 0);
+      oh = SELO(pos, oh, (uint64_t)0);
       hdiag = Hc[j];
       odiag = oH[j];
       Hc[j] = h;
@@ -743,7 +804,23 @@ int ora_search(const ora_seqset *qs, const ora_seqset *ss, const ora_matrix *m, 
   int qi, si, strand, k;
   int maxL = 0;
   unsigned char **scode = (unsigned char **)malloc((size_t)ss->n * sizeof(unsigned char *));
+  int use_simd = 0;
+  int *bylen = (int *)malloc((size_t)(ss->n > 0 ? ss->n : 1) * sizeof(int)); /* subjects by ascending length */
+  char *passes = (char *)calloc((size_t)(ss->n > 0 ? ss->n : 1), 1);
   memset(out, 0, sizeof(*out));
+#ifdef ORA_HAVE_AVX2
+  use_simd = __builtin_cpu_supports("avx2") && !getenv("RM_ORACLE_SCALAR") && p->minscore <= ORA_CAP &&
+             p->gap_init > -16000 && p->ins_gap_ext > -16000 && p->del_gap_ext > -16000;
+#endif
+  for (si = 0; si < ss->n; si++) bylen[si] = si;
+  {
+    int a2, b2; /* insertion sort is enough for the few thousand records of a library; ties keep file order */
+    for (a2 = 1; a2 < ss->n; a2++) {
+      int t2 = bylen[a2];
+      for (b2 = a2 - 1; b2 >= 0 && ss->len[bylen[b2]] > ss->len[t2]; b2--) bylen[b2 + 1] = bylen[b2];
+      bylen[b2 + 1] = t2;
+    }
+  }
   for (si = 0; si < ss->n; si++) {
     scode[si] = (unsigned char *)malloc((size_t)ss->len[si] + 1);
     for (k = 0; k < ss->len[si]; k++) scode[si][k] = (unsigned char)m->code_of[(unsigned char)ss->seq[si][k]];
@@ -759,6 +836,20 @@ int ora_search(const ora_seqset *qs, const ora_seqset *ss, const ora_matrix *m, 
       else
         ora_revcomp(qs->seq[qi], Q, qlet);
       for (k = 0; k < Q; k++) qcode[k] = (unsigned char)m->code_of[(unsigned char)qlet[k]];
+#ifdef ORA_HAVE_AVX2
+      if (use_simd) { /* exact prefilter, 16 subjects (of similar length) per pass */
+        for (k = 0; k < ss->n; k += ORA_LANES) {
+          const unsigned char *sp[ORA_LANES];
+          int sl[ORA_LANES], sb[ORA_LANES], nb = ss->n - k < ORA_LANES ? ss->n - k : ORA_LANES, b;
+          for (b = 0; b < nb; b++) {
+            sp[b] = scode[bylen[k + b]];
+            sl[b] = ss->len[bylen[k + b]];
+          }
+          ora_sw_score_batch(qcode, Q, sp, sl, nb, m, p, sb);
+          for (b = 0; b < nb; b++) passes[bylen[k + b]] = sb[b] >= p->minscore;
+        }
+      }
+#endif
       for (si = 0; si < ss->n; si++) {
         int L = ss->len[si];
         candmap cm;
@@ -766,7 +857,7 @@ int ora_search(const ora_seqset *qs, const ora_seqset *ss, const ora_matrix *m, 
         size_t nc = 0, c;
         out->cells += (double)Q * (double)L;
         if (Q == 0 || L == 0) continue;
-        if (ora_sw_score(qcode, Q, scode[si], L, m, p) < p->minscore) continue;
+        if (use_simd ? !passes[si] : ora_sw_score(qcode, Q, scode[si], L, m, p) < p->minscore) continue;
         candmap_init(&cm);
         origin_pass(qcode, Q, scode[si], L, m, p, &cm);
         cands = (cand_t *)malloc((cm.n + 1) * sizeof(cand_t));
@@ -856,6 +947,8 @@ int ora_search(const ora_seqset *qs, const ora_seqset *ss, const ora_matrix *m, 
   out->cells *= 1.0; /* both strands already counted in the loop */
   for (si = 0; si < ss->n; si++) free(scode[si]);
   free(scode);
+  free(bylen);
+  free(passes);
   qsort(out->hit, (size_t)out->n, sizeof(ora_hit), cmp_hit);
   apply_masklevel_and_star(out, p->masklevel);
   return 0;

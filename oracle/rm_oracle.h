@@ -93,6 +93,9 @@ void ora_result_free(ora_result *r);
 /* pieces exposed for unit tests */
 int ora_sw_score(const unsigned char *q, int Q, const unsigned char *s, int L, const ora_matrix *m,
                  const ora_params *p); /* best local raw score */
+/* the same for up to 16 subjects at once (AVX2, x86-64 only; saturates at 32000): the prefilter ora_search() uses */
+void ora_sw_score_batch(const unsigned char *q, int Q, const unsigned char *const *s, const int *L, int nsub,
+                        const ora_matrix *m, const ora_params *p, int *best_out);
 int ora_complexity_adjust(int raw, const long counts[ORA_MAXA], const ora_matrix *m);
 int ora_global_traceback(const unsigned char *q, int n, const unsigned char *s, int mlen, const ora_matrix *m,
                          const ora_params *p, int want_score, char *qaln, char *saln,

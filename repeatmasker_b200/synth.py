@@ -90,18 +90,25 @@ def make_genome(seed, length, lib_seqs, coverage=0.45, gc=0.41, div_lo=0.10, div
 
 
 def fragment(seq, name, frag=60000, overlap=2000):
-    """SimpleBatcher-style fragments (SimpleBatcher.pm:642-749): equal pieces with `overlap` bases shared."""
+    """The fragments SimpleBatcher cuts a sequence longer than `frag` into, with its own arithmetic
+    (SimpleBatcher.pm:642-720): the smallest divisor >= 2 with (n + (divisor-1)*overlap) / divisor <= frag, pieces of
+    size = int((n + (divisor-1)*overlap) / divisor) starting every size - overlap bases, the last piece taking the
+    remainder and ending at the end of the sequence; ids `<name>frag-<k>`."""
     n = len(seq)
     if n <= frag:
         return [name], [seq]
-    k = int(np.ceil((n - overlap) / (frag - overlap)))
-    step = (n - overlap) / k
+    divisor = 2
+    while (n + (divisor - 1) * overlap) / divisor > frag:
+        divisor += 1
+    size = (n + (divisor - 1) * overlap) // divisor
     names, seqs = [], []
-    for i in range(k):
-        a = int(round(i * step))
-        b = n if i == k - 1 else int(round((i + 1) * step)) + overlap
+    for i in range(divisor - 1):
+        a = i * (size - overlap)
         names.append(f"{name}frag-{i + 1}")
-        seqs.append(seq[a:b])
+        seqs.append(seq[a:a + size])
+    last = size + (n + (divisor - 1) * overlap) % divisor
+    names.append(f"{name}frag-{divisor}")
+    seqs.append(seq[n - last:])
     return names, seqs
 
 

@@ -15,6 +15,13 @@ Fixtures:
                         with its cross_match 0.990329 hit lists at masklevel 101/98/97
   (matrices.json also holds) Matrix.pm lambda for every Matrices/crossmatch/*.matrix, produced by
                         running the reference's own Matrix.pm under perl
+  config1/              BASELINE configuration 1 inputs, copied verbatim: t/seqs/general/{hum-1.fa,small-1.fa,NT_001493.seq},
+                        t/libraries/{alu.fa,sinecutlib} (data files of the reference's own tests, not source code)
+  hum1_sine.json        the 3,882 hit lines of real cross_match 0.990329 in t/seqs/masklevel/hum-1-sine-ml101.out
+                        (query hum-1.fa; subject library of 2005, absent -- t/libraries/sinecutlib is a newer file
+                        with the same family names), its argv, and the matrix printed in its header
+  masklevel.json        survivors of SearchResultCollection::maskLevelFilter / filterContainedResults
+                        (SearchResultCollection.pm:198-358, :379-470) run under perl on the two fixtures above
   matrices.json         alphabet / FREQS / integer rows of every Matrices/crossmatch/*.matrix as parsed
                         by the reference's Matrix.pm (values only; tests re-materialise matrix files
                         from it with tests/util.py:write_matrix)
@@ -124,7 +131,62 @@ foreach my $f (@ARGV) { my $m = Matrix->new(fileName=>$f); my @p=split(/\//,$f);
     return dict(source="Matrix.pm:308-364,397-464 executed by perl on Matrices/crossmatch/*.matrix", matrices=out)
 
 
+def config1():
+    dst = f"{OUT}/config1"
+    os.makedirs(dst, exist_ok=True)
+    for rel in ("t/seqs/general/hum-1.fa", "t/seqs/general/small-1.fa", "t/seqs/general/NT_001493.seq",
+                "t/libraries/alu.fa", "t/libraries/sinecutlib"):
+        shutil.copyfile(f"{REF}/{rel}", f"{dst}/{os.path.basename(rel)}")
+        os.chmod(f"{dst}/{os.path.basename(rel)}", 0o644)
+
+
+HIT_KEYS = ["score", "div", "dele", "ins", "qname", "qstart", "qend", "qleft", "strand", "sname", "sstart", "send", "sleft", "star"]
+
+
+def hum1_sine():
+    f = f"{REF}/t/seqs/masklevel/hum-1-sine-ml101.out"
+    lines = open(f).readlines()
+    start = next(i for i, l in enumerate(lines) if l.startswith("Score matrix")) + 1
+    hits = parse_cm_hits(f)
+    return dict(
+        source="t/seqs/masklevel/hum-1-sine-ml101.out (cross_match 0.990329, 2005); query t/seqs/general/hum-1.fa",
+        argv=lines[0].strip(),
+        matrix_text="".join(lines[start:start + 12]),
+        params=dict(minmatch=10, minscore=250, gap_init=-25, ins_gap_ext=-6, del_gap_ext=-6, bandwidth=14, masklevel=101),
+        keys=HIT_KEYS,
+        hits=[[h[k] for k in HIT_KEYS] for h in hits],
+    )
+
+
+def masklevel():
+    """The reference's own Perl on the reference's own fixtures: which records survive each filter."""
+    perl = r'''
+use lib "%s"; use CrossmatchSearchEngine; use SearchResultCollection; use SearchResult;
+my ($file, $mode, $value) = @ARGV;
+my $col = CrossmatchSearchEngine::parseOutput( searchOutput => $file );
+for ( my $i = 0 ; $i < $col->size() ; $i++ ) { $col->get( $i )->setId( $i ); }
+if ( $mode eq "masklevel" ) { $col->maskLevelFilter( value => $value ); }
+else { $col->filterContainedResults( value => $value ); }
+my @ids = map { $col->get( $_ )->getId() } ( 0 .. $col->size() - 1 );
+print join( ",", @ids ) . "\n";
+''' % REF
+    out = {}
+    for name, rel in (("seq1_2", "t/seqs/masklevel/seq1-2-ml101.out"), ("hum1_sine", "t/seqs/masklevel/hum-1-sine-ml101.out")):
+        hits = parse_cm_hits(f"{REF}/{rel}")
+        rec = dict(source=rel, records=[[h["qname"], h["qstart"], h["qend"], h["score"]] for h in hits], masklevel={}, contained={})
+        for v in (0, 10, 30, 50, 80, 90, 95, 98, 100):
+            r = subprocess.run(["perl", "-e", perl, f"{REF}/{rel}", "masklevel", str(v)], capture_output=True, text=True, check=True)
+            rec["masklevel"][str(v)] = [int(x) for x in r.stdout.strip().split(",") if x != ""]
+        r = subprocess.run(["perl", "-e", perl, f"{REF}/{rel}", "contained", "80"], capture_output=True, text=True, check=True)
+        rec["contained"]["80"] = [int(x) for x in r.stdout.strip().split(",") if x != ""]
+        out[name] = rec
+    return dict(source="SearchResultCollection.pm:198-358 (maskLevelFilter), :379-470 (filterContainedResults) executed by perl", sets=out)
+
+
 def main():
+    config1()
+    json.dump(hum1_sine(), open(f"{OUT}/hum1_sine.json", "w"))
+    json.dump(masklevel(), open(f"{OUT}/masklevel.json", "w"))
     json.dump(parse_searchresult_t(), open(f"{OUT}/searchresult_t.json", "w"), indent=1)
     json.dump(seq1_2(), open(f"{OUT}/seq1_2.json", "w"), indent=1)
     json.dump(lambdas(), open(f"{OUT}/matrices.json", "w"))

@@ -41,6 +41,10 @@ def oracle_lib():
                                               C.c_char_p]
         _lib.ora_sw_score.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(OraMatrix),
                                       C.POINTER(OraParams)]
+        if hasattr(_lib, "ora_sw_score_batch"):
+            _lib.ora_sw_score_batch.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.c_int,
+                                                C.POINTER(OraMatrix), C.POINTER(OraParams), C.POINTER(C.c_int)]
+            _lib.ora_sw_score_batch.restype = None
     return _lib
 
 
@@ -132,3 +136,62 @@ def oracle_argv(query, subject, matrix, gap_init=-30, ins_gap_ext=-6, del_gap_ex
 def run_oracle(query, subject, matrix, **kw):
     res = subprocess.run(oracle_argv(query, subject, matrix, **kw), capture_output=True, text=True, check=True)
     return parse_crossmatch(res.stdout), res.stdout
+
+
+def read_fasta(path):
+    names, seqs = [], []
+    for ln in open(path):
+        if ln.startswith(">"):
+            names.append(ln[1:].split()[0] if ln[1:].split() else "")
+            seqs.append([])
+        elif names:
+            seqs[-1].append(ln.strip())
+    return names, ["".join(x) for x in seqs]
+
+
+def union_library(first, second, out):
+    """Records of `first`, then the records of `second` whose name `first` does not hold."""
+    n1, s1 = read_fasta(first)
+    n2, s2 = read_fasta(second)
+    have = set(n1)
+    with open(out, "w") as f:
+        for n, s in list(zip(n1, s1)) + [(n, s) for n, s in zip(n2, s2) if n not in have]:
+            f.write(f">{n}\n")
+            for i in range(0, len(s), 60):
+                f.write(s[i:i + 60] + "\n")
+    return out
+
+
+HARNESS = os.path.join(ROOT, "baseline", "_ref")
+
+
+def harness_ready():
+    import shutil
+
+    return os.path.exists(os.path.join(HARNESS, "env.sh")) and shutil.which("perl") is not None
+
+
+def run_repeatmasker(workdir, engine, args, query="genome.fa", lib="lib.fa", pa=4, env=None):
+    """The reference driver itself (baseline/_ref, built by tools/make_rm_harness.sh): `-engine crossmatch` runs the
+    oracle as cross_match, `-engine gpu` runs librmgpu through GpuSearchEngine.pm.  Returns its stdout."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "repeatmasker_b200", "perl")], check=True, capture_output=True)
+    cmd = (f"source {HARNESS}/env.sh && cd {workdir} && perl $RM_HOME/RepeatMasker -engine {engine} -lib {lib} "
+           f"-pa {pa} {' '.join(args)} {query}")
+    e = dict(os.environ)
+    e.update(env or {})
+    res = subprocess.run(["bash", "-c", cmd], capture_output=True, text=True, env=e)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    return res.stdout
+
+
+def driver_outputs(workdir, query="genome.fa", exts=("out", "masked", "cat", "tbl")):
+    out = {}
+    for ext in exts:
+        p = os.path.join(workdir, f"{query}.{ext}")
+        out[ext] = open(p).read() if os.path.exists(p) else None
+    return out
+
+
+def strip_engine_trailer(text):
+    """.cat / .tbl name the engine and its version ("run with ..."); everything else must be identical."""
+    return None if text is None else "\n".join(l for l in text.splitlines() if not l.startswith("run with "))

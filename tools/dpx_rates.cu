@@ -528,7 +528,8 @@ static void run_rate(uint32_t* d, int sms, double clk_hz, int warpsPerSM) {
 }
 
 int main(int argc, char** argv) {
-  const bool full = argc > 1;
+  const bool full = argc > 1 && argv[1][0] == 'f';
+  const bool cellsOnly = argc > 1 && argv[1][0] == 'c';  // for ncu: one pass of the cell loops at 24 warps/SM
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, 0);
   int clk_khz = 0;
@@ -539,6 +540,7 @@ int main(int argc, char** argv) {
   uint32_t* d;
   cudaMalloc(&d, (size_t)sms * 64 * 256 * 4);
   for (int w : {16, 32}) {
+    if (cellsOnly) break;
     if (full) {
       run_rate<VIADDMAX>(d, sms, clk_hz, w);
       run_rate<VIADDMAX_RELU>(d, sms, clk_hz, w);
@@ -569,6 +571,7 @@ int main(int argc, char** argv) {
   cudaEventCreate(&b);
   const uint32_t gi2 = 0xffe2ffe2u, ie2 = 0xfffafffau, de2 = 0xfffbfffbu, twoG2 = 0x003c003cu;
   for (int warps : {16, 20, 24, 32}) {
+    if (cellsOnly && warps != 24) continue;
     const int threads = 128, blocks = sms * (warps * 32 / threads), iters = 20000;
     auto report = [&](const char* name, int R, double ms) {
       printf("%-28s R=%2d warps/SM %2d  %8.3f ms  %8.1f GCUPS\n", name, R, warps, ms, (double)blocks * threads * R * (double)iters * 2.0 / (ms * 1e-3) / 1e9);
