@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RMGPU_ABI_VERSION 2
+#define RMGPU_ABI_VERSION 3
 
 /* Search parameters.  Replaces the argv that CrossmatchSearchEngine.pm:277-363 (getParameters) builds from the
  * SearchEngineI.pm:132-681 setters:
@@ -137,6 +137,19 @@ int rmgpu_session_counts(const rmgpu_session *s, int32_t *n_queries, int32_t *n_
  * (RepeatMasker:1043-1180) should use.  The two calls below are management helpers: 0 = server answered.            */
 int rmgpu_server_ping(const char *socket_path);
 int rmgpu_server_quit(const char *socket_path);
+
+/* ---- The two collection filters RepeatMasker runs on an engine's results (RepeatMasker:2838-2987), on the device, with
+ * the reference's own arithmetic and tie order.  n records in collection order: an integer per distinct query name, 1-based
+ * inclusive query coordinates, score.  keep[i] = 1 for the survivors; the order of the collection is not changed.
+ *   rmgpu_masklevel_filter   SearchResultCollection::maskLevelFilter( value => masklevel )   SearchResultCollection.pm:198-358
+ *                            (sort by name, score descending, span ascending; pairwise sprintf("%0.0f") test against every
+ *                            kept domain; masklevel >= 101 keeps everything)
+ *   rmgpu_contained_filter   SearchResultCollection::filterContainedResults( value => masklevel )     :379-470
+ * device -1 = current device.  Both return 0 on success. */
+int rmgpu_masklevel_filter(int device, int32_t n, const int32_t *name_id, const int32_t *qstart, const int32_t *qend,
+                           const int32_t *score, int32_t masklevel, uint8_t *keep);
+int rmgpu_contained_filter(int device, int32_t n, const int32_t *name_id, const int32_t *qstart, const int32_t *qend,
+                           const int32_t *score, int32_t masklevel, uint8_t *keep);
 
 /* Measured integer-SIMD ("DPX") peak of this GPU: a register-resident loop of the bare recurrence.
  * Returns 16-bit-lane cell updates per second (GCUPS*1e9) in *cups and raw VIADDMNMX.S16x2 warp-instructions/s. */

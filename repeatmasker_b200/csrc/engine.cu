@@ -150,16 +150,6 @@ struct HotMask {
   }
 };
 
-struct HitRec {
-  int score, raw, qidx, sidx, strand;
-  int qstart, qend, qleft, sstart, send, sleft;
-  int ti, tv, amb, gap_inits, gap_bases;
-  bool star = false;
-  char div[8], del[8], ins[8], kimura[8];
-  int cpg = 0, wcb = 0;
-  std::string qaln, saln;
-};
-
 }  // namespace rmgpu
 
 using namespace rmgpu;
@@ -204,6 +194,10 @@ struct rmgpu_session {
   int8_t class_score[16][8] = {};
   bool classesExact = true;
   std::vector<uint8_t> classKey;  // to detect class-map changes
+  int64_t canonCounts[16] = {};   // residues of the batch (both strands) per canonical code
+  bool streamsValid = false;      // sel / code streams and class map match the current matrix and batch
+  void prepare_streams();
+  int64_t h2d_bytes_library = 0;
   int64_t h2d_bytes_queries = 0;
   double ms_h2d_queries = 0;
 
@@ -247,8 +241,22 @@ struct rmgpu_session {
   int scoreSlack = 0;  // how much below the true best the sampled K1 best can be (0 in exact mode)
   void run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest,
                   const std::vector<unsigned long long>& hotmask, std::vector<Candidate>& cands, rmgpu_stats& st);
-  void run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands, std::vector<std::vector<uint8_t>>& ops,
-                     rmgpu_stats& st);
+  void run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands, rmgpu_stats& st);
+  void run_finalize(const rmgpu_params& p, const std::vector<Candidate>& cands, std::vector<HitDev>& hits,
+                    std::vector<char>& rows, rmgpu_stats& st);
+  int respell_exotic(const HitDev& h, char* qrow, char* srow) const;
+  std::vector<TraceCand> h_candAll;
+  DevBuf<TraceCand> d_candAll;
+  int64_t opsBytes = 0;
+  std::vector<double> h_logtab;
+  DevBuf<double> d_logtab;
+  DevBuf<char> d_rowsOut, d_rowsPacked;
+  DevBuf<HitDev> d_hits;
+  DevBuf<int32_t> d_qFirst, d_qCount, d_rankOrder, d_nKept;
+  DevBuf<int64_t> d_coverOff;
+  DevBuf<uint32_t> d_cover;
+  DevBuf<long long> d_rowsTotal;
+  double ms_finalize = 0;
   rmgpu_result* search(const rmgpu_params& p);        // whole resident batch, in memory-bounded chunks of queries
   rmgpu_result* search_batch(const rmgpu_params& p);  // one chunk: K1 -> K2 -> K3 -> host post
   int query_capacity() const;
@@ -266,8 +274,9 @@ struct rmgpu_session {
 // stripe are filled with subjects that fit entirely.
 // -------------------------------------------------------------------------------------------------------------
 void rmgpu_session::set_library(SeqSet s) {
-  if (!haveMatrix) throw Error("set the matrix before the library");
   lib = std::move(s);
+  lib.mark_exotic();
+  const CanonTables& ct = canon();
   const int n = (int)lib.seqs.size();
   std::vector<int> groups(n);
   std::multimap<int, int> pool;  // groups -> subject, the subjects not yet placed
@@ -314,7 +323,7 @@ void rmgpu_session::set_library(SeqSet s) {
       gflags[g] = gi == 0 ? 1 : 0;
       for (int r = 0; r < R; r++) {
         size_t pos = (size_t)gi * R + r;
-        if (pos < sq.size()) rowcode[(size_t)g * R + r] = matrix.code_of[(unsigned char)sq[pos]];
+        if (pos < sq.size()) rowcode[(size_t)g * R + r] = ct.of_letter[(unsigned char)sq[pos]];
       }
     }
   }, 32);
@@ -336,8 +345,10 @@ void rmgpu_session::set_library(SeqSet s) {
   }
   std::vector<uint8_t> scodes((size_t)std::max<int64_t>(h_soff[n], 1));
   parallel_for(n, [&](int i) {
-    for (size_t k = 0; k < lib.seqs[i].size(); k++) scodes[h_soff[i] + k] = matrix.code_of[(unsigned char)lib.seqs[i][k]];
+    for (size_t k = 0; k < lib.seqs[i].size(); k++) scodes[h_soff[i] + k] = ct.of_letter[(unsigned char)lib.seqs[i][k]];
   }, 32);
+  h2d_bytes_library = (int64_t)rowcode.size() + gflags.size() + sflags.size() + h_gsubject.size() * 4 + scodes.size() +
+                      h_soff.size() * 8 + slen.size() * 4;
   d_rowcode.upload(rowcode, stream);
   d_gflags.upload(gflags, stream);
   d_sflags.upload(sflags, stream);
@@ -351,8 +362,9 @@ void rmgpu_session::set_library(SeqSet s) {
 }
 
 void rmgpu_session::set_queries(SeqSet s) {
-  if (!haveMatrix) throw Error("set the matrix before the queries");
   queries = std::move(s);
+  queries.mark_exotic();
+  const CanonTables& ct = canon();
   const int n = (int)queries.seqs.size();
   h_qoff.assign(n + 1, 0);
   h_selOff.assign(n + 1, 0);
@@ -374,7 +386,7 @@ void rmgpu_session::set_queries(SeqSet s) {
   }
   selTotal = h_selOff[n];
   std::vector<uint8_t> packed((size_t)(h_qoff[n] / 2 + 1), 0);
-  int64_t counts[16] = {};
+  for (auto& c : canonCounts) c = 0;
   {
     // every record starts on a byte of `packed` (even nibble offsets), so records are packed independently
     std::vector<std::array<int64_t, 16>> cnt(n);
@@ -383,7 +395,7 @@ void rmgpu_session::set_queries(SeqSet s) {
       std::array<int64_t, 16>& cc = cnt[i];
       cc.fill(0);
       for (size_t k = 0; k < q.size(); k++) {
-        uint8_t c = matrix.code_of[(unsigned char)q[k]];
+        uint8_t c = ct.of_letter[(unsigned char)q[k]];
         cc[c]++;
         int64_t nib = h_qoff[i] + (int64_t)k;
         packed[nib >> 1] |= (uint8_t)(c << ((nib & 1) * 4));
@@ -391,42 +403,9 @@ void rmgpu_session::set_queries(SeqSet s) {
     }, 1);
     for (int i = 0; i < n; i++)
       for (int c = 0; c < 16; c++) {
-        counts[c] += cnt[i][c];
-        counts[matrix.comp_code[c]] += cnt[i][c];
+        canonCounts[c] += cnt[i][c];
+        canonCounts[ct.comp[c]] += cnt[i][c];
       }
-  }
-  // residue classes: up to 7 exact; beyond that the rarest codes share class 6 with row-wise max scores, which
-  // makes K1 an upper bound (still an exact filter: K2 recomputes every passing pair with the full alphabet)
-  std::vector<int> present;
-  for (int c = 0; c < matrix.n; c++)
-    if (counts[c] > 0) present.push_back(c);
-  std::stable_sort(present.begin(), present.end(), [&](int a, int b) { return counts[a] > counts[b]; });
-  std::vector<uint8_t> key;
-  int nExact = present.size() <= 7 ? (int)present.size() : 6;
-  classesExact = present.size() <= 7;
-  for (int c = 0; c < 16; c++) class_of_code[c] = 6;
-  for (int k = 0; k < nExact; k++) class_of_code[present[k]] = (uint8_t)k;
-  for (int sc = 0; sc < 16; sc++) {
-    for (int k = 0; k < 8; k++) class_score[sc][k] = -128;
-    if (sc >= matrix.n) continue;
-    auto clampv = [&](int v) {
-      if (v > 127) throw Error("matrix score > 127 is not supported by the int8 profile");
-      if (v < -128) classesExact = false;  // clamped: K1 becomes an upper bound, its checkpoints are not exact
-      return (int8_t)std::max(v, -128);
-    };
-    for (int k = 0; k < nExact; k++) class_score[sc][k] = clampv(matrix.score[sc][present[k]]);
-    if (!classesExact) {
-      int mx = -128;
-      for (size_t k = 6; k < present.size(); k++) mx = std::max(mx, matrix.score[sc][present[k]]);
-      class_score[sc][6] = clampv(mx);
-    }
-  }
-  for (int c = 0; c < 16; c++) key.push_back(class_of_code[c]);
-  for (int sc = 0; sc < 16; sc++)
-    for (int k = 0; k < 8; k++) key.push_back((uint8_t)class_score[sc][k]);
-  if (key != classKey) {
-    classKey = key;
-    profileValid = false;
   }
   double t0 = now_ms();
   d_qpacked.upload(packed, stream);
@@ -438,6 +417,57 @@ void rmgpu_session::set_queries(SeqSet s) {
   d_sel.ensure((size_t)std::max<int64_t>(selTotal, 1));
   d_codes_fwd.ensure((size_t)std::max<int64_t>(h_qoff[n], 1));
   d_codes_rc.ensure((size_t)std::max<int64_t>(h_qoff[n], 1));
+  streamsValid = false;
+  haveQueries = true;
+  if (haveMatrix) prepare_streams();  // K0 now, so that the copy and the expansion are both inside the upload's time
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  ms_h2d_queries = now_ms() - t0;
+  h2d_bytes_queries = (int64_t)packed.size() + (int64_t)(n + 1) * 24;
+}
+
+// Residue classes of the score pass and the per-column selector / code streams (K0).  Depends on the matrix (which letters
+// share a column) and on the batch (which columns occur): rebuilt when either changes.
+// Up to 7 exact classes; beyond that the rarest columns share class 6 with row-wise max scores, which makes K1 an upper
+// bound (still an exact filter: K2 recomputes every passing pair with the full alphabet).
+void rmgpu_session::prepare_streams() {
+  if (streamsValid) return;
+  if (!haveMatrix || !haveQueries) throw Error("matrix and queries must be set");
+  const int n = (int)queries.seqs.size();
+  int64_t counts[16] = {};
+  for (int c = 0; c < 16; c++) counts[matrix.col_of_canon[c]] += canonCounts[c];
+  std::vector<int> present;
+  for (int c = 0; c < matrix.n; c++)
+    if (counts[c] > 0) present.push_back(c);
+  std::stable_sort(present.begin(), present.end(), [&](int a, int b) { return counts[a] > counts[b]; });
+  std::vector<uint8_t> key;
+  int nExact = present.size() <= 7 ? (int)present.size() : 6;
+  classesExact = present.size() <= 7;
+  uint8_t class_of_col[16];
+  for (int c = 0; c < 16; c++) class_of_col[c] = 6;
+  for (int k = 0; k < nExact; k++) class_of_col[present[k]] = (uint8_t)k;
+  for (int c = 0; c < 16; c++) class_of_code[c] = class_of_col[matrix.col_of_canon[c]];
+  for (int sc = 0; sc < 16; sc++) {  // sc: canonical subject code
+    for (int k = 0; k < 8; k++) class_score[sc][k] = -128;
+    const int scol = matrix.col_of_canon[sc];
+    auto clampv = [&](int v) {
+      if (v > 127) throw Error("matrix score > 127 is not supported by the int8 profile");
+      if (v < -128) classesExact = false;  // clamped: K1 becomes an upper bound, its checkpoints are not exact
+      return (int8_t)std::max(v, -128);
+    };
+    for (int k = 0; k < nExact; k++) class_score[sc][k] = clampv(matrix.score[scol][present[k]]);
+    if (!classesExact && present.size() > 7) {
+      int mx = -128;
+      for (size_t k = 6; k < present.size(); k++) mx = std::max(mx, matrix.score[scol][present[k]]);
+      class_score[sc][6] = clampv(mx);
+    }
+  }
+  for (int c = 0; c < 16; c++) key.push_back(class_of_code[c]);
+  for (int sc = 0; sc < 16; sc++)
+    for (int k = 0; k < 8; k++) key.push_back((uint8_t)class_score[sc][k]);
+  if (key != classKey) {
+    classKey = key;
+    profileValid = false;
+  }
   if (n > 0) {
     StreamArgs a;
     a.qpacked = d_qpacked.p;
@@ -450,15 +480,14 @@ void rmgpu_session::set_queries(SeqSet s) {
     a.codes_rc = d_codes_rc.p;
     a.nQueries = n;
     memcpy(a.class_of_code, class_of_code, 16);
-    memcpy(a.comp_code, matrix.comp_code, 16);
+    memcpy(a.comp_code, canon().comp, 16);
     dim3 grid((unsigned)std::min<int64_t>(((int64_t)maxQ + 64 + 255) / 256, 1024), (unsigned)n);
     build_streams_kernel<<<grid, 256, 0, stream>>>(a);
     CUDA_CHECK(cudaGetLastError());
   }
-  CUDA_CHECK(cudaStreamSynchronize(stream));
-  ms_h2d_queries = now_ms() - t0;
-  h2d_bytes_queries = (int64_t)packed.size() + (int64_t)(n + 1) * 24;
-  haveQueries = true;
+  for (int i = 0; i < 16; i++)
+    for (int j = 0; j < 16; j++) h_mat[i][j] = matrix.score[matrix.col_of_canon[i]][matrix.col_of_canon[j]];
+  streamsValid = true;
 }
 
 void rmgpu_session::build_classes_and_profile() {
@@ -546,6 +575,7 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   if (nQ == 0 || nS == 0) return;
   if (p.gap_init >= 0 || p.ins_gap_ext > 0 || p.del_gap_ext > 0 || p.gap_init < -20000)
     throw Error("gap penalties must be negative");
+  prepare_streams();
   build_classes_and_profile();
   int blocksPerSM = 0;
   if (exact)
@@ -701,9 +731,6 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     c.i1 = (int)(0xFFFFFu - (uint32_t)((v >> 20) & 0xFFFFFu));
     c.j1 = (int)(0xFFFFFu - (uint32_t)(v & 0xFFFFFu));
   };
-  for (int i = 0; i < 16; i++)
-    for (int j = 0; j < 16; j++) h_mat[i][j] = (i < matrix.n && j < matrix.n) ? matrix.score[i][j] : -128;
-
   static const bool dbgK2 = getenv("RMGPU_DEBUG_K2") != nullptr;
   const double k2t0 = now_ms();
   std::atomic<int> chainLaunched{0};  // set once the fallback sweep's kernel is in its stream (or there is none)
@@ -1185,20 +1212,44 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   st.n_candidates = (int)cands.size();
 }
 
-// K3 with the band schedule W = max(bandwidth,1) * 2^k until the banded score reproduces the raw score.
-void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands,
-                                  std::vector<std::vector<uint8_t>>& ops, rmgpu_stats& st) {
-  ops.assign(cands.size(), {});
-  // band schedule: W0 = max(bandwidth,1) + max(n,m)/32, doubled until the banded score reproduces the raw score
-  std::vector<int> todo(cands.size()), W(cands.size());
+// K3 with the band schedule W = max(bandwidth,1) * 2^k until the banded score reproduces the raw score.  The edit
+// operations stay on the device (d_ops, one slot of n + m bytes per candidate): K4 spells the rows from them.
+void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands, rmgpu_stats& st) {
+  const size_t nC = cands.size();
+  h_candAll.resize(nC);
+  int64_t opsTotal = 0;
+  std::vector<int> todo(nC), W(nC);
   std::iota(todo.begin(), todo.end(), 0);
-  for (size_t i = 0; i < cands.size(); i++)
-    W[i] = std::max(p.bandwidth, 1) + std::max(cands[i].i1 - cands[i].i0 + 1, cands[i].j1 - cands[i].j0 + 1) / 32;
+  for (size_t i = 0; i < nC; i++) {
+    const Candidate& c = cands[i];
+    const int n = c.i1 - c.i0 + 1, m = c.j1 - c.j0 + 1;
+    W[i] = std::max(p.bandwidth, 1) + std::max(n, m) / 32;
+    TraceCand& t = h_candAll[i];
+    memset(&t, 0, sizeof(t));
+    t.q = c.q;
+    t.strand = c.strand;
+    t.subject = c.subject;
+    t.i0 = c.i0;
+    t.j0 = c.j0;
+    t.i1 = c.i1;
+    t.j1 = c.j1;
+    t.raw = c.raw;
+    t.id = (int32_t)i;
+    t.opsOff = opsTotal;
+    opsTotal += n + m;
+  }
+  opsBytes = opsTotal;
+  if (nC == 0) return;
+  d_ops.ensure((size_t)opsTotal);
+  d_opsLen.ensure(nC);
+  d_status.ensure(nC);
+  d_candAll.upload(h_candAll, stream);
   auto band_of = [&](int id) {
     const Candidate& c = cands[id];
     return (int64_t)std::abs((c.i1 - c.i0) - (c.j1 - c.j0)) + 2 * (int64_t)W[id] + 1;
   };
   const int64_t kDirBudget = 4ll << 30;  // direction bytes per launch
+  std::vector<int32_t> hlen(nC);
   while (!todo.empty()) {
     std::vector<int> next;
     // narrow bands first (one warp each), then wide bands (a team of up to 512 threads of a block each)
@@ -1206,36 +1257,25 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
     size_t at = 0;
     while (at < todo.size()) {
       std::vector<TraceCand> tc;
-      std::vector<int> ids;
-      int64_t dirTot = 0, rowTot = 0, opsTot = 0;
+      int64_t dirTot = 0, rowTot = 0;
       while (at < todo.size()) {
-        const Candidate& c = cands[todo[at]];
-        int n = c.i1 - c.i0 + 1, m = c.j1 - c.j0 + 1, w = W[todo[at]];
+        const int id = todo[at];
+        const Candidate& c = cands[id];
+        int n = c.i1 - c.i0 + 1, m = c.j1 - c.j0 + 1, w = W[id];
         int64_t bw = (int64_t)std::abs(n - m) + 2 * (int64_t)w + 1;
         // the kernel itself retries once with the doubled band (same schedule, no second launch for the few that
         // need it): the scratch is sized for that last attempt
         const int64_t bwLast = (int64_t)std::abs(n - m) + 2 * ((int64_t)w << (kTraceAttempts - 1)) + 1;
         int64_t dirBytes = (int64_t)(n + 1) * bwLast;
-        if (!tc.empty() && (dirTot + dirBytes > kDirBudget || (band_of(ids[0]) > 64) != (bw > 64))) break;
-        TraceCand t;
-        t.q = c.q;
-        t.strand = c.strand;
-        t.subject = c.subject;
-        t.i0 = c.i0;
-        t.j0 = c.j0;
-        t.i1 = c.i1;
-        t.j1 = c.j1;
-        t.raw = c.raw;
+        if (!tc.empty() && (dirTot + dirBytes > kDirBudget || (band_of(tc[0].id) > 64) != (bw > 64))) break;
+        TraceCand t = h_candAll[id];
         t.W = w;
         t.attempts = kTraceAttempts;
         t.dirOff = dirTot;
         t.rowOff = rowTot;
-        t.opsOff = opsTot;
         dirTot += dirBytes;
         rowTot += 3 * bwLast;
-        opsTot += n + m;
         tc.push_back(t);
-        ids.push_back(todo[at]);
         at++;
       }
       TraceArgs a;
@@ -1247,109 +1287,166 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
       a.qoff = d_qoff.p;
       a.scodes = d_scodes.p;
       a.soff = d_soff.p;
-      for (int i = 0; i < 16; i++)
-        for (int j = 0; j < 16; j++) a.mat[i][j] = (i < matrix.n && j < matrix.n) ? matrix.score[i][j] : -128;
+      memcpy(a.mat, h_mat, sizeof(h_mat));
       a.gap_init = p.gap_init;
       a.ins_ext = p.ins_gap_ext;
       a.del_ext = p.del_gap_ext;
       a.dir = d_dir.ensure((size_t)dirTot);
       a.rows = d_rows.ensure((size_t)rowTot);
-      a.ops = d_ops.ensure((size_t)opsTot);
-      a.opsLen = d_opsLen.ensure(tc.size());
-      a.status = d_status.ensure(tc.size());
+      a.ops = d_ops.p;
+      a.opsLen = d_opsLen.p;
+      a.status = d_status.p;
+      const bool wide = band_of(tc[0].id) > 64;
       EventTimer tm;
       tm.start(stream);
-      if (band_of(ids[0]) > 64)
+      if (wide)
         traceback_kernel<true><<<(int)tc.size(), kTraceBlockThreads, 0, stream>>>(a);
       else
         traceback_kernel<false><<<((int)tc.size() + kTraceWarps - 1) / kTraceWarps, kTraceWarps * 32, 0, stream>>>(a);
       tm.stop(stream);
       CUDA_CHECK(cudaGetLastError());
-      std::vector<uint8_t> hops((size_t)opsTot);
-      std::vector<int32_t> hlen(tc.size());
-      CUDA_CHECK(cudaMemcpyAsync(hops.data(), a.ops, (size_t)opsTot, cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaMemcpyAsync(hlen.data(), a.opsLen, tc.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaMemcpyAsync(hlen.data(), d_opsLen.p, nC * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
       CUDA_CHECK(cudaStreamSynchronize(stream));
       st.ms_traceback += tm.ms();
       st.launches += 1;
-      st.d2h_bytes += opsTot + (int64_t)tc.size() * 4;
+      st.d2h_bytes += (int64_t)nC * 4;
       static const bool dbgK3 = getenv("RMGPU_DEBUG_K3") != nullptr;
       if (dbgK3) {
         int maxN = 0, failed = 0;
         int64_t maxBand = 0, longBand = 0;
-        for (size_t i = 0; i < tc.size(); i++) {
-          const int n = tc[i].i1 - tc[i].i0 + 1;
-          if (n > maxN) maxN = n, longBand = band_of(ids[i]);
-          maxBand = std::max(maxBand, band_of(ids[i]));
-          failed += hlen[i] <= 0;
+        for (auto& t : tc) {
+          const int n = t.i1 - t.i0 + 1;
+          if (n > maxN) maxN = n, longBand = band_of(t.id);
+          maxBand = std::max(maxBand, band_of(t.id));
+          failed += hlen[t.id] <= 0;
         }
         fprintf(stderr, "[K3 dbg] %s launch: %zu candidates, %.2f ms, longest %d rows (band %lld), widest band %lld, %d to retry, dir bytes %.1f MB\n",
-                band_of(ids[0]) > 64 ? "block" : "warp", tc.size(), tm.ms(), maxN, (long long)longBand, (long long)maxBand, failed, dirTot / 1e6);
+                wide ? "block" : "warp", tc.size(), tm.ms(), maxN, (long long)longBand, (long long)maxBand, failed, dirTot / 1e6);
       }
-      for (size_t i = 0; i < tc.size(); i++) {
-        int id = ids[i];
-        if (hlen[i] > 0) {
-          ops[id].assign(hops.begin() + tc[i].opsOff, hops.begin() + tc[i].opsOff + hlen[i]);
-          std::reverse(ops[id].begin(), ops[id].end());
-        } else {
-          const Candidate& c = cands[id];
-          int full = std::max(c.i1 - c.i0 + 1, c.j1 - c.j0 + 1);
-          if (W[id] >= full) throw Error("traceback could not reproduce the forward score");
-          W[id] <<= kTraceAttempts;
-          next.push_back(id);
-        }
+      for (auto& t : tc) {
+        const int id = t.id;
+        if (hlen[id] > 0) continue;
+        const Candidate& c = cands[id];
+        int full = std::max(c.i1 - c.i0 + 1, c.j1 - c.j0 + 1);
+        if (W[id] >= full) throw Error("traceback could not reproduce the forward score");
+        W[id] <<= kTraceAttempts;
+        next.push_back(id);
       }
     }
     todo.swap(next);
   }
 }
 
-// -------------------------------------------------------------------------------------------------------------
-// Host post-processing: alignment rows, percentages, adjusted score, order, '*', masklevel.
-// -------------------------------------------------------------------------------------------------------------
-namespace {
-
-int base_class(char c) {
-  if (c == 'A' || c == 'G') return 0;
-  if (c == 'C' || c == 'T') return 1;
-  return -1;
+// K4 + K5: rows, counts, adjusted score and Kimura counts per candidate; '*' and masklevel per query record; the
+// survivors' rows packed.  Downloads the hit records and the packed rows.
+void rmgpu_session::run_finalize(const rmgpu_params& p, const std::vector<Candidate>& cands, std::vector<HitDev>& hits,
+                                 std::vector<char>& rows, rmgpu_stats& st) {
+  const int nC = (int)cands.size(), nQ = (int)queries.seqs.size();
+  hits.clear();
+  rows.clear();
+  if (nC == 0) return;
+  // ln(k) table of the host for every count an alignment can reach
+  {
+    int64_t need = 2;
+    for (auto& c : cands) need = std::max<int64_t>(need, std::min(c.i1 - c.i0, c.j1 - c.j0) + 2);
+    if ((int64_t)h_logtab.size() < need) {
+      const size_t old = h_logtab.size();
+      h_logtab.resize((size_t)std::max<int64_t>(need, 4096));
+      for (size_t k = old; k < h_logtab.size(); k++) h_logtab[k] = k == 0 ? 0.0 : std::log((double)k);
+      d_logtab.upload(h_logtab, stream);
+    }
+  }
+  EventTimer tm;
+  tm.start(stream);
+  RenderArgs r;
+  r.cand = d_candAll.p;
+  r.nCand = nC;
+  r.codes_fwd = d_codes_fwd.p;
+  r.codes_rc = d_codes_rc.p;
+  r.qoff = d_qoff.p;
+  r.qlen = d_qlen.p;
+  r.scodes = d_scodes.p;
+  r.soff = d_soff.p;
+  r.ops = d_ops.p;
+  r.opsLen = d_opsLen.p;
+  memcpy(r.col_of_canon, matrix.col_of_canon, 16);
+  r.nCols = matrix.n;
+  r.lambda = matrix.lambda;
+  for (int k = 0; k < 16; k++) {
+    const bool use = k < matrix.n && matrix.freq[k] > 0 && std::log(matrix.freq[k]) != 0;
+    r.freqUse[k] = use;
+    r.logfreq[k] = use ? std::log(matrix.freq[k]) : 0.0;
+  }
+  r.logtab = d_logtab.p;
+  r.logtabN = (int)h_logtab.size();
+  r.rawMode = p.raw ? 1 : 0;
+  r.minscore = p.minscore;
+  r.rows = d_rowsOut.ensure((size_t)(2 * opsBytes + 2 * (int64_t)nC + 16));
+  r.out = d_hits.ensure((size_t)nC);
+  render_alignment_kernel<<<(nC + kRenderWarps - 1) / kRenderWarps, kRenderWarps * 32, 0, stream>>>(r);
+  CUDA_CHECK(cudaGetLastError());
+  // per query record: candidates are sorted by query, so each record owns a contiguous range
+  std::vector<int32_t> qFirst(nQ, 0), qCount(nQ, 0);
+  std::vector<int64_t> coverOff(nQ + 1, 0);
+  for (int i = 0; i < nC; i++) qCount[cands[i].q]++;
+  int maxCount = 0;
+  for (int q = 0; q < nQ; q++) {
+    qFirst[q] = q ? qFirst[q - 1] + qCount[q - 1] : 0;
+    maxCount = std::max(maxCount, qCount[q]);
+    coverOff[q + 1] = coverOff[q] + (p.masklevel < 101 ? ((int64_t)h_qlen[q] + 31) / 32 + 1 : 0);
+  }
+  FinalizeArgs f;
+  d_qFirst.upload(qFirst, stream);
+  d_qCount.upload(qCount, stream);
+  d_coverOff.upload(coverOff, stream);
+  f.hits = d_hits.p;
+  f.qFirst = d_qFirst.p;
+  f.qCount = d_qCount.p;
+  f.qlen = d_qlen.p;
+  f.nQueries = nQ;
+  f.masklevel = p.masklevel;
+  f.order = d_rankOrder.ensure((size_t)nC);
+  f.nKept = d_nKept.ensure((size_t)nQ);
+  f.cover = d_cover.ensure((size_t)std::max<int64_t>(coverOff[nQ], 1));
+  f.coverOff = d_coverOff.p;
+  CUDA_CHECK(cudaMemsetAsync(f.nKept, 0, (size_t)nQ * sizeof(int32_t), stream));
+  star_rank_kernel<<<dim3((unsigned)((maxCount + 255) / 256), (unsigned)nQ), 256, 0, stream>>>(f);
+  CUDA_CHECK(cudaGetLastError());
+  st.launches += 2;
+  if (p.masklevel < 101) {
+    CUDA_CHECK(cudaMemsetAsync(f.cover, 0, (size_t)coverOff[nQ] * sizeof(uint32_t), stream));
+    masklevel_kernel<<<(nQ + 3) / 4, 128, 0, stream>>>(f);
+    CUDA_CHECK(cudaGetLastError());
+    st.launches += 1;
+  }
+  GatherArgs g;
+  g.hits = d_hits.p;
+  g.nCand = nC;
+  g.rows = d_rowsOut.p;
+  g.packed = d_rowsPacked.ensure((size_t)(2 * opsBytes + 2 * (int64_t)nC + 16));
+  g.total = d_rowsTotal.ensure(1);
+  scan_rows_kernel<<<1, 1024, 0, stream>>>(g);
+  if (p.want_alignments) gather_rows_kernel<<<(nC + 7) / 8, 256, 0, stream>>>(g);
+  CUDA_CHECK(cudaGetLastError());
+  st.launches += p.want_alignments ? 2 : 1;
+  tm.stop(stream);
+  hits.resize((size_t)nC);
+  long long total = 0;
+  CUDA_CHECK(cudaMemcpyAsync(hits.data(), d_hits.p, (size_t)nC * sizeof(HitDev), cudaMemcpyDeviceToHost, stream));
+  CUDA_CHECK(cudaMemcpyAsync(&total, g.total, sizeof(total), cudaMemcpyDeviceToHost, stream));
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  st.d2h_bytes += (int64_t)nC * (int64_t)sizeof(HitDev) + 8;
+  if (p.want_alignments && total > 0) {
+    rows.resize((size_t)total);
+    CUDA_CHECK(cudaMemcpyAsync(rows.data(), g.packed, (size_t)total, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    st.d2h_bytes += total;
+  }
+  ms_finalize = tm.ms();
 }
 
+namespace {
 void fmt_pct(char* out, long num, long den) { snprintf(out, 8, "%.2f", den > 0 ? 100.0 * (double)num / (double)den : 0.0); }
-
-struct IntervalUnion {  // disjoint, merged closed intervals
-  std::map<int, int> iv;  // start -> end
-  bool overlaps(int a, int b) const {
-    auto it = iv.upper_bound(b);
-    if (it == iv.begin()) return false;
-    --it;
-    return it->second >= a;
-  }
-  long covered(int a, int b) const {
-    long c = 0;
-    auto it = iv.upper_bound(a);
-    if (it != iv.begin()) --it;
-    for (; it != iv.end() && it->first <= b; ++it) {
-      int lo = std::max(a, it->first), hi = std::min(b, it->second);
-      if (hi >= lo) c += hi - lo + 1;
-    }
-    return c;
-  }
-  void add(int a, int b) {
-    auto it = iv.upper_bound(a);
-    if (it != iv.begin()) {
-      auto pr = std::prev(it);
-      if (pr->second >= a - 1) it = pr;
-    }
-    while (it != iv.end() && it->first <= b + 1) {
-      a = std::min(a, it->first);
-      b = std::max(b, it->second);
-      it = iv.erase(it);
-    }
-    iv[a] = b;
-  }
-};
-
 }  // namespace
 
 // How many query records one pass may hold: the K1 column checkpoints (kHotBlocks x rows x 8 B per query) and the stripe
@@ -1429,8 +1526,12 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
   st.h2d_bytes = h2d_bytes_queries;
   st.ms_h2d = ms_h2d_queries;
   const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
-  for (int q = 0; q < nQ; q++)
-    for (int s = 0; s < nS; s++) st.cells += 2.0 * (double)queries.seqs[q].size() * (double)lib.seqs[s].size();
+  {
+    double qb = 0, sb = 0;
+    for (int q = 0; q < nQ; q++) qb += (double)queries.seqs[q].size();
+    for (int s = 0; s < nS; s++) sb += (double)lib.seqs[s].size();
+    st.cells = 2.0 * qb * sb;
+  }
 
   std::vector<int32_t> pairbest;
   std::vector<unsigned long long> hotmask;
@@ -1442,204 +1543,116 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
   std::vector<Candidate> cands;
   run_origin(p, pairbest, hotmask, cands, st);
   const double w2 = now_ms();
-  std::vector<std::vector<uint8_t>> ops;
-  run_traceback(p, cands, ops, st);
+  run_traceback(p, cands, st);
   const double w3 = now_ms();
+  std::vector<HitDev> dh;
+  std::vector<char> rows;
+  run_finalize(p, cands, dh, rows, st);
+  const double w4 = now_ms();
 
+  // What is left for the host: the output order, the decimal text of three percentages and of the Kimura divergence
+  // (one logarithm per hit), names and pointers.  No per-column work.
   const double t_post = now_ms();
-  // one record per candidate, built by a few host threads (candidates are independent; the order is restored below)
-  std::vector<std::string> rcCache(nQ);
-  {
-    std::vector<char> needRc(nQ, 0);
-    for (const Candidate& c : cands)
-      if (c.strand) needRc[c.q] = 1;
-    parallel_for(nQ, [&](int q) {
-      if (needRc[q]) rcCache[q] = revcomp_letters(queries.seqs[q]);
-    });
+  struct Key {
+    int idx, qstart, qend;
+  };
+  std::vector<Key> keep;
+  keep.reserve(dh.size());
+  for (size_t i = 0; i < dh.size(); i++) {
+    const HitDev& h = dh[i];
+    if (!(h.flags & kHitKeep) || (h.flags & kHitDrop)) continue;
+    const int Q = h_qlen[h.q];
+    Key k;
+    k.idx = (int)i;
+    k.qstart = h.strand ? Q + 1 - h.i1 : h.i0;
+    k.qend = h.strand ? Q + 1 - h.i0 : h.i1;
+    keep.push_back(k);
   }
-  std::vector<HitRec> built(cands.size());
-  std::vector<char> keepRec(cands.size(), 0);
-  parallel_for((int)cands.size(), [&](int ci) {
-    const Candidate& c = cands[ci];
-    const std::string& qf = queries.seqs[c.q];
-    const std::string& sj = lib.seqs[c.subject];
-    const std::string& ql = c.strand ? rcCache[c.q] : qf;
-    const int Q = (int)qf.size(), L = (int)sj.size();
-    HitRec& h = built[ci];
-    const std::vector<uint8_t>& op_list = ops[ci];
-    h.qaln.resize(op_list.size());
-    h.saln.resize(op_list.size());
-    int64_t counts[kMaxAlpha] = {};
-    long nsub = 0, ndel = 0, nins = 0;
-    h.ti = h.tv = h.amb = h.gap_inits = h.gap_bases = 0;
-    int qi = c.i0 - 1, si = c.j0 - 1, prev = 0;
-    size_t col = 0;
-    for (uint8_t op : op_list) {
-      if (op == 0) {
-        char a = ql[qi++], b = sj[si++];
-        h.qaln[col] = a;
-        h.saln[col] = b;
-        counts[matrix.code_of[(unsigned char)a]]++;
-        if (a != b) {
-          nsub++;
-          int ca = base_class(a), cb = base_class(b);
-          if (ca < 0 || cb < 0)
-            h.amb++;
-          else if (ca == cb)
-            h.ti++;
-          else
-            h.tv++;
-        }
-      } else if (op == 1) {
-        h.qaln[col] = ql[qi++];
-        h.saln[col] = '-';
-        nins++;
-        h.gap_bases++;
-        if (prev != 1) h.gap_inits++;
-      } else {
-        h.qaln[col] = '-';
-        h.saln[col] = sj[si++];
-        ndel++;
-        h.gap_bases++;
-        if (prev != 2) h.gap_inits++;
-      }
-      prev = op;
-      col++;
-    }
-    h.raw = c.raw;
-    h.score = p.raw ? c.raw : complexity_adjust(c.raw, counts, matrix);
-    if (h.score < p.minscore) return;
-    h.qidx = c.q;
-    h.sidx = c.subject;
-    h.strand = c.strand;
-    if (!c.strand) {
-      h.qstart = c.i0;
-      h.qend = c.i1;
-    } else {
-      h.qstart = Q + 1 - c.i1;
-      h.qend = Q + 1 - c.i0;
-    }
-    h.qleft = Q - h.qend;
-    h.sstart = c.j0;
-    h.send = c.j1;
-    h.sleft = L - c.j1;
-    const int span = c.i1 - c.i0 + 1;
-    fmt_pct(h.div, nsub, span);
-    fmt_pct(h.del, ndel, span);
-    fmt_pct(h.ins, nins, span);
-    h.kimura[0] = 0;
-    if (p.want_alignments) {
-      const KimuraResult k = kimura_divergence(h.qaln.data(), h.saln.data(), h.qaln.size(), c.strand != 0);
-      snprintf(h.kimura, sizeof(h.kimura), "%4.2f", k.kimura);
-      h.cpg = k.cpgSites;
-      h.wcb = k.wellCharacterized;
-    }
-    keepRec[ci] = 1;
-  });
-  std::vector<HitRec> hits;
-  hits.reserve(cands.size());
-  for (size_t ci = 0; ci < cands.size(); ci++)
-    if (keepRec[ci]) hits.push_back(std::move(built[ci]));
   // output order: query order, ascending query start, DESCENDING subject order, then subject start, query end, strand
-  std::sort(hits.begin(), hits.end(), [](const HitRec& x, const HitRec& y) {
-    if (x.qidx != y.qidx) return x.qidx < y.qidx;
+  std::sort(keep.begin(), keep.end(), [&](const Key& x, const Key& y) {
+    const HitDev &a = dh[x.idx], &b = dh[y.idx];
+    if (a.q != b.q) return a.q < b.q;
     if (x.qstart != y.qstart) return x.qstart < y.qstart;
-    if (x.sidx != y.sidx) return x.sidx > y.sidx;
-    if (x.sstart != y.sstart) return x.sstart < y.sstart;
+    if (a.subject != b.subject) return a.subject > b.subject;
+    if (a.j0 != b.j0) return a.j0 < b.j0;
     if (x.qend != y.qend) return x.qend < y.qend;
-    if (x.strand != y.strand) return x.strand < y.strand;
-    return x.send < y.send;
+    if (a.strand != b.strand) return a.strand < b.strand;
+    return a.j1 < b.j1;
   });
-  // '*' and masklevel: per query, descending score, equal scores handled as a group (strictly higher counts)
-  {
-    std::vector<int> order(hits.size());
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      if (hits[a].qidx != hits[b].qidx) return hits[a].qidx < hits[b].qidx;
-      return hits[a].score > hits[b].score;
-    });
-    std::vector<char> drop(hits.size(), 0);
-    size_t i = 0;
-    while (i < order.size()) {
-      size_t qend = i;
-      while (qend < order.size() && hits[order[qend]].qidx == hits[order[i]].qidx) qend++;
-      IntervalUnion all, kept;
-      size_t g = i;
-      while (g < qend) {
-        size_t ge = g;
-        while (ge < qend && hits[order[ge]].score == hits[order[g]].score) ge++;
-        for (size_t k = g; k < ge; k++) {
-          HitRec& h = hits[order[k]];
-          h.star = all.overlaps(h.qstart, h.qend);
-          if (p.masklevel < 101) {
-            long len = h.qend - h.qstart + 1, unc = len - kept.covered(h.qstart, h.qend);
-            if (unc * 100 < (long)(100 - p.masklevel) * len) drop[order[k]] = 1;
-          }
-        }
-        for (size_t k = g; k < ge; k++) {
-          HitRec& h = hits[order[k]];
-          all.add(h.qstart, h.qend);
-          if (!drop[order[k]]) kept.add(h.qstart, h.qend);
-        }
-        g = ge;
-      }
-      i = qend;
-    }
-    if (p.masklevel < 101) {
-      std::vector<HitRec> keep;
-      for (size_t k = 0; k < hits.size(); k++)
-        if (!drop[k]) keep.push_back(std::move(hits[k]));
-      hits.swap(keep);
-    }
-  }
-  // marshal
   auto* arena = new ResultArena();
   res->opaque = arena;
-  res->n_hits = (int32_t)hits.size();
-  res->hits = hits.empty() ? nullptr : new rmgpu_hit[hits.size()];
+  res->n_hits = (int32_t)keep.size();
+  res->hits = keep.empty() ? nullptr : new rmgpu_hit[keep.size()];
+  const char* rowBase = arena->keep_buffer(std::move(rows));
   std::vector<const char*> qn(nQ, nullptr), sn(nS, nullptr);
-  for (size_t k = 0; k < hits.size(); k++) {
-    const HitRec& h = hits[k];
+  for (size_t k = 0; k < keep.size(); k++) {
+    const HitDev& h = dh[keep[k].idx];
     rmgpu_hit& o = res->hits[k];
     memset(&o, 0, sizeof(o));
+    const int Q = h_qlen[h.q], L = (int)lib.seqs[h.subject].size();
     o.score = h.score;
     o.raw_score = h.raw;
-    o.query_index = h.qidx;
-    o.subject_index = h.sidx;
-    if (!qn[h.qidx]) qn[h.qidx] = arena->dup(queries.names[h.qidx]);
-    if (!sn[h.sidx]) sn[h.sidx] = arena->dup(lib.names[h.sidx]);
-    o.query_name = qn[h.qidx];
-    o.subject_name = sn[h.sidx];
-    o.qstart = h.qstart;
-    o.qend = h.qend;
-    o.qleft = h.qleft;
-    o.sstart = h.sstart;
-    o.send = h.send;
-    o.sleft = h.sleft;
+    o.query_index = h.q;
+    o.subject_index = h.subject;
+    if (!qn[h.q]) qn[h.q] = arena->dup(queries.names[h.q]);
+    if (!sn[h.subject]) sn[h.subject] = arena->dup(lib.names[h.subject]);
+    o.query_name = qn[h.q];
+    o.subject_name = sn[h.subject];
+    o.qstart = keep[k].qstart;
+    o.qend = keep[k].qend;
+    o.qleft = Q - o.qend;
+    o.sstart = h.j0;
+    o.send = h.j1;
+    o.sleft = L - h.j1;
     o.strand = (uint8_t)h.strand;
-    o.overlap_star = h.star;
-    memcpy(o.pct_div, h.div, 8);
-    memcpy(o.pct_del, h.del, 8);
-    memcpy(o.pct_ins, h.ins, 8);
-    memcpy(o.pct_kimura, h.kimura, 8);
-    o.cpg_sites = h.cpg;
-    o.well_characterized = h.wcb;
+    o.overlap_star = (h.flags & kHitStar) ? 1 : 0;
+    int nsub = h.nsub;
+    if (p.want_alignments && h.outOff >= 0) {
+      o.qaln = rowBase + h.outOff;
+      o.saln = o.qaln + h.len + 1;
+      if (queries.exotic[h.q] || lib.exotic[h.subject])
+        nsub = respell_exotic(h, const_cast<char*>(o.qaln), const_cast<char*>(o.saln));
+    }
+    const int span = h.i1 - h.i0 + 1;
+    fmt_pct(o.pct_div, nsub, span);
+    fmt_pct(o.pct_del, h.ndel, span);
+    fmt_pct(o.pct_ins, h.nins, span);
     o.transitions = h.ti;
     o.transversions = h.tv;
     o.ambiguous = h.amb;
     o.gap_inits = h.gap_inits;
     o.gap_bases = h.gap_bases;
+    o.pct_kimura[0] = 0;
     if (p.want_alignments) {
-      o.qaln = arena->keep(std::move(hits[k].qaln));
-      o.saln = arena->keep(std::move(hits[k].saln));
+      snprintf(o.pct_kimura, sizeof(o.pct_kimura), "%4.2f", kimura_from_counts(h.ktrans, h.ktv, h.wcb));
+      o.cpg_sites = h.cpg;
+      o.well_characterized = h.wcb;
     }
   }
   st.ms_host_post = now_ms() - t_post;
   st.ms_total = now_ms() - t_begin + ms_h2d_queries;
   if (getenv("RMGPU_DEBUG_HOST"))
-    fprintf(stderr, "[host dbg] search_batch wall: setup %.2f  score %.2f (kernel %.2f)  origin %.2f  traceback %.2f (kernels %.2f)  post %.2f ms\n",
-            w0 - t_begin, w1 - w0, st.ms_score, w2 - w1, w3 - w2, st.ms_traceback, st.ms_host_post);
+    fprintf(stderr, "[host dbg] search_batch wall: setup %.2f  score %.2f (kernel %.2f)  origin %.2f  traceback %.2f (kernels %.2f)  finalize %.2f (kernels %.2f)  post %.2f ms\n",
+            w0 - t_begin, w1 - w0, st.ms_score, w2 - w1, w3 - w2, st.ms_traceback, w4 - w3, ms_finalize, st.ms_host_post);
   return res;
+}
+
+// A record with letters outside the canonical 16 (scored as N, like the oracle does) was spelled with N by the device:
+// put the original letters back and recount the mismatching pairs (letters, not codes, are compared).
+int rmgpu_session::respell_exotic(const HitDev& h, char* qrow, char* srow) const {
+  const std::string& qf = queries.seqs[h.q];
+  const std::string& sj = lib.seqs[h.subject];
+  const int Q = (int)qf.size();
+  int qi = h.i0 - 1, si = h.j0 - 1, nsub = 0;
+  for (int c = 0; c < h.len; c++) {
+    if (qrow[c] != '-') {
+      qrow[c] = h.strand ? complement_letter(qf[Q - 1 - qi]) : qf[qi];
+      qi++;
+    }
+    if (srow[c] != '-') srow[c] = sj[si++];
+    if (qrow[c] != '-' && srow[c] != '-' && qrow[c] != srow[c]) nsub++;
+  }
+  return nsub;
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -1725,9 +1738,9 @@ int rmgpu_session_set_matrix_file(rmgpu_session* s, const char* f) {
     CUDA_CHECK(cudaSetDevice(s->device));
     s->matrix = ScoreMatrix::from_file(f);
     s->haveMatrix = true;
-    s->profileValid = false;
-    s->classKey.clear();
-    s->haveLib = s->haveQueries = false;  // codes depend on the matrix alphabet
+    // residue codes are matrix-independent: the packed library and batch stay; only the class map, the selector streams
+    // and the row profiles are rebuilt (K0, microseconds) at the next search
+    s->streamsValid = false;
   });
 }
 
@@ -1860,6 +1873,81 @@ int rmgpu_adjusted_score(const char* matrix_file, int32_t raw, const char* qaln,
       if (qaln[i] != '-' && saln[i] != '-') counts[m.code_of[(unsigned char)qaln[i]]]++;  // aligned pairs, query letter
     *adjusted = complexity_adjust(raw, counts, m);
   });
+}
+
+static int collection_filter(int device, int32_t n, const int32_t* name_id, const int32_t* qstart, const int32_t* qend,
+                             const int32_t* score, int32_t masklevel, uint8_t* keep, bool contained) {
+  return guarded([&] {
+    for (int i = 0; i < n; i++) keep[i] = 1;
+    if (n <= 0 || masklevel >= 101) return;  // both filters return at once for masklevel >= 101
+    if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
+    // the sort is the reference's own (a stable merge sort in perl): by name, then the filter's keys, ties in collection order
+    std::vector<int32_t> order((size_t)n);
+    std::iota(order.begin(), order.end(), 0);
+    if (!contained)
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (name_id[a] != name_id[b]) return name_id[a] < name_id[b];
+        if (score[a] != score[b]) return score[a] > score[b];
+        return qend[a] - qstart[a] < qend[b] - qstart[b];
+      });
+    else
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (name_id[a] != name_id[b]) return name_id[a] < name_id[b];
+        if (qstart[a] != qstart[b]) return qstart[a] < qstart[b];
+        return qend[a] > qend[b];
+      });
+    std::vector<int32_t> gFirst, gCount;
+    for (int i = 0; i < n; i++) {
+      if (i == 0 || name_id[order[i]] != name_id[order[i - 1]]) {
+        gFirst.push_back(i);
+        gCount.push_back(0);
+      }
+      gCount.back()++;
+    }
+    cudaStream_t st;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    DevBuf<int32_t> dStart, dEnd, dScore, dOrder, dFirst, dCount, dDom;
+    DevBuf<uint8_t> dDel;
+    std::vector<int32_t> vs(qstart, qstart + n), ve(qend, qend + n), vc(score, score + n);
+    dStart.upload(vs, st);
+    dEnd.upload(ve, st);
+    dScore.upload(vc, st);
+    dOrder.upload(order, st);
+    dFirst.upload(gFirst, st);
+    dCount.upload(gCount, st);
+    CollectionFilterArgs a;
+    a.start = dStart.p;
+    a.end = dEnd.p;
+    a.score = dScore.p;
+    a.order = dOrder.p;
+    a.gFirst = dFirst.p;
+    a.gCount = dCount.p;
+    a.nGroups = (int)gFirst.size();
+    a.n = n;
+    a.masklevel = masklevel;
+    a.domains = dDom.ensure((size_t)n);
+    a.deleted = dDel.ensure((size_t)n);
+    CUDA_CHECK(cudaMemsetAsync(a.deleted, 0, (size_t)n, st));
+    if (!contained)
+      perl_masklevel_kernel<<<(a.nGroups + 3) / 4, 128, 0, st>>>(a);
+    else
+      contained_kernel<<<(n + 255) / 256, 256, 0, st>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    std::vector<uint8_t> del((size_t)n);
+    CUDA_CHECK(cudaMemcpyAsync(del.data(), a.deleted, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaStreamDestroy(st);
+    for (int i = 0; i < n; i++) keep[i] = del[i] ? 0 : 1;
+  });
+}
+
+int rmgpu_masklevel_filter(int device, int32_t n, const int32_t* name_id, const int32_t* qstart, const int32_t* qend,
+                           const int32_t* score, int32_t masklevel, uint8_t* keep) {
+  return collection_filter(device, n, name_id, qstart, qend, score, masklevel, keep, false);
+}
+int rmgpu_contained_filter(int device, int32_t n, const int32_t* name_id, const int32_t* qstart, const int32_t* qend,
+                           const int32_t* score, int32_t masklevel, uint8_t* keep) {
+  return collection_filter(device, n, name_id, qstart, qend, score, masklevel, keep, true);
 }
 
 int rmgpu_measure_dpx_peak(int device, double* cups, double* dpx_instr_per_s) {

@@ -39,6 +39,20 @@ void parallel_for(int n, F&& f, int grain = 8) {
 
 constexpr int kMaxAlpha = 16;  // 4-bit residue codes on the device
 
+// Residue codes on the device are matrix-independent ("canonical"): the 15 IUPAC nucleotide letters and X, so that the
+// packed library and query records stay valid when only the scoring matrix changes (RepeatMasker switches GC-bin
+// matrices per batch, RepeatMasker:4784-4821) and the device can spell alignment rows itself.  Any other letter is
+// scored as N like the oracle does and marks its record "exotic" (its rows are then spelled on the host).
+constexpr char kCanonLetters[17] = "ACGTRYKMSWBDHVNX";
+constexpr uint8_t kCanonN = 14;
+struct CanonTables {
+  uint8_t of_letter[256];  // upper- or lower-case letter -> canonical code
+  bool exact[256];         // the letter is one of the 16 (else it was folded into N)
+  uint8_t comp[16];        // canonical code of the complementary letter (table of CrossmatchSearchEngine.pm:833)
+  CanonTables();
+};
+const CanonTables& canon();
+
 struct Error : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
@@ -52,6 +66,7 @@ struct ScoreMatrix {
   double lambda = 0;
   uint8_t code_of[256] = {};  // letter -> matrix column (fallback: N, else last column)
   uint8_t comp_code[kMaxAlpha] = {};  // column of the complementary letter
+  uint8_t col_of_canon[kMaxAlpha] = {};  // canonical device code -> matrix column (= code_of[kCanonLetters[c]])
   std::string name;           // basename, reported as matrixName (CrossmatchSearchEngine.pm:398-409)
 
   static ScoreMatrix from_file(const std::string& path);
@@ -63,6 +78,8 @@ struct ScoreMatrix {
 struct SeqSet {
   std::vector<std::string> names;
   std::vector<std::string> seqs;  // upper-case letters (FastaDB.pm:1110-1118 upper-cases on load)
+  std::vector<uint8_t> exotic;    // per record: holds a letter outside the canonical 16 (filled by mark_exotic)
+  void mark_exotic();
   int64_t total_bases() const {
     int64_t t = 0;
     for (auto& s : seqs) t += (int64_t)s.size();
@@ -82,6 +99,8 @@ struct KimuraResult {
   int transversions, wellCharacterized, cpgSites;
 };
 KimuraResult kimura_divergence(const char* qaln, const char* saln, size_t len, bool strandC);
+// the final formula of the same routine from its three counts: |-1/2 ln((1 - 2p - q) sqrt(1 - 2q))| * 100
+double kimura_from_counts(double transitions, int transversions, int wellCharacterized);
 
 // SearchResult.pm:2111-2150 in double precision, perl int() truncation.
 int complexity_adjust(int raw, const int64_t counts[kMaxAlpha], const ScoreMatrix& m);
@@ -98,6 +117,11 @@ struct ResultArena {
     return blocks.back().get();
   }
   const char* dup(const std::string& s) { return dup(s.data(), s.size()); }
+  std::vector<std::vector<char>> buffers;  // whole buffers handed over without a copy (the packed alignment rows)
+  const char* keep_buffer(std::vector<char>&& b) {
+    buffers.emplace_back(std::move(b));
+    return buffers.back().data();
+  }
   std::vector<std::unique_ptr<std::string>> strings;  // strings handed over without a copy
   const char* keep(std::string&& s) {
     strings.emplace_back(new std::string(std::move(s)));

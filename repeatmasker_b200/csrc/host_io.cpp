@@ -78,6 +78,36 @@ ScoreMatrix ScoreMatrix::from_file(const std::string& path) {
   return m;
 }
 
+CanonTables::CanonTables() {
+  for (int i = 0; i < 256; i++) {
+    of_letter[i] = kCanonN;
+    exact[i] = false;
+  }
+  for (int k = 0; k < 16; k++) {
+    const unsigned char up = (unsigned char)kCanonLetters[k], lo = (unsigned char)std::tolower(up);
+    of_letter[up] = of_letter[lo] = (uint8_t)k;
+    exact[up] = exact[lo] = true;
+  }
+  for (int k = 0; k < 16; k++) comp[k] = of_letter[(unsigned char)complement_letter(kCanonLetters[k])];
+}
+
+const CanonTables& canon() {
+  static const CanonTables t;
+  return t;
+}
+
+void SeqSet::mark_exotic() {
+  const CanonTables& ct = canon();
+  exotic.assign(seqs.size(), 0);
+  parallel_for((int)seqs.size(), [&](int i) {
+    for (unsigned char c : seqs[i])
+      if (!ct.exact[c]) {
+        exotic[i] = 1;
+        break;
+      }
+  }, 64);
+}
+
 char complement_letter(char c) {
   // table of CrossmatchSearchEngine.pm:833 (tr/ACGTYRMKHBVD/TGCARYKMDVBH/), everything else maps to itself
   static const struct Table {
@@ -134,6 +164,7 @@ void ScoreMatrix::finish() {
     code_of[(unsigned char)std::tolower((unsigned char)alphabet[i])] = (uint8_t)i;
   }
   for (int i = 0; i < n; i++) comp_code[i] = code_of[(unsigned char)complement_letter(alphabet[i])];
+  for (int k = 0; k < kMaxAlpha; k++) col_of_canon[k] = code_of[(unsigned char)kCanonLetters[k]];
 }
 
 int ScoreMatrix::min_score() const {
@@ -231,13 +262,17 @@ KimuraResult kimura_divergence(const char* qaln, const char* saln, size_t len, b
     pS = sb;
   }
   transitions += prevTrans;
+  return {kimura_from_counts(transitions, transversions, wcb), transitions, transversions, wcb, cpg};
+}
+
+double kimura_from_counts(double transitions, int transversions, int wcb) {
   double kimura = 100.00;
   if (wcb >= 1) {
     const double p = transitions / wcb, q = (double)transversions / wcb;
     const double logOperand = (1 - (2 * p) - q) * std::pow(1 - (2 * q), 0.5);
     if (logOperand > 0) kimura = std::fabs(-0.5 * std::log(logOperand)) * 100;
   }
-  return {kimura, transitions, transversions, wcb, cpg};
+  return kimura;
 }
 
 int complexity_adjust(int raw, const int64_t counts[kMaxAlpha], const ScoreMatrix& m) {

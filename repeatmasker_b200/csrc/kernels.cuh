@@ -1187,6 +1187,8 @@ struct TraceCand {
   int32_t raw;
   int32_t W;                // band half-width of the first attempt
   int32_t attempts;         // attempts made inside the kernel, W doubling each time (scratch is sized for the last)
+  int32_t id;               // candidate number of the call: index into opsLen / status (a launch holds a subset)
+  int32_t pad_;
   int64_t dirOff;           // offset into dir scratch
   int64_t rowOff;           // offset into row scratch (3 * bw ints)
   int64_t opsOff;           // offset into ops
@@ -1205,8 +1207,8 @@ struct TraceArgs {
   uint8_t* dir;
   int32_t* rows;
   uint8_t* ops;
-  int32_t* opsLen;   // [nCand] number of ops, or -1
-  int32_t* status;   // [nCand] 1 + index of the attempt that succeeded, 0 if none did
+  int32_t* opsLen;   // [candidate id] number of ops, or -1
+  int32_t* status;   // [candidate id] 1 + index of the attempt that succeeded, 0 if none did
 };
 
 // Band cell (u, k) (k = d - dlo, v = u - dlo - k) depends on (u-1, k-1) [E], (u-1, k) [D] and (u, k+1) [F]; all
@@ -1429,9 +1431,517 @@ __global__ void __launch_bounds__(BLOCK ? kTraceBlockThreads : kTraceWarps * 32)
       __syncwarp();
   }
   if (tid == 0) {
-    a.opsLen[c] = len;
-    a.status[c] = len > 0 ? used : 0;
+    a.opsLen[tc.id] = len;
+    a.status[tc.id] = len > 0 ? used : 0;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4: alignment rows and everything that is counted over them, one warp per candidate (SearchResult.pm:2486-2834 prints
+// these rows; ti/tv as CrossmatchSearchEngine.pm:671-674 reads them; SearchResult.pm:2111-2150 adjusts the score;
+// SearchResult.pm:1607-1683 is the Kimura pass).
+//   rows     gapped query and subject rows in cross_match's display orientation (strand C: the reverse-complemented query
+//            ascending, subject forward), spelled from the canonical residue codes, NUL-terminated
+//   counts   mismatches / gaps (the percentages' numerators), transitions / transversions / ambiguous, gap starts and
+//            bases, aligned query letters per matrix column
+//   score    complexity-adjusted: int(raw + (sum c ln f - (sum c ln c - N ln N)) / lambda + .999) in IEEE double with
+//            round-to-nearest multiplies and adds in the host's order and the host's own ln() values (ln f and a table of
+//            ln k), so the result is the host's bit for bit
+//   Kimura   the sequential CpG-aware state machine, run by lane 0 over the finished rows; the logarithm of the final
+//            formula stays on the host (three numbers per hit)
+// ---------------------------------------------------------------------------------------------------------------
+struct HitDev {
+  int32_t raw, score;
+  int32_t q, subject, strand;
+  int32_t i0, j0, i1, j1;       // 1-based strand coordinates of origin and end cell
+  int32_t len;                  // alignment columns (0: no traceback)
+  int32_t nsub, ndel, nins, ti, tv, amb, gap_inits, gap_bases;
+  int32_t ktv, wcb, cpg;        // Kimura: transversions, well-characterised pairs, CpG sites
+  int32_t flags;                // kHitKeep | kHitStar | kHitDrop
+  double ktrans;                // Kimura: transitions (fractional with the CpG rule)
+  int64_t rowOff;               // query row at rows + rowOff (len + 1 bytes), subject row right behind it
+  int64_t outOff;               // after the gather: offset of the rows in the packed buffer that crosses PCIe
+};
+constexpr int kHitKeep = 1;  // reported score >= minscore
+constexpr int kHitStar = 2;  // a strictly higher-scoring kept hit of the same query overlaps its query domain
+constexpr int kHitDrop = 4;  // removed by masklevel
+
+struct RenderArgs {
+  const TraceCand* cand;
+  int nCand;
+  const uint8_t* codes_fwd;
+  const uint8_t* codes_rc;
+  const int64_t* qoff;
+  const int32_t* qlen;
+  const uint8_t* scodes;
+  const int64_t* soff;
+  const uint8_t* ops;
+  const int32_t* opsLen;
+  uint8_t col_of_canon[16];
+  int nCols;
+  double lambda;
+  double logfreq[16];     // host ln(freq[col]); NaN-free: see freqUse
+  uint8_t freqUse[16];    // freq[col] > 0 && ln(freq[col]) != 0
+  const double* logtab;   // host ln(k), k = 0 .. logtabN - 1
+  int logtabN;
+  int rawMode, minscore;
+  char* rows;
+  HitDev* out;
+};
+
+__device__ __forceinline__ int base_class_dev(int canon) {  // A G purine 0, C T pyrimidine 1, else -1 (canonical: A0 C1 G2 T3)
+  return canon == 0 || canon == 2 ? 0 : (canon == 1 || canon == 3 ? 1 : -1);
+}
+
+constexpr int kRenderWarps = 4;
+
+__global__ void __launch_bounds__(kRenderWarps * 32) render_alignment_kernel(RenderArgs a) {
+  __shared__ int s_cnt[kRenderWarps][16];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int c = blockIdx.x * kRenderWarps + wib;
+  if (c >= a.nCand) return;
+  const TraceCand tc = a.cand[c];
+  const int len = a.opsLen[tc.id];
+  HitDev h;
+  h.raw = tc.raw;
+  h.score = 0;
+  h.q = tc.q;
+  h.subject = tc.subject;
+  h.strand = tc.strand;
+  h.i0 = tc.i0;
+  h.j0 = tc.j0;
+  h.i1 = tc.i1;
+  h.j1 = tc.j1;
+  h.len = len > 0 ? len : 0;
+  h.nsub = h.ndel = h.nins = h.ti = h.tv = h.amb = h.gap_inits = h.gap_bases = 0;
+  h.ktv = h.wcb = h.cpg = 0;
+  h.flags = 0;
+  h.ktrans = 0;
+  h.rowOff = 2 * tc.opsOff + 2 * (int64_t)tc.id;  // rows need len + 1 bytes each, ops had n + m >= len
+  h.outOff = -1;
+  if (len <= 0) {
+    if (lane == 0) a.out[tc.id] = h;
+    return;
+  }
+  if (lane < 16) s_cnt[wib][lane] = 0;
+  __syncwarp();
+  const uint8_t* qc = (tc.strand ? a.codes_rc : a.codes_fwd) + a.qoff[tc.q];
+  const uint8_t* sc = a.scodes + a.soff[tc.subject];
+  const uint8_t* ops = a.ops + tc.opsOff;  // written back to front by the walk
+  char* qrow = a.rows + h.rowOff;
+  char* srow = qrow + len + 1;
+  const char* L = "ACGTRYKMSWBDHVNX";
+  int qi0 = tc.i0 - 1, si0 = tc.j0 - 1, carry = 0;
+  int nsub = 0, ndel = 0, nins = 0, ti = 0, tv = 0, amb = 0, ginit = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int c0 = 0; c0 < len; c0 += 32) {
+    const int col = c0 + lane;
+    const bool valid = col < len;
+    const int op = valid ? (int)ops[len - 1 - col] : 3;
+    const unsigned mq = __ballot_sync(0xffffffffu, valid && op != 2);
+    const unsigned ms = __ballot_sync(0xffffffffu, valid && op != 1);
+    int prev = __shfl_up_sync(0xffffffffu, op, 1);
+    if (lane == 0) prev = carry;
+    if (valid) {
+      const int qk = qc[qi0 + __popc(mq & lt)], sk = sc[si0 + __popc(ms & lt)];
+      if (op == 0) {
+        qrow[col] = L[qk];
+        srow[col] = L[sk];
+        atomicAdd(&s_cnt[wib][a.col_of_canon[qk]], 1);
+        if (qk != sk) {
+          nsub++;
+          const int ca = base_class_dev(qk), cb = base_class_dev(sk);
+          if (ca < 0 || cb < 0)
+            amb++;
+          else if (ca == cb)
+            ti++;
+          else
+            tv++;
+        }
+      } else if (op == 1) {
+        qrow[col] = L[qk];
+        srow[col] = '-';
+        nins++;
+        ginit += prev != 1;
+      } else {
+        qrow[col] = '-';
+        srow[col] = L[sk];
+        ndel++;
+        ginit += prev != 2;
+      }
+    }
+    qi0 += __popc(mq);
+    si0 += __popc(ms);
+    carry = __shfl_sync(0xffffffffu, op, 31);
+  }
+  if (lane == 0) {
+    qrow[len] = 0;
+    srow[len] = 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nsub += __shfl_xor_sync(0xffffffffu, nsub, o);
+    ndel += __shfl_xor_sync(0xffffffffu, ndel, o);
+    nins += __shfl_xor_sync(0xffffffffu, nins, o);
+    ti += __shfl_xor_sync(0xffffffffu, ti, o);
+    tv += __shfl_xor_sync(0xffffffffu, tv, o);
+    amb += __shfl_xor_sync(0xffffffffu, amb, o);
+    ginit += __shfl_xor_sync(0xffffffffu, ginit, o);
+  }
+  __syncwarp();  // rows and counts of every lane are visible to lane 0
+  if (lane != 0) return;
+  h.nsub = nsub;
+  h.ndel = ndel;
+  h.nins = nins;
+  h.ti = ti;
+  h.tv = tv;
+  h.amb = amb;
+  h.gap_inits = ginit;
+  h.gap_bases = ndel + nins;
+  // complexity-adjusted score (host_io.cpp:complexity_adjust, SearchResult.pm:2111-2150)
+  int score = tc.raw;
+  if (!a.rawMode) {
+    double t_factor = 0, t_sum = 0, t_counts = 0;
+    for (int k = 0; k < a.nCols; k++) {
+      const int cnt = s_cnt[wib][k];
+      if (cnt > 0 && a.freqUse[k]) {
+        const double kd = (double)cnt;
+        const double lk = cnt < a.logtabN ? a.logtab[cnt] : log(kd);
+        t_factor = __dadd_rn(t_factor, __dmul_rn(kd, lk));
+        t_sum = __dadd_rn(t_sum, __dmul_rn(kd, a.logfreq[k]));
+        t_counts = __dadd_rn(t_counts, kd);
+      }
+    }
+    if (t_counts != 0) {
+      const int tc_i = (int)t_counts;
+      const double lt_ = tc_i < a.logtabN ? a.logtab[tc_i] : log(t_counts);
+      t_factor = __dsub_rn(t_factor, __dmul_rn(t_counts, lt_));
+    }
+    t_sum = __dsub_rn(t_sum, t_factor);
+    const double adj = __dadd_rn(__dadd_rn((double)tc.raw, __ddiv_rn(t_sum, a.lambda)), .999);
+    score = (int)adj;
+    if (score < 0) score = 0;
+  }
+  h.score = score;
+  if (score >= a.minscore) h.flags |= kHitKeep;
+  // Kimura divergence counts (host_io.cpp:kimura_divergence): strand C reads the rows back to front through the
+  // complement, i.e. as CrossmatchSearchEngine.pm:824-837 stores them
+  {
+    auto base = [](char ch) { return ch == 'A' ? 0 : ch == 'G' ? 1 : ch == 'C' ? 2 : ch == 'T' ? 3 : -1; };
+    auto comp = [](char ch) {
+      switch (ch) {
+        case 'A': return 'T';
+        case 'C': return 'G';
+        case 'G': return 'C';
+        case 'T': return 'A';
+        case 'Y': return 'R';
+        case 'R': return 'Y';
+        case 'M': return 'K';
+        case 'K': return 'M';
+        case 'H': return 'D';
+        case 'B': return 'V';
+        case 'V': return 'B';
+        case 'D': return 'H';
+        default: return ch;
+      }
+    };
+    double transitions = 0, prevTrans = 0;
+    int transversions = 0, cpg = 0, wcb = 0;
+    char pS = 0;
+    for (int i = 0; i < len; i++) {
+      const int at = tc.strand ? len - 1 - i : i;
+      const char sb = tc.strand ? comp(srow[at]) : srow[at];
+      if (sb == '-') continue;
+      const char qb = tc.strand ? comp(qrow[at]) : qrow[at];
+      const int bq = base(qb), bs = base(sb);
+      const bool wc = bq >= 0 && bs >= 0;
+      wcb += wc;
+      const int mt = (!wc || bq == bs) ? 0 : ((bq >> 1) == (bs >> 1) ? 1 : 2);
+      if (pS == 'C' && sb == 'G') {
+        cpg++;
+        if (mt == 1)
+          prevTrans = __dadd_rn(prevTrans, 1.0);
+        else if (mt == 2)
+          transversions++;
+        if (prevTrans == 2)
+          prevTrans = 1;
+        else if (prevTrans == 1)
+          prevTrans = 1.0 / 10;
+      } else {
+        transitions = __dadd_rn(transitions, prevTrans);
+        prevTrans = 0;
+        if (mt == 1)
+          prevTrans = 1;
+        else if (mt == 2)
+          transversions++;
+      }
+      pS = sb;
+    }
+    transitions = __dadd_rn(transitions, prevTrans);
+    h.ktrans = transitions;
+    h.ktv = transversions;
+    h.wcb = wcb;
+    h.cpg = cpg;
+  }
+  a.out[tc.id] = h;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K5: what is decided over all hits of one query record, on the device so that only survivors cross PCIe.
+//   star_rank_kernel   one thread per hit against every hit of its query: the '*' flag (a strictly higher-scoring kept hit
+//                      overlaps the query domain, CrossmatchSearchEngine.pm:99-100) and the hit's rank by descending score
+//   masklevel_kernel   cross_match's masklevel (repeatmasker.help:714-728; fixtures seq1-2-ml{97,98}.out): one warp per
+//                      query walks its hits in rank order, equal scores as a group, against a bitmap of the query positions
+//                      covered by kept, strictly higher-scoring hits; a hit stays when at least (100 - masklevel) % of its
+//                      domain is uncovered
+// Query coordinates here are forward-strand (qs, qe), 1-based inclusive.
+// ---------------------------------------------------------------------------------------------------------------
+struct FinalizeArgs {
+  HitDev* hits;            // all candidates of the pass, grouped by query record
+  const int32_t* qFirst;   // [nQueries] first candidate of the query
+  const int32_t* qCount;   // [nQueries]
+  const int32_t* qlen;
+  int nQueries;
+  int masklevel;
+  int32_t* order;          // [nCand] candidates of a query by rank (only kept ones), at qFirst[q] + rank
+  int32_t* nKept;          // [nQueries]
+  uint32_t* cover;         // [coverOff[q] ...] one bit per query position
+  const int64_t* coverOff; // [nQueries] word offset of the query's bitmap
+};
+
+__device__ __forceinline__ void fwd_domain(const HitDev& h, int Q, int& qs, int& qe) {
+  if (!h.strand) {
+    qs = h.i0;
+    qe = h.i1;
+  } else {
+    qs = Q + 1 - h.i1;
+    qe = Q + 1 - h.i0;
+  }
+}
+
+__global__ void star_rank_kernel(FinalizeArgs a) {
+  const int q = blockIdx.y;
+  const int n = a.qCount[q], first = a.qFirst[q], Q = a.qlen[q];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_kept;
+  if (threadIdx.x == 0) s_kept = 0;
+  __syncthreads();
+  if (i < n) {
+    HitDev& me = a.hits[first + i];
+    if (me.flags & kHitKeep) {
+      int qs, qe;
+      fwd_domain(me, Q, qs, qe);
+      bool star = false;
+      int rank = 0;
+      for (int j = 0; j < n; j++) {
+        const HitDev& o = a.hits[first + j];
+        if (!(o.flags & kHitKeep)) continue;
+        int os, oe;
+        fwd_domain(o, Q, os, oe);
+        if (o.score > me.score) {
+          rank++;
+          star |= os <= qe && oe >= qs;
+        } else if (o.score == me.score && j < i)
+          rank++;
+      }
+      if (star) me.flags |= kHitStar;
+      a.order[first + rank] = i;
+      atomicAdd(&s_kept, 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_kept) atomicAdd(&a.nKept[q], s_kept);
+}
+
+__global__ void masklevel_kernel(FinalizeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= a.nQueries) return;
+  const int nk = a.nKept[q], first = a.qFirst[q], Q = a.qlen[q];
+  uint32_t* cov = a.cover + a.coverOff[q];
+  auto covered = [&](int qs, int qe) {  // covered positions of [qs, qe] (1-based); bit p-1 of the bitmap = position p
+    const int w0 = (qs - 1) >> 5, w1 = (qe - 1) >> 5;
+    int cnt = 0;
+    for (int w = w0 + lane; w <= w1; w += 32) {
+      uint32_t m = cov[w];
+      if (w == w0) m &= ~0u << ((qs - 1) & 31);
+      if (w == w1) m &= ~0u >> (31 - ((qe - 1) & 31));
+      cnt += __popc(m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    return cnt;
+  };
+  int g = 0;
+  while (g < nk) {
+    const int sc = a.hits[first + a.order[first + g]].score;
+    int ge = g;
+    while (ge < nk && a.hits[first + a.order[first + ge]].score == sc) ge++;
+    for (int k = g; k < ge; k++) {
+      HitDev& h = a.hits[first + a.order[first + k]];
+      int qs, qe;
+      fwd_domain(h, Q, qs, qe);
+      const long lenq = qe - qs + 1, unc = lenq - covered(qs, qe);
+      if (lane == 0 && unc * 100 < (long)(100 - a.masklevel) * lenq) h.flags |= kHitDrop;
+    }
+    __syncwarp();
+    for (int k = g; k < ge; k++) {
+      const HitDev& h = a.hits[first + a.order[first + k]];
+      if (h.flags & kHitDrop) continue;
+      int qs, qe;
+      fwd_domain(h, Q, qs, qe);
+      const int w0 = (qs - 1) >> 5, w1 = (qe - 1) >> 5;
+      for (int w = w0 + lane; w <= w1; w += 32) {
+        uint32_t m = ~0u;
+        if (w == w0) m &= ~0u << ((qs - 1) & 31);
+        if (w == w1) m &= ~0u >> (31 - ((qe - 1) & 31));
+        cov[w] |= m;
+      }
+      __syncwarp();
+    }
+    g = ge;
+  }
+}
+
+// Survivors' rows, packed: a single-block exclusive scan of the row bytes (2 * (len + 1) per surviving hit) followed by
+// one warp per hit copying its two rows.
+struct GatherArgs {
+  HitDev* hits;
+  int nCand;
+  const char* rows;
+  char* packed;
+  long long* total;  // bytes of the packed buffer
+};
+
+__global__ void __launch_bounds__(1024) scan_rows_kernel(GatherArgs a) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < a.nCand; base += 1024) {
+    const int i = base + threadIdx.x;
+    long long v = 0;
+    if (i < a.nCand) {
+      const HitDev& h = a.hits[i];
+      if ((h.flags & kHitKeep) && !(h.flags & kHitDrop)) v = 2ll * (h.len + 1);
+    }
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[wib] = x;
+    __syncthreads();
+    if (wib == 0) {
+      long long w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const long long before = s_carry + (wib ? s_warp[wib - 1] : 0) + x - v;
+    if (i < a.nCand && v) a.hits[i].outOff = before;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += s_warp[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *a.total = s_carry;
+}
+
+__global__ void gather_rows_kernel(GatherArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= a.nCand) return;
+  const HitDev h = a.hits[i];
+  if (h.outOff < 0) return;
+  const char* src = a.rows + h.rowOff;
+  char* dst = a.packed + h.outOff;
+  for (int k = lane; k < 2 * (h.len + 1); k += 32) dst[k] = src[k];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The two collection filters RepeatMasker applies after a search (RepeatMasker:2838-2987), query-domain flavour, with the
+// reference's own arithmetic:
+//   perl_masklevel_kernel   SearchResultCollection::maskLevelFilter (SearchResultCollection.pm:198-358): records sorted by
+//                           (name, score descending, query span ascending), stable; a record is deleted when SOME kept
+//                           record of the same name overlaps it and sprintf("%0.0f", 100 * outside / length) <= 100 -
+//                           masklevel (pairwise, not against the union; round-half-even like printf).  One warp per name:
+//                           the walk down the sorted list is sequential, the kept domains are checked 32 at a time.
+//   contained_kernel        SearchResultCollection::filterContainedResults (:379-470): records sorted by (name, start,
+//                           end descending); record j is deleted when an earlier record i of the same name has
+//                           start_j <= end_i, end_j < end_i and a strictly higher score (deleted records still delete:
+//                           the reference never checks record i).  No sequential dependence: one thread per record.
+// ---------------------------------------------------------------------------------------------------------------
+struct CollectionFilterArgs {
+  const int32_t* start;   // [n] 1-based inclusive, in collection order
+  const int32_t* end;
+  const int32_t* score;
+  const int32_t* order;   // [n] record numbers in the filter's sort order, grouped by name
+  const int32_t* gFirst;  // [nGroups] first position of the group in `order`
+  const int32_t* gCount;
+  int nGroups, n, masklevel;
+  int32_t* domains;       // [n] scratch: kept records of a group, at gFirst[g] + k
+  uint8_t* deleted;       // [n] out, by record number
+};
+
+__global__ void perl_masklevel_kernel(CollectionFilterArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= a.nGroups) return;
+  const int first = a.gFirst[g], cnt = a.gCount[g];
+  const double thr = (double)(100 - a.masklevel);
+  int nd = 0;
+  for (int k = 0; k < cnt; k++) {
+    const int rec = a.order[first + k];
+    const int b1 = a.start[rec], e1 = a.end[rec];
+    const double len = (double)(e1 - b1 + 1);
+    bool del = false;
+    for (int d = lane; d < nd; d += 32) {
+      const int dom = a.domains[first + d];
+      const int db = a.start[dom], de = a.end[dom];
+      if (db > e1 || de < b1) continue;
+      const int inter = min(e1, de) - max(b1, db) + 1;
+      const double pct = rint(__dmul_rn(__ddiv_rn((double)((e1 - b1 + 1) - inter), len), 100.0));
+      del |= pct <= thr;
+    }
+    del = __any_sync(0xffffffffu, del);
+    if (lane == 0) {
+      if (del)
+        a.deleted[rec] = 1;
+      else
+        a.domains[first + nd] = rec;
+    }
+    nd += del ? 0 : 1;
+    __syncwarp();
+  }
+}
+
+__global__ void contained_kernel(CollectionFilterArgs a) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;  // position in the sorted order
+  if (pos >= a.n) return;
+  // group of this position: gFirst is ascending
+  int lo = 0, hi = a.nGroups - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (a.gFirst[mid] <= pos)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const int first = a.gFirst[lo];
+  const int rec = a.order[pos];
+  const int b2 = a.start[rec], e2 = a.end[rec], s2 = a.score[rec];
+  bool del = false;
+  for (int i = first; i < pos && !del; i++) {
+    const int r1 = a.order[i];
+    del = b2 <= a.end[r1] && e2 < a.end[r1] && a.score[r1] > s2;
+  }
+  if (del) a.deleted[rec] = 1;
 }
 
 }  // namespace rmgpu

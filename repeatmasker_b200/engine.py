@@ -57,7 +57,7 @@ EXPORTS = ["rmgpu_version", "rmgpu_abi_version", "rmgpu_last_error", "rmgpu_sear
            "rmgpu_session_set_library_fasta", "rmgpu_session_set_queries", "rmgpu_session_set_queries_fasta",
            "rmgpu_session_search", "rmgpu_session_score_only", "rmgpu_session_counts", "rmgpu_measure_dpx_peak",
            "rmgpu_server_ping", "rmgpu_server_quit", "rmgpu_kimura_divergence", "rmgpu_matrix_info",
-           "rmgpu_adjusted_score"]
+           "rmgpu_adjusted_score", "rmgpu_masklevel_filter", "rmgpu_contained_filter"]
 
 
 def lib():
@@ -86,6 +86,9 @@ def lib():
     L.rmgpu_session_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)]
     L.rmgpu_measure_dpx_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    fargs = [C.c_int, C.c_int32] + [C.POINTER(C.c_int32)] * 4 + [C.c_int32, C.POINTER(C.c_uint8)]
+    L.rmgpu_masklevel_filter.argtypes = fargs
+    L.rmgpu_contained_filter.argtypes = fargs
     L.rmgpu_server_ping.argtypes = [C.c_char_p]
     L.rmgpu_server_quit.argtypes = [C.c_char_p]
     _lib = L
@@ -111,6 +114,18 @@ def _hits_to_dicts(res):
                         kimura=h.pct_kimura.decode(), cpg=h.cpg_sites))
     st = {k: getattr(r.stats, k) for k, _ in Stats._fields_}
     return out, st
+
+
+def collection_filter(names, starts, ends, scores, masklevel, contained=False, device=-1):
+    """rmgpu_masklevel_filter / rmgpu_contained_filter: the survivors' indices, in collection order."""
+    n = len(names)
+    ids = {}
+    nid = (C.c_int32 * n)(*[ids.setdefault(x, len(ids)) for x in names])
+    arr = lambda v: (C.c_int32 * n)(*v)
+    keep = (C.c_uint8 * n)()
+    fn = lib().rmgpu_contained_filter if contained else lib().rmgpu_masklevel_filter
+    _check(fn(device, n, nid, arr(starts), arr(ends), arr(scores), masklevel, keep))
+    return [i for i in range(n) if keep[i]]
 
 
 def kimura_divergence(qaln, saln, strand_c=False):

@@ -112,6 +112,18 @@ def fragment(seq, name, frag=60000, overlap=2000):
     return names, seqs
 
 
+def fragment_offsets(n, frag=60000, overlap=2000):
+    """0-based start of every fragment `fragment()` cuts a sequence of n bases into."""
+    if n <= frag:
+        return [0]
+    divisor = 2
+    while (n + (divisor - 1) * overlap) / divisor > frag:
+        divisor += 1
+    size = (n + (divisor - 1) * overlap) // divisor
+    last = size + (n + (divisor - 1) * overlap) % divisor
+    return [i * (size - overlap) for i in range(divisor - 1)] + [n - last]
+
+
 def write_fasta(path, names, seqs, width=50):
     with open(path, "w") as f:
         for n, s in zip(names, seqs):

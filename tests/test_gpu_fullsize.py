@@ -127,6 +127,52 @@ def test_full_size_sharded_equals_single_batch(config2):
     c["s"].set_queries(c["qs"], c["qn"])
 
 
+@pytest.mark.parametrize("frag", [0, 8, 17])
+def test_full_size_fragment_equals_oracle_hit_for_hit(config2, tmp_path, frag):
+    """Whole fragments of configuration 2 (57 kbp x all 500 families x both strands, 6.7e10 cells each) against the oracle
+    run on every host core: every hit line, alignment row, '*' flag and the output order.  A hit the score pass or the
+    hot-block mask dropped would show up here as a missing line."""
+    from repeatmasker_b200 import sharding
+    from test_gpu_parity import assert_same_hits
+
+    c = config2
+    q = str(tmp_path / "q.fa")
+    synth.write_fasta(q, [c["qn"][frag]], [c["qs"][frag]])
+    want = util.run_oracle_parallel(q, c["snames"], c["sseqs"], c["m"], str(tmp_path), gap_init=-30, ins_gap_ext=-6,
+                                    del_gap_ext=-5, minscore=225)
+    got = sharding.split_hits_by_fragment(c["hits"], c["qn"])[frag]
+    assert len(want) > 20
+    assert_same_hits(got, want)
+
+
+def test_full_size_recall_of_implanted_copies(config2):
+    """The generator's own record of what it planted (`truth`: position, length, family, strand, divergence) against the
+    hits: every intact copy (not overwritten by a later one) of >= 200 bases and <= 25 % divergence must be found with
+    its family and strand over at least half of its length; >= 90 % of all intact copies of >= 150 bases."""
+    c = config2
+    truth = c["truth"]
+    offs = synth.fragment_offsets(1_000_000)
+    assert len(offs) == len(c["qn"])
+    off = dict(zip(c["qn"], offs))
+    by = {}
+    for h in c["hits"]:
+        by.setdefault((h["sname"], h["strand"]), []).append((off[h["qname"]] + h["qstart"], off[h["qname"]] + h["qend"]))
+    ends = sorted((p, p + l) for p, l, *_ in truth)
+    strong = strong_found = weak = weak_found = 0
+    for i, (pos, ln, fam, strand, div) in enumerate(truth):
+        if ln < 150 or any(tp < pos + ln and tp + tl > pos for tp, tl, *_ in truth[i + 1:]):
+            continue
+        ivs = by.get((c["snames"][fam], "C" if strand else "+"), [])
+        ok = any(min(b, pos + ln) - max(a, pos + 1) + 1 >= 0.5 * ln for a, b in ivs)
+        weak += 1
+        weak_found += ok
+        if ln >= 200 and div <= 0.25:
+            strong += 1
+            strong_found += ok
+    assert strong > 200 and strong_found == strong, (strong_found, strong)
+    assert weak_found >= 0.9 * weak, (weak_found, weak)
+
+
 def test_many_family_library_against_oracle(tmp_path):
     """Configuration 5 in miniature: thousands of short families plus a few long ones, many small query records
     (several ticket-order groups, many fillers per stripe)."""

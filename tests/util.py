@@ -195,3 +195,32 @@ def driver_outputs(workdir, query="genome.fa", exts=("out", "masked", "cat", "tb
 def strip_engine_trailer(text):
     """.cat / .tbl name the engine and its version ("run with ..."); everything else must be identical."""
     return None if text is None else "\n".join(l for l in text.splitlines() if not l.startswith("run with "))
+
+
+def run_oracle_parallel(query, snames, sseqs, matrix, workdir, procs=None, **kw):
+    """The oracle over a whole library on several processes: the subjects are dealt round-robin to `procs` oracle
+    processes (each sees the one query file), the hit lists are merged into the specified output order and the '*' flags
+    (which depend on every hit of the query) are recomputed.  masklevel 101 only; one query record."""
+    from repeatmasker_b200 import synth
+
+    assert kw.get("masklevel", 101) >= 101
+    procs = procs or os.cpu_count() or 1
+    procs = max(1, min(procs, len(snames)))
+    # longest subjects first, dealt round-robin: even work per process
+    order = sorted(range(len(snames)), key=lambda i: -len(sseqs[i]))
+    running = []
+    for t in range(procs):
+        sub = sorted(order[t::procs])
+        sp = os.path.join(workdir, f"ora_part{t}.fa")
+        synth.write_fasta(sp, [snames[i] for i in sub], [sseqs[i] for i in sub])
+        running.append(subprocess.Popen(oracle_argv(query, sp, matrix, **kw), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+    hits = []
+    for p in running:
+        out, _ = p.communicate()
+        assert p.returncode == 0
+        hits += parse_crossmatch(out)
+    sidx = {n: i for i, n in enumerate(snames)}
+    hits.sort(key=lambda h: (h["qstart"], -sidx[h["sname"]], h["sstart"], h["qend"], h["strand"] == "C", h["send"]))
+    for h in hits:
+        h["star"] = any(o["score"] > h["score"] and o["qstart"] <= h["qend"] and o["qend"] >= h["qstart"] for o in hits)
+    return hits
