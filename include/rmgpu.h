@@ -122,12 +122,19 @@ int rmgpu_session_set_library_fasta(rmgpu_session *s, const char *subject_fasta)
 int rmgpu_session_set_queries(rmgpu_session *s, int32_t n, const char *const *names, const char *const *seqs,
                               const int32_t *lens);
 int rmgpu_session_set_queries_fasta(rmgpu_session *s, const char *query_fasta);
+/* The batch files of several callers as ONE batch (what rmgpu_server does with the pending calls of RepeatMasker's forked
+ * children, RepeatMasker:1040-1180): records of file f are first_record[f] .. first_record[f+1]-1 of the batch
+ * (first_record holds n_files + 1 entries); rmgpu_hit::query_index tells the results apart. */
+int rmgpu_session_set_queries_fasta_multi(rmgpu_session *s, int32_t n_files, const char *const *files, int32_t *first_record);
 /* Run the search on the resident batch x resident library. */
 int rmgpu_session_search(rmgpu_session *s, const rmgpu_params *p, rmgpu_result **out);
 /* K1 only, on resident data: best raw Smith-Waterman-Gotoh score per (query, subject, strand).
  * best must hold n_queries*n_subjects*2 int32 (strand fastest).  Used by tests and by bench.py's kernel-only leg;
  * returns the kernel time in *ms (CUDA events). */
 int rmgpu_session_score_only(rmgpu_session *s, const rmgpu_params *p, int32_t *best, double *ms);
+/* Bytes set_library copied to the device (row codes in 16-row groups, 1 B/base codes for K2-K4, group / stripe tables); the
+ * 8 B/row score profiles are built on the device. */
+int64_t rmgpu_session_library_h2d_bytes(const rmgpu_session *s);
 int rmgpu_session_counts(const rmgpu_session *s, int32_t *n_queries, int32_t *n_subjects, int64_t *query_bases,
                          int64_t *subject_bases);
 
@@ -135,12 +142,14 @@ int rmgpu_session_counts(const rmgpu_session *s, int32_t *n_queries, int32_t *n_
  * rmgpu_search() makes no CUDA call in the calling process: it sends the request to the server, which keeps one
  * session (matrix + packed library resident in HBM) per GPU.  This is what a forked, short-lived RepeatMasker batch child
  * (RepeatMasker:1043-1180) should use.  The two calls below are management helpers: 0 = server answered.            */
+int rmgpu_device_count(void); /* visible CUDA devices (0 and an error text when there is none); `rmgpu_server --gpus all` */
 int rmgpu_server_ping(const char *socket_path);
 int rmgpu_server_quit(const char *socket_path);
 
 /* ---- The two collection filters RepeatMasker runs on an engine's results (RepeatMasker:2838-2987), on the device, with
- * the reference's own arithmetic and tie order.  n records in collection order: an integer per distinct query name, 1-based
- * inclusive query coordinates, score.  keep[i] = 1 for the survivors; the order of the collection is not changed.
+ * the reference's own arithmetic and tie order.  n records in collection order: an integer per distinct query name that
+ * orders like the names do under perl's `cmp` (the contained filter's scan crosses name boundaries, as the reference's
+ * does), 1-based inclusive query coordinates, score.  keep[i] = 1 for the survivors; the order of the collection is not changed.
  *   rmgpu_masklevel_filter   SearchResultCollection::maskLevelFilter( value => masklevel )   SearchResultCollection.pm:198-358
  *                            (sort by name, score descending, span ascending; pairwise sprintf("%0.0f") test against every
  *                            kept domain; masklevel >= 101 keeps everything)

@@ -1459,11 +1459,24 @@ int rmgpu_session::query_capacity() const {
   const long long freeNow = freeAtOpen - (g_devbuf_bytes[device & 63].load() - devbufAtOpen);
   const size_t freeB = (size_t)std::max<long long>(freeNow, 0);
   const double budget = 0.45 * (double)(freeB + d_ck.cap * sizeof(uint2) + d_bnd1.cap * 8);
-  const double perQuery = (double)kHotBlocks * nGroups * R * 8.0 + (double)nStripes * ((double)maxQ + 64.0) * 8.0;
-  const double byCk = (double)kCheckpointBudget / std::max((double)kHotBlocks * nGroups * R * 8.0, 1.0);
+  const double stride = (double)maxQ + 64.0;
+  const double ckPerQuery = (double)kHotBlocks * nGroups * R * 8.0;
+  // boundary ring: at most 15 tag generations per launch (run_score), i.e. nQ * nStripes / 14 slots, and never fewer than
+  // a few per resident warp and per chain of a ticket-order group
+  const double ringPerQuery = (double)nStripes / 14.0 * stride * 8.0;
+  const double ringFixed = 12.0 * (double)numSMs * 16.0 * stride * 8.0;
   // (query, strand, subject) triples are numbered in 24 bits by the origin pass
   const double byTriples = std::floor(((double)(1u << 24) - 1.0) / std::max(2.0 * (double)lib.seqs.size(), 1.0));
-  return (int)std::max(1.0, std::floor(std::min(std::min(budget / std::max(perQuery, 1.0), byCk), byTriples)));
+  const double withCk = std::min((budget - ringFixed) / std::max(ckPerQuery + ringPerQuery, 1.0), (double)kCheckpointBudget / std::max(ckPerQuery, 1.0));
+  double cap = withCk;
+  if (withCk < 8.0) {
+    // A library so large that K1's column checkpoints (1 KB per library row and query record) would leave only a few
+    // records per pass: plan without them.  run_score() then disables them (they do not fit the budget) and the origin
+    // pass sweeps the passing triples from column 0 (swg_origin_kernel), which at such a library is a few per cent of K1.
+    const double noCk = std::min(32.0, (budget - ringFixed) / std::max(ringPerQuery, 1.0));
+    cap = std::max(withCk, noCk);
+  }
+  return (int)std::max(1.0, std::floor(std::min(cap, byTriples)));
 }
 
 rmgpu_result* rmgpu_session::search(const rmgpu_params& p) {
@@ -1779,6 +1792,23 @@ int rmgpu_session_set_queries_fasta(rmgpu_session* s, const char* f) {
   });
 }
 
+int rmgpu_session_set_queries_fasta_multi(rmgpu_session* s, int32_t n_files, const char* const* files, int32_t* first_record) {
+  return guarded([&] {
+    CUDA_CHECK(cudaSetDevice(s->device));
+    SeqSet all;
+    for (int f = 0; f < n_files; f++) {
+      first_record[f] = (int32_t)all.seqs.size();
+      SeqSet one = SeqSet::from_fasta(files[f]);
+      for (size_t i = 0; i < one.seqs.size(); i++) {
+        all.names.push_back(std::move(one.names[i]));
+        all.seqs.push_back(std::move(one.seqs[i]));
+      }
+    }
+    first_record[n_files] = (int32_t)all.seqs.size();
+    s->set_queries(std::move(all));
+  });
+}
+
 int rmgpu_session_search(rmgpu_session* s, const rmgpu_params* p, rmgpu_result** out) {
   *out = nullptr;
   return guarded([&] {
@@ -1808,6 +1838,18 @@ int rmgpu_session_counts(const rmgpu_session* s, int32_t* nq, int32_t* ns, int64
   if (sb) *sb = s->lib.total_bases();
   return 0;
 }
+
+int rmgpu_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_last_error = std::string("no CUDA device: librmgpu has no CPU fallback (") + cudaGetErrorString(e) + ")";
+    return 0;
+  }
+  return n;
+}
+
+int64_t rmgpu_session_library_h2d_bytes(const rmgpu_session* s) { return s->h2d_bytes_library; }
 
 int rmgpu_search(const rmgpu_params* p, const char* query_fasta, const char* subject_fasta, const char* matrix_file,
                  rmgpu_result** out) {
@@ -1931,7 +1973,7 @@ static int collection_filter(int device, int32_t n, const int32_t* name_id, cons
     if (!contained)
       perl_masklevel_kernel<<<(a.nGroups + 3) / 4, 128, 0, st>>>(a);
     else
-      contained_kernel<<<(n + 255) / 256, 256, 0, st>>>(a);
+      contained_kernel<<<1, 32, 0, st>>>(a);
     CUDA_CHECK(cudaGetLastError());
     std::vector<uint8_t> del((size_t)n);
     CUDA_CHECK(cudaMemcpyAsync(del.data(), a.deleted, (size_t)n, cudaMemcpyDeviceToHost, st));

@@ -1873,9 +1873,11 @@ __global__ void gather_rows_kernel(GatherArgs a) {
 //                           masklevel (pairwise, not against the union; round-half-even like printf).  One warp per name:
 //                           the walk down the sorted list is sequential, the kept domains are checked 32 at a time.
 //   contained_kernel        SearchResultCollection::filterContainedResults (:379-470): records sorted by (name, start,
-//                           end descending); record j is deleted when an earlier record i of the same name has
-//                           start_j <= end_i, end_j < end_i and a strictly higher score (deleted records still delete:
-//                           the reference never checks record i).  No sequential dependence: one thread per record.
+//                           end descending); for every record i in that order the following records are scanned until
+//                           the first LIVE one that starts beyond end_i, and a scanned record is deleted when it ends
+//                           before end_i with a strictly lower score.  As in the reference the scan does not stop at
+//                           the end of a name (so the order of the names matters), deleted records are skipped without
+//                           ending the scan, and a deleted record i still deletes.
 // ---------------------------------------------------------------------------------------------------------------
 struct CollectionFilterArgs {
   const int32_t* start;   // [n] 1-based inclusive, in collection order
@@ -1922,26 +1924,32 @@ __global__ void perl_masklevel_kernel(CollectionFilterArgs a) {
 }
 
 __global__ void contained_kernel(CollectionFilterArgs a) {
-  const int pos = blockIdx.x * blockDim.x + threadIdx.x;  // position in the sorted order
-  if (pos >= a.n) return;
-  // group of this position: gFirst is ascending
-  int lo = 0, hi = a.nGroups - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (a.gFirst[mid] <= pos)
-      lo = mid;
-    else
-      hi = mid - 1;
-  }
-  const int first = a.gFirst[lo];
-  const int rec = a.order[pos];
-  const int b2 = a.start[rec], e2 = a.end[rec], s2 = a.score[rec];
-  bool del = false;
-  for (int i = first; i < pos && !del; i++) {
+  // One warp walks the whole sorted list (see the note above: the reference's inner loop runs across name boundaries).
+  // For record i the lanes look at 32 successors at a time: already deleted ones are skipped (they neither stop the scan
+  // nor are examined), the first live one that starts beyond end_i stops it, live ones before that are deleted when
+  // they end before end_i with a lower score.
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  for (int i = 0; i < a.n; i++) {
     const int r1 = a.order[i];
-    del = b2 <= a.end[r1] && e2 < a.end[r1] && a.score[r1] > s2;
+    const int e1 = a.end[r1], s1 = a.score[r1];
+    for (int j0 = i + 1; j0 < a.n; j0 += 32) {
+      const int j = j0 + lane;
+      bool live = false, stop = false, kill = false;
+      int r2 = 0;
+      if (j < a.n) {
+        r2 = a.order[j];
+        live = !a.deleted[r2];
+        stop = live && a.start[r2] > e1;
+        kill = live && !stop && a.end[r2] < e1 && s1 > a.score[r2];
+      }
+      const unsigned stops = __ballot_sync(0xffffffffu, stop);
+      const unsigned before = stops ? ((1u << (__ffs(stops) - 1)) - 1u) : 0xffffffffu;
+      if (kill && ((before >> lane) & 1u)) a.deleted[r2] = 1;
+      if (stops) break;
+    }
+    __syncwarp();
   }
-  if (del) a.deleted[rec] = 1;
 }
 
 }  // namespace rmgpu

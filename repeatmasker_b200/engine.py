@@ -57,7 +57,8 @@ EXPORTS = ["rmgpu_version", "rmgpu_abi_version", "rmgpu_last_error", "rmgpu_sear
            "rmgpu_session_set_library_fasta", "rmgpu_session_set_queries", "rmgpu_session_set_queries_fasta",
            "rmgpu_session_search", "rmgpu_session_score_only", "rmgpu_session_counts", "rmgpu_measure_dpx_peak",
            "rmgpu_server_ping", "rmgpu_server_quit", "rmgpu_kimura_divergence", "rmgpu_matrix_info",
-           "rmgpu_adjusted_score", "rmgpu_masklevel_filter", "rmgpu_contained_filter"]
+           "rmgpu_adjusted_score", "rmgpu_masklevel_filter", "rmgpu_contained_filter",
+           "rmgpu_session_library_h2d_bytes", "rmgpu_session_set_queries_fasta_multi", "rmgpu_device_count"]
 
 
 def lib():
@@ -85,6 +86,8 @@ def lib():
     L.rmgpu_session_score_only.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.rmgpu_session_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)]
+    L.rmgpu_session_library_h2d_bytes.argtypes = [C.c_void_p]
+    L.rmgpu_session_library_h2d_bytes.restype = C.c_int64
     L.rmgpu_measure_dpx_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     fargs = [C.c_int, C.c_int32] + [C.POINTER(C.c_int32)] * 4 + [C.c_int32, C.POINTER(C.c_uint8)]
     L.rmgpu_masklevel_filter.argtypes = fargs
@@ -119,8 +122,8 @@ def _hits_to_dicts(res):
 def collection_filter(names, starts, ends, scores, masklevel, contained=False, device=-1):
     """rmgpu_masklevel_filter / rmgpu_contained_filter: the survivors' indices, in collection order."""
     n = len(names)
-    ids = {}
-    nid = (C.c_int32 * n)(*[ids.setdefault(x, len(ids)) for x in names])
+    ids = {x: k for k, x in enumerate(sorted(set(names)))}  # ranks in string order, like perl's cmp
+    nid = (C.c_int32 * n)(*[ids[x] for x in names])
     arr = lambda v: (C.c_int32 * n)(*v)
     keep = (C.c_uint8 * n)()
     fn = lib().rmgpu_contained_filter if contained else lib().rmgpu_masklevel_filter
@@ -209,6 +212,9 @@ class Session:
         nq, ns, qb, sb = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
         lib().rmgpu_session_counts(self._h, C.byref(nq), C.byref(ns), C.byref(qb), C.byref(sb))
         return nq.value, ns.value, qb.value, sb.value
+
+    def library_h2d_bytes(self):
+        return lib().rmgpu_session_library_h2d_bytes(self._h)
 
     def search(self, params):
         res = C.POINTER(Result)()

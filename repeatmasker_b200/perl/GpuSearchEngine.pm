@@ -72,6 +72,7 @@ sub new {
   my $path = delete $nameValuePairs{'pathToEngine'};
   $path = _defaultLibraryPath() if ( !defined $path || $path eq "" );
   $this->setPathToEngine( $path );
+  _ensureServer( $path );
 
   if ( %nameValuePairs ) {
     while ( my ( $name, $value ) = each( %nameValuePairs ) ) {
@@ -88,6 +89,54 @@ sub new {
 sub _defaultLibraryPath {
   my $dir = dirname( $INC{'GpuSearchEngine.pm'} || __FILE__ );
   return "$dir/../librmgpu.so";
+}
+
+##---------------------------------------------------------------------------##
+## The persistent GPU worker.  RepeatMasker builds ONE engine object in the
+## parent (RepeatMasker:602) and forks a short-lived child per batch
+## (RepeatMasker:1040-1180); a CUDA context cannot cross fork, and a context
+## plus a packed library per child would cost more than the searches.  So the
+## constructor -- still without any CUDA call in this process -- starts
+## rmgpu_server (all visible GPUs, library resident, pending calls of the
+## children coalesced into one pass per GPU) unless RMGPU_SERVER already names
+## one, and exports its socket to the children through the environment.  The
+## process that started it stops it when it exits.  RMGPU_NO_SERVER=1 keeps the
+## in-process path (one CUDA context per search() call).
+##---------------------------------------------------------------------------##
+my ( $serverPid, $serverOwner, $serverSocket );
+
+sub _ensureServer {
+  my $libPath = shift;
+  return if ( defined $ENV{'RMGPU_SERVER'} && $ENV{'RMGPU_SERVER'} ne "" );
+  return if ( $ENV{'RMGPU_NO_SERVER'} );
+  my $bin = dirname( $libPath ) . "/rmgpu_server";
+  return unless ( -x $bin );
+  my $sock = ( $ENV{'TMPDIR'} || "/tmp" ) . "/rmgpu.$$.sock";
+  my $gpus = defined $ENV{'RMGPU_GPUS'} ? $ENV{'RMGPU_GPUS'} : "all";
+  my $pid  = fork();
+  return unless ( defined $pid );
+  if ( $pid == 0 ) {
+    open( STDERR, ">", "/dev/null" ) unless ( $ENV{'RMGPU_SERVER_LOG'} );
+    exec( $bin, "--socket", $sock, "--gpus", $gpus ) or exit( 1 );
+  }
+  for ( my $i = 0 ; $i < 400 ; $i++ ) {
+    last if ( -S $sock && RMGpu::server_ping( $sock ) == 0 );
+    if ( waitpid( $pid, 1 ) == $pid ) {    # WNOHANG: the worker died (no GPU): keep the in-process path, which reports it
+      return;
+    }
+    select( undef, undef, undef, 0.025 );
+  }
+  $ENV{'RMGPU_SERVER'} = $sock;
+  ( $serverPid, $serverOwner, $serverSocket ) = ( $pid, $$, $sock );
+}
+
+END {
+  if ( defined $serverPid && $$ == $serverOwner ) {
+    my $status = $?;
+    RMGpu::server_quit( $serverSocket );
+    waitpid( $serverPid, 0 );
+    $? = $status;
+  }
 }
 
 sub setPathToEngine {

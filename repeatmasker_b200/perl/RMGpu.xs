@@ -21,6 +21,22 @@ version()
   OUTPUT:
     RETVAL
 
+int
+server_ping(socket_path)
+    const char *socket_path
+  CODE:
+    RETVAL = rmgpu_server_ping(socket_path);
+  OUTPUT:
+    RETVAL
+
+int
+server_quit(socket_path)
+    const char *socket_path
+  CODE:
+    RETVAL = rmgpu_server_quit(socket_path);
+  OUTPUT:
+    RETVAL
+
 void
 search(query, subject, matrix, gap_init, ins_gap_ext, del_gap_ext, minscore, masklevel, minmatch, bandwidth, raw, word_raw, alignments, device)
     const char *query

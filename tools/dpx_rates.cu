@@ -410,6 +410,57 @@ __global__ void cellLp(uint32_t* out, int iters, uint32_t seed, uint32_t gi2, ui
   out[blockIdx.x * blockDim.x + threadIdx.x] = best;
 }
 
+// S: round-1 recurrence with the score looked up in shared memory instead of PRMT: a table of packed (forward, reverse)
+// scores per (subject residue, query class pair), replicated per lane (entry stride 128 B: bank = lane, no conflicts);
+// address = row term (fixed per row and ticket) + column term (changes per column).  IMADADDR: the address add as an IMAD
+// (fmaheavy pipe) instead of an IADD3.
+template <int R, bool IMADADDR>
+__global__ void cellS(uint32_t* out, int iters, uint32_t seed, uint32_t gi2, uint32_t ie2, uint32_t de2, uint32_t one) {
+  extern __shared__ uint32_t s_tab[];  // [5 residues * 50 pairs][32 lanes]
+  for (int i = threadIdx.x; i < 5 * 50 * 32; i += blockDim.x) s_tab[i] = 0x00090009u + (uint32_t)(i % 7) * 0x00010001u - ((i % 3) ? 0x00140014u : 0u);
+  __syncthreads();
+  uint32_t rowterm[R], H[R], E[R];
+  const uint32_t lane4 = (threadIdx.x & 31) * 4;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    rowterm[r] = (uint32_t)((r * 7 + threadIdx.x) % 5) * 50u * 128u;
+    H[r] = 0;
+    E[r] = 0;
+  }
+  uint32_t best = 0, pair = seed % 49, diag = 0, hu = 0, f = 0;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(s_tab);
+  for (int it = 0; it < iters; it++) {
+    uint32_t hd = diag;
+    diag = hu;
+    pair = (pair * 5 + 3) % 49;
+    const uint32_t coloff = base + pair * 128u + lane4;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      uint32_t s;
+      if (IMADADDR) {
+        uint32_t addr = rowterm[r] * one + coloff;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(s) : "r"(addr));
+      } else {
+        s = s_tab[(rowterm[r] + coloff - base) >> 2];  // plain C load: the compiler picks the address arithmetic
+      }
+      uint32_t hl = H[r];
+      E[r] = __viaddmax_s16x2(E[r], ie2, hl);
+      uint32_t d = __vadd2(hd, s);
+      uint32_t tt = __viaddmax_s16x2_relu(E[r], gi2, d);
+      uint32_t h = __viaddmax_s16x2(f, gi2, tt);
+      f = __viaddmax_s16x2(f, de2, tt);
+      hd = hl;
+      H[r] = h;
+      hu = h;
+    }
+    if ((it & 7) == 7) {
+#pragma unroll
+      for (int r = 0; r < R; r++) best = __vmaxs2(best, E[r]);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = best;
+}
+
 // B: biased cell.  A = H + G, B = E + 2G, C = F + 2G (G = -gap_init), profile scores s' = s + G >= 0:
 //   B  = max(B + ie, A_left)              VIADDMNMX
 //   X  = A_diag + s'                      IMAD (no carry between halves: both operands >= 0)
@@ -599,6 +650,9 @@ int main(int argc, char** argv) {
     RUN("cell Lp (VIMNMX3 forced)", 12, (cellLp<12><<<blocks, threads>>>(d, iters, rep, gi2, ie2, de2, 1u)));
     RUN("cell L (VIMNMX3, long chain)", 8, (cellL<8><<<blocks, threads>>>(d, iters, rep, gi2, ie2, de2)));
     RUN("cell L (VIMNMX3, long chain)", 12, (cellL<12><<<blocks, threads>>>(d, iters, rep, gi2, ie2, de2)));
+    RUN("cell S (LDS scores, IADD address)", 16, (cellS<16, false><<<blocks, threads, 32000>>>(d, iters, rep, gi2, ie2, de2, 1u)));
+    RUN("cell S (LDS scores, IMAD address)", 16, (cellS<16, true><<<blocks, threads, 32000>>>(d, iters, rep, gi2, ie2, de2, 1u)));
+    RUN("cell S (LDS scores, IADD address)", 12, (cellS<12, false><<<blocks, threads, 32000>>>(d, iters, rep, gi2, ie2, de2, 1u)));
     RUN("cell B (biased, short chain)", 8, (cellB<8><<<blocks, threads>>>(d, iters, rep, gi2, ie2, de2, twoG2, 1u)));
     RUN("cell B (biased, short chain)", 16, (cellB<16><<<blocks, threads>>>(d, iters, rep, gi2, ie2, de2, twoG2, 1u)));
     RUN("cell C (biased, long chain)", 8, (cellC<8><<<blocks, threads>>>(d, iters, rep, gi2, ie2, de2, twoG2, 1u)));

@@ -24,10 +24,8 @@ our %preProcData = ();
 PM
 printf '#!/bin/sh\nexit 0\n' > "$DST/bin/trf"
 chmod +x "$DST/bin/trf"
-# the oracle, under the name the driver looks for
+# the oracle, under the name the driver looks for: CROSSMATCH_DIR points at oracle/_build itself (never a stale copy)
 make -C "$ROOT/oracle" >/dev/null
-mkdir -p "$DST/crossmatch"
-cp "$ROOT/oracle/_build/cross_match" "$DST/crossmatch/cross_match"
 # ---- the two driver edits that add "-engine gpu"  ----
 python3 - "$RM/RepeatMasker" <<'PY'
 import sys
@@ -51,7 +49,7 @@ cat > "$DST/env.sh" <<ENV
 # source this: configuration of the harness through the driver's own environment overrides.
 # HARNESS_ROOT is resolved at source time so the tree can live at another path on the GPU box.
 HARNESS_ROOT="\$(cd "\$(dirname "\${BASH_SOURCE[0]}")/../.." && pwd)"
-export CROSSMATCH_DIR="\$HARNESS_ROOT/baseline/_ref/crossmatch"
+export CROSSMATCH_DIR="\$HARNESS_ROOT/oracle/_build"
 export TRF_PRGM="\$HARNESS_ROOT/baseline/_ref/bin/trf"
 export LIBDIR="\$HARNESS_ROOT/baseline/_ref/libdir"
 export PERL5LIB="\$HARNESS_ROOT/baseline/_ref/libdir:\$HARNESS_ROOT/repeatmasker_b200/perl:\$PERL5LIB"
