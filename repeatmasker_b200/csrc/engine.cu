@@ -172,11 +172,26 @@ struct rmgpu_session {
   bool ckEnabled = false;
   DevBuf<uint8_t> d_rowcode, d_gflags, d_sflags, d_scodes;
   DevBuf<uint2> d_prof;
-  DevBuf<int32_t> d_gsubject, d_slen, d_order, d_prodPos, d_consPos;
+  DevBuf<int32_t> d_gsubject, d_slen;
   std::vector<uint8_t> h_sflags;
-  int orderGroup = 0;   // max position distance between a stripe and the stripe below it in the ticket order
-  int orderForNQ = -1;  // batch size the order was built for
-  void build_order(int nQ, int warps);
+  // One K1 launch in flight: its ticket order (depends on the number of query records), boundary ring and counters.  Two
+  // slots: search_batch() cuts a batch in two sub-batches whose score passes are both queued at once, and works on the first
+  // one's origin pass / traceback / rows while the second one's score pass has the integer pipes.
+  struct ScoreSlot {
+    DevBuf<int32_t> d_order, d_prodPos, d_consPos;
+    int orderGroup = 0;   // max position distance between a stripe and the stripe below it in the ticket order
+    int orderForNQ = -1;  // batch size the order was built for
+    DevBuf<unsigned long long> d_bnd, d_dbg;
+    DevBuf<int> d_finished, d_ticket, d_abort;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    int q0 = 0, nQ = 0, grid = 0, nslot = 0;
+    bool dbg = false;
+  } slot[2];
+  void build_order(ScoreSlot& sl, int nQ, int warps);
+  void launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, int nQ, bool exact, bool quota);
+  void collect_score(ScoreSlot& sl, std::vector<int32_t>& pairbest, std::vector<unsigned long long>& hotmask);
+  void prepare_score(const rmgpu_params& p, bool exact);
   DevBuf<int64_t> d_soff;
   std::vector<int64_t> h_soff;
   bool profileValid = false;
@@ -203,7 +218,7 @@ struct rmgpu_session {
 
   // ---- scratch
   DevBuf<int32_t> d_pairbest;
-  DevBuf<unsigned long long> d_bnd1, d_hotmask;
+  DevBuf<unsigned long long> d_hotmask;
   DevBuf<int32_t> d_hotShift;
   DevBuf<unsigned long long> d_dbg;
   DevBuf<int> d_abort, d_leftFlag;
@@ -236,11 +251,11 @@ struct rmgpu_session {
   void set_queries(SeqSet s);
   void build_classes_and_profile();
   void run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest, std::vector<unsigned long long>& hotmask,
-                 double& ms, int& launches, bool exact);
+                 double& ms, int& launches, bool exact);  // the whole batch in one launch, waited for
   int ovfThresh = 32000;  // K1 reports 32767 for any best at or above this
   int scoreSlack = 0;  // how much below the true best the sampled K1 best can be (0 in exact mode)
-  void run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest,
-                  const std::vector<unsigned long long>& hotmask, std::vector<Candidate>& cands, rmgpu_stats& st);
+  void run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest, const std::vector<unsigned long long>& hotmask,
+                  int q0, int q1, std::vector<Candidate>& cands, rmgpu_stats& st);  // query records [q0, q1)
   void run_traceback(const rmgpu_params& p, const std::vector<Candidate>& cands, rmgpu_stats& st);
   void run_finalize(const rmgpu_params& p, const std::vector<Candidate>& cands, std::vector<HitDev>& hits,
                     std::vector<char>& rows, rmgpu_stats& st);
@@ -335,7 +350,7 @@ void rmgpu_session::set_library(SeqSet s) {
     }
   }
   h_sflags = sflags;
-  orderForNQ = -1;
+  slot[0].orderForNQ = slot[1].orderForNQ = -1;
   // unpacked subject codes for K2 / K3
   h_soff.assign(n + 1, 0);
   std::vector<int32_t> slen(n);
@@ -510,8 +525,8 @@ static uint32_t pack2(int v) { return ((uint32_t)(uint16_t)(int16_t)v) | ((uint3
 // a few times more tickets than there are resident warps, a consumer stripe is claimed long after its producer
 // finished (no polling in steady state), while the producer->consumer distance stays bounded by the group size,
 // which bounds the boundary ring.
-void rmgpu_session::build_order(int nQ, int warps) {
-  if (orderForNQ == nQ) return;
+void rmgpu_session::build_order(ScoreSlot& sl, int nQ, int warps) {
+  if (sl.orderForNQ == nQ) return;
   struct Chain {
     int first, len;
   };
@@ -529,14 +544,14 @@ void rmgpu_session::build_order(int nQ, int warps) {
   std::vector<std::vector<Chain>> grp(nGroupsT);
   for (size_t c = 0; c < chains.size(); c++) grp[c % nGroupsT].push_back(chains[c]);
   std::vector<int32_t> order, posOf(nStripes, -1);
-  orderGroup = 0;
+  sl.orderGroup = 0;
   for (auto& gchains : grp) {
     int tot = 0, maxLen = 0;
     for (auto& c : gchains) {
       tot += c.len;
       maxLen = std::max(maxLen, c.len);
     }
-    orderGroup = std::max(orderGroup, tot);
+    sl.orderGroup = std::max(sl.orderGroup, tot);
     for (int level = 0; level < maxLen; level++)
       for (auto& c : gchains)
         if (level < c.len) {
@@ -550,13 +565,13 @@ void rmgpu_session::build_order(int nQ, int warps) {
     if (h_sflags[k] & 1) prodPos[pos] = posOf[k - 1];
     if (h_sflags[k] & 2) consPos[pos] = posOf[k + 1];
   }
-  d_order.upload(order, stream);
-  d_prodPos.upload(prodPos, stream);
-  d_consPos.upload(consPos, stream);
-  orderForNQ = nQ;
+  sl.d_order.upload(order, sl.stream);
+  sl.d_prodPos.upload(prodPos, sl.stream);
+  sl.d_consPos.upload(consPos, sl.stream);
+  sl.orderForNQ = nQ;
 }
 
-void rmgpu_session::check_abort(const char* what) { check_abort_on(what, d_abort.p, stream); }
+void rmgpu_session::check_abort(const char* what) { check_abort_on(what, d_abort.p, stream); }  // K2b
 
 void rmgpu_session::check_abort_on(const char* what, int* flag, cudaStream_t stq) {
   int f = 0;
@@ -566,37 +581,51 @@ void rmgpu_session::check_abort_on(const char* what, int* flag, cudaStream_t stq
 }
 
 // K1 over the resident batch x library.
-void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest,
-                              std::vector<unsigned long long>& hotmask, double& ms, int& launches, bool exact) {
+// prepare_score: what every launch of the batch shares (class map / streams / profile, thresholds, result and checkpoint
+// buffers); launch_score: one launch over the query records [q0, q0 + nQ) on the slot's own stream; collect_score: wait for
+// it and bring its best scores and hot masks to the host.
+void rmgpu_session::prepare_score(const rmgpu_params& p, bool exact) {
   const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
-  pairbest.assign((size_t)nQ * nS * 2, 0);
-  hotmask.assign((size_t)nQ * nS * 2 * kHotWords, 0);
-  ms = 0;
-  if (nQ == 0 || nS == 0) return;
   if (p.gap_init >= 0 || p.ins_gap_ext > 0 || p.del_gap_ext > 0 || p.gap_init < -20000)
     throw Error("gap penalties must be negative");
   prepare_streams();
   build_classes_and_profile();
+  scoreSlack = exact ? 0 : 7 * std::abs(p.ins_gap_ext);
+  // between two samples (8 columns) a score can rise by at most 8 * max matrix score
+  ovfThresh = 32767 - 9 * std::max(matrix.max_score(), 1) - scoreSlack;
+  if (ovfThresh < 16384) throw Error("matrix scores too large for the int16 score pass");
+  const size_t nPair = (size_t)nQ * nS * 2;
+  d_pairbest.ensure(std::max<size_t>(nPair, 1));
+  d_hotmask.ensure(std::max<size_t>(nPair * kHotWords, 1));
+  // column checkpoints for the origin pass (kHotBlocks per query): only when they fit the budget
+  static const bool noCk = getenv("RMGPU_NO_CHECKPOINTS") != nullptr;
+  const int64_t ckElems = (int64_t)nQ * kHotBlocks * nGroups * R;
+  ckEnabled = !noCk && ckElems * (int64_t)sizeof(uint2) <= kCheckpointBudget;
+  if (ckEnabled) d_ck.ensure((size_t)ckElems);
+  CUDA_CHECK(cudaMemsetAsync(d_pairbest.p, 0, nPair * sizeof(int32_t), stream));
+  CUDA_CHECK(cudaMemsetAsync(d_hotmask.p, 0, nPair * kHotWords * sizeof(unsigned long long), stream));
+  CUDA_CHECK(cudaStreamSynchronize(stream));  // K0 and the cleared buffers are in place before any slot's stream starts
+}
+
+void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, int nQ, bool exact, bool quota) {
+  const int nS = (int)lib.seqs.size();
   int blocksPerSM = 0;
   if (exact)
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R, true>, kScoreWarps * 32, 0));
   else
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R, false>, kScoreWarps * 32, 0));
-  scoreSlack = exact ? 0 : 7 * std::abs(p.ins_gap_ext);
-  // between two samples (8 columns) a score can rise by at most 8 * max matrix score
-  ovfThresh = 32767 - 9 * std::max(matrix.max_score(), 1) - scoreSlack;
-  if (ovfThresh < 16384) throw Error("matrix scores too large for the int16 score pass");
   if (blocksPerSM < 1) throw Error("K1 does not fit on an SM");
   const int64_t nTickets = (int64_t)nQ * nStripes;
   if (nTickets >= (1ll << 31)) throw Error("too many stripe tasks in one batch");
-  int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, (nTickets + kScoreWarps - 1) / kScoreWarps);
-  const int warps = grid * kScoreWarps;
-  build_order(nQ, warps);
+  const int resident = numSMs * blocksPerSM;
+  // ticket order and ring are sized for the warps that can run at once
+  const int warps = (int)std::min<int64_t>((int64_t)resident * kScoreWarps, nTickets);
+  build_order(sl, nQ, warps);
   // ring slots: a slot is rewritten nslot tickets later; its reader is at most orderGroup * nQ tickets after its writer
   // ... and a boundary's 4-bit tag (generation = ticket / nslot, 15 values) must be unique within a launch: a slot keeps
   // the boundary of its last WRITER, which may be many generations old when the tickets in between had no stripe below
   const int nslot = (int)std::min<int64_t>(
-      nTickets, std::max<int64_t>(std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)orderGroup * nQ + 2), nTickets / 14 + 1));
+      nTickets, std::max<int64_t>(std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)sl.orderGroup * nQ + 2), nTickets / 14 + 1));
   if ((nTickets + nslot - 1) / nslot > 15) throw Error("K1 boundary ring: more than 15 tag generations in one launch");
   const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
   ScoreArgs a;
@@ -604,75 +633,102 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   a.gflags = d_gflags.p;
   a.gsubject = d_gsubject.p;
   a.sflags = d_sflags.p;
-  a.order = d_order.p;
-  a.prodPos = d_prodPos.p;
-  a.consPos = d_consPos.p;
+  a.order = sl.d_order.p;
+  a.prodPos = sl.d_prodPos.p;
+  a.consPos = sl.d_consPos.p;
   a.sel = d_sel.p;
-  a.selOff = d_selOff.p;
-  a.qlen = d_qlen.p;
-  a.hotShift = d_hotShift.p;
+  a.selOff = d_selOff.p + q0;  // offsets into sel are absolute
+  a.qlen = d_qlen.p + q0;
+  a.hotShift = d_hotShift.p + q0;
   a.nQueries = nQ;
   a.nStripes = nStripes;
   a.nSubjects = nS;
-  a.pairbest = d_pairbest.ensure(pairbest.size());
-  a.hotmask = d_hotmask.ensure(hotmask.size());
-  a.bnd = d_bnd1.ensure((size_t)nslot * bndStride);
+  a.pairbest = d_pairbest.p + (size_t)q0 * nS * 2;
+  a.hotmask = d_hotmask.p + (size_t)q0 * nS * 2 * kHotWords;
+  a.bnd = sl.d_bnd.ensure((size_t)nslot * bndStride);
   a.bndStride = bndStride;
   a.nslot = nslot;
-  a.finished = d_finished.ensure((size_t)nTickets);
-  a.ticket = d_ticket.ensure(1);
+  a.finished = sl.d_finished.ensure((size_t)nTickets);
+  a.ticket = sl.d_ticket.ensure(1);
   a.gi2 = pack2(p.gap_init);
   a.ie2 = pack2(p.ins_gap_ext);
   a.df2 = pack2(std::max(p.del_gap_ext, p.gap_init));
   a.minscore = std::max(1, std::min(p.minscore, ovfThresh) - scoreSlack);
   a.ovfThresh = ovfThresh;
-  a.abort_flag = d_abort.ensure(1);
-  // column checkpoints for the origin pass (kHotBlocks per query): only when they fit the budget
-  {
-    static const bool noCk = getenv("RMGPU_NO_CHECKPOINTS") != nullptr;
-    const int64_t ckElems = (int64_t)nQ * kHotBlocks * nGroups * R;
-    ckEnabled = !noCk && ckElems * (int64_t)sizeof(uint2) <= kCheckpointBudget;
-    a.ck = ckEnabled ? d_ck.ensure((size_t)ckElems) : nullptr;
-    a.ckRows = (int64_t)nGroups * R;
-  }
-  CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream));
+  a.abort_flag = sl.d_abort.ensure(1);
+  a.ck = ckEnabled ? d_ck.p + (size_t)q0 * kHotBlocks * ((size_t)nGroups * R) : nullptr;
+  a.ckRows = (int64_t)nGroups * R;
   static const bool dbgOn = getenv("RMGPU_DEBUG_K1") != nullptr;
+  sl.dbg = dbgOn;
   a.dbg = nullptr;
   if (dbgOn) {
-    a.dbg = d_dbg.ensure(8);
-    CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 64, stream));
+    a.dbg = sl.d_dbg.ensure(8);
+    CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 64, sl.stream));
   }
-  CUDA_CHECK(cudaMemsetAsync(a.pairbest, 0, pairbest.size() * sizeof(int32_t), stream));
-  CUDA_CHECK(cudaMemsetAsync(a.hotmask, 0, hotmask.size() * sizeof(unsigned long long), stream));
-  CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream));
-  CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), stream));
-  EventTimer tm;
-  tm.start(stream);
+  // CTAs: with a quota more than fit at once, each warp taking `quota` tickets; else one persistent wave
+  int grid;
+  a.quota = 0;
+  if (quota && nTickets > 2ll * resident * kScoreWarps) {
+    a.quota = 2;
+    grid = (int)((nTickets + (int64_t)kScoreWarps * a.quota - 1) / ((int64_t)kScoreWarps * a.quota));
+  } else
+    grid = (int)std::min<int64_t>(resident, (nTickets + kScoreWarps - 1) / kScoreWarps);
+  sl.q0 = q0;
+  sl.nQ = nQ;
+  sl.grid = grid;
+  sl.nslot = nslot;
+  CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), sl.stream));
+  CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), sl.stream));
+  CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), sl.stream));
+  CUDA_CHECK(cudaEventRecord(sl.evStart, sl.stream));
   // tag 0 = "never written": the boundary ring must not hold tags of an earlier launch
-  CUDA_CHECK(cudaMemsetAsync(a.bnd, 0, (size_t)nslot * bndStride * sizeof(unsigned long long), stream));
+  CUDA_CHECK(cudaMemsetAsync(a.bnd, 0, (size_t)nslot * bndStride * sizeof(unsigned long long), sl.stream));
   if (exact)
-    swg_score_kernel<R, true><<<grid, kScoreWarps * 32, 0, stream>>>(a);
+    swg_score_kernel<R, true><<<grid, kScoreWarps * 32, 0, sl.stream>>>(a);
   else
-    swg_score_kernel<R, false><<<grid, kScoreWarps * 32, 0, stream>>>(a);
-  tm.stop(stream);
+    swg_score_kernel<R, false><<<grid, kScoreWarps * 32, 0, sl.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaMemcpyAsync(pairbest.data(), a.pairbest, pairbest.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  CUDA_CHECK(cudaMemcpyAsync(hotmask.data(), a.hotmask, hotmask.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-  CUDA_CHECK(cudaStreamSynchronize(stream));
-  check_abort("K1");
-  ms = tm.ms();
-  launches += 2;
-  if (dbgOn) {
+  CUDA_CHECK(cudaEventRecord(sl.evStop, sl.stream));
+}
+
+void rmgpu_session::collect_score(ScoreSlot& sl, std::vector<int32_t>& pairbest, std::vector<unsigned long long>& hotmask) {
+  const int nS = (int)lib.seqs.size();
+  const size_t off = (size_t)sl.q0 * nS * 2, n = (size_t)sl.nQ * nS * 2;
+  CUDA_CHECK(cudaMemcpyAsync(pairbest.data() + off, d_pairbest.p + off, n * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+  CUDA_CHECK(cudaMemcpyAsync(hotmask.data() + off * kHotWords, d_hotmask.p + off * kHotWords, n * kHotWords * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, sl.stream));
+  CUDA_CHECK(cudaStreamSynchronize(sl.stream));
+  check_abort_on("K1", sl.d_abort.p, sl.stream);
+  if (sl.dbg) {
     unsigned long long d[8];
-    CUDA_CHECK(cudaMemcpy(d, a.dbg, 64, cudaMemcpyDeviceToHost));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, sl.evStart, sl.evStop);
+    CUDA_CHECK(cudaMemcpy(d, sl.d_dbg.p, 64, cudaMemcpyDeviceToHost));
     int64_t rows = 0;
     for (auto& sq : lib.seqs) rows += (int64_t)sq.size();
-    fprintf(stderr, "[K1 dbg] tasks %llu  producer-wait %.1f%% of task cycles  slot-wait %.2e cyc  mean task %.0f cyc  grid %d nslot %d\n", d[2],
-            100.0 * (double)d[0] / (double)std::max(d[3], 1ull), (double)d[1], (double)d[3] / (double)std::max(d[2], 1ull), grid, nslot);
-    fprintf(stderr, "[K1 dbg] stripes %d  padded rows %.2f%%  warp busy until exit: mean %.1f%% of the last warp's (%.2f ms)  kernel %.2f ms\n", nStripes,
+    const int warps = sl.grid * kScoreWarps;
+    fprintf(stderr, "[K1 dbg] records %d..%d tasks %llu  producer-wait %.1f%% of task cycles  slot-wait %.2e cyc  mean task %.0f cyc  grid %d nslot %d\n", sl.q0,
+            sl.q0 + sl.nQ - 1, d[2], 100.0 * (double)d[0] / (double)std::max(d[3], 1ull), (double)d[1], (double)d[3] / (double)std::max(d[2], 1ull), sl.grid, sl.nslot);
+    fprintf(stderr, "[K1 dbg] stripes %d  padded rows %.2f%%  warp busy until exit: mean %.1f%% of the last warp's (%.2f ms)  launch %.2f ms\n", nStripes,
             100.0 * ((double)nStripes * 32 * R - (double)rows) / (double)std::max<int64_t>(rows, 1),
             100.0 * (double)d[4] / ((double)warps * (double)std::max(d[5], 1ull)), (double)d[5] * 1e-6, ms);
   }
+}
+
+void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest,
+                              std::vector<unsigned long long>& hotmask, double& ms, int& launches, bool exact) {
+  const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
+  pairbest.assign((size_t)nQ * nS * 2, 0);
+  hotmask.assign((size_t)nQ * nS * 2 * kHotWords, 0);
+  ms = 0;
+  if (nQ == 0 || nS == 0) return;
+  prepare_score(p, exact);
+  launch_score(p, slot[0], 0, nQ, exact, /*quota=*/false);
+  collect_score(slot[0], pairbest, hotmask);
+  float f = 0;
+  cudaEventElapsedTime(&f, slot[0].evStart, slot[0].evStop);
+  ms = f;
+  launches += 2;
 }
 
 // K2 over every (query, strand, subject) triple whose K1 best reached minscore.
@@ -683,9 +739,9 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
 //                too large for the 31-bit relative origin or hold merged residue classes, or when checkpoints are
 //                disabled (those from column 0); runs concurrently on a second stream.
 void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>& pairbest,
-                               const std::vector<unsigned long long>& hotmask, std::vector<Candidate>& cands,
+                               const std::vector<unsigned long long>& hotmask, int q0, int q1, std::vector<Candidate>& cands,
                                rmgpu_stats& st) {
-  const int nQ = (int)queries.seqs.size(), nS = (int)lib.seqs.size();
+  const int nS = (int)lib.seqs.size();
   static const bool fullMode = getenv("RMGPU_K2_FULL") != nullptr;
   struct Triple {
     int q, strand, subject;
@@ -693,7 +749,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     bool chain;
   };
   std::vector<Triple> triples;
-  for (int q = 0; q < nQ; q++)
+  for (int q = q0; q < q1; q++)
     for (int s = 0; s < nS; s++)
       for (int strand = 0; strand < 2; strand++) {
         const size_t idx = ((size_t)q * nS + s) * 2 + strand;
@@ -714,7 +770,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
                   (CB + 2) * (L + 1) >= (1ll << 31);
         triples.push_back(t);
       }
-  st.n_pairs_passed = (int)triples.size();
+  st.n_pairs_passed += (int)triples.size();
   cands.clear();
   if (triples.empty()) return;
   // the candidate tables carry the triple and the raw score in 24-bit fields (cand_val, resolve_candidates_kernel)
@@ -1186,7 +1242,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   st.d2h_bytes += chainD2H;
   st.n_origin_redo += chainRedo;
   st.origin_cells += chainCells;
-  st.ms_origin = now_ms() - k2t0;  // both paths overlap: wall time of the origin pass (kernels, table downloads, host merge)
+  st.ms_origin += now_ms() - k2t0;  // both paths overlap: wall time of the origin pass (kernels, table downloads, host merge)
   // one candidate per (triple, origin)
   std::sort(found.begin(), found.end(), [](const std::pair<int, Candidate>& x, const std::pair<int, Candidate>& y) {
     if (x.first != y.first) return x.first < y.first;
@@ -1209,7 +1265,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     if (x.i0 != y.i0) return x.i0 < y.i0;
     return x.j0 < y.j0;
   });
-  st.n_candidates = (int)cands.size();
+  st.n_candidates += (int)cands.size();
 }
 
 // K3 with the band schedule W = max(bandwidth,1) * 2^k until the banded score reproduces the raw score.  The edit
@@ -1458,7 +1514,7 @@ int rmgpu_session::query_capacity() const {
   // itself costs up to milliseconds per call)
   const long long freeNow = freeAtOpen - (g_devbuf_bytes[device & 63].load() - devbufAtOpen);
   const size_t freeB = (size_t)std::max<long long>(freeNow, 0);
-  const double budget = 0.45 * (double)(freeB + d_ck.cap * sizeof(uint2) + d_bnd1.cap * 8);
+  const double budget = 0.45 * (double)(freeB + d_ck.cap * sizeof(uint2) + (slot[0].d_bnd.cap + slot[1].d_bnd.cap) * 8);
   const double stride = (double)maxQ + 64.0;
   const double ckPerQuery = (double)kHotBlocks * nGroups * R * 8.0;
   // boundary ring: at most 15 tag generations per launch (run_score), i.e. nQ * nStripes / 14 slots, and never fewer than
@@ -1546,44 +1602,87 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
     st.cells = 2.0 * qb * sb;
   }
 
-  std::vector<int32_t> pairbest;
-  std::vector<unsigned long long> hotmask;
+  // The batch is cut in two sub-batches whose score passes are both queued at once (each on its own low-priority stream;
+  // the second one's CTAs take the SM slots the first one's retiring CTAs leave).  While the second score pass runs, the
+  // origin pass, traceback and rows of the first sub-batch are launched on high-priority streams: score-pass CTAs retire
+  // all along their launch (ScoreArgs::quota), so those kernels get slots next to it instead of waiting for its end.
+  struct Part {
+    int q0, q1;
+    std::vector<HitDev> dh;
+    std::vector<char> rows;
+    const char* rowBase = nullptr;
+  };
+  // Measured on the bench workload (profiles/r2_pipeline_experiment.txt): 267-279 ms per step with two sub-batches against
+  // 247 ms with one -- the origin pass and the traceback are latency-bound, so next to a score pass that owns every
+  // register of the SM they hold the slots they get four to five times longer, and the score pass loses more than they
+  // gain.  One sub-batch is therefore the default; RMGPU_PIPELINE=1 keeps the experiment reachable.
+  static const bool pipe = getenv("RMGPU_PIPELINE") != nullptr;
+  std::vector<Part> parts;
+  if (nQ >= 8 && pipe && nS > 0) {
+    parts.resize(2);
+    parts[0].q0 = 0;
+    parts[0].q1 = parts[1].q0 = (nQ + 1) / 2;
+    parts[1].q1 = nQ;
+  } else {
+    parts.resize(1);
+    parts[0].q0 = 0;
+    parts[0].q1 = nQ;
+  }
+  std::vector<int32_t> pairbest((size_t)nQ * nS * 2, 0);
+  std::vector<unsigned long long> hotmask((size_t)nQ * nS * 2 * kHotWords, 0);
   const double w0 = now_ms();
-  run_score(p, pairbest, hotmask, st.ms_score, st.launches, /*exact=*/false);
-  st.score_launches = 1;
-  st.d2h_bytes += (int64_t)pairbest.size() * 12;
-  const double w1 = now_ms();
-  std::vector<Candidate> cands;
-  run_origin(p, pairbest, hotmask, cands, st);
-  const double w2 = now_ms();
-  run_traceback(p, cands, st);
-  const double w3 = now_ms();
-  std::vector<HitDev> dh;
-  std::vector<char> rows;
-  run_finalize(p, cands, dh, rows, st);
+  double wOrigin = 0, wTrace = 0, wFinal = 0, msFinal = 0;
+  if (nQ > 0 && nS > 0) {
+    prepare_score(p, /*exact=*/false);
+    for (size_t k = 0; k < parts.size(); k++)
+      launch_score(p, slot[k], parts[k].q0, parts[k].q1 - parts[k].q0, /*exact=*/false, /*quota=*/parts.size() > 1);
+    st.launches += 2 * (int)parts.size();
+    st.score_launches = (int)parts.size();
+    st.d2h_bytes += (int64_t)pairbest.size() * 12;
+    for (size_t k = 0; k < parts.size(); k++) {
+      Part& P = parts[k];
+      collect_score(slot[k], pairbest, hotmask);
+      const double t1 = now_ms();
+      std::vector<Candidate> cands;
+      run_origin(p, pairbest, hotmask, P.q0, P.q1, cands, st);
+      const double t2 = now_ms();
+      run_traceback(p, cands, st);
+      const double t3 = now_ms();
+      run_finalize(p, cands, P.dh, P.rows, st);
+      wOrigin += t2 - t1;
+      wTrace += t3 - t2;
+      wFinal += now_ms() - t3;
+      msFinal += ms_finalize;
+    }
+    // the score pass as one span: first launch's start to last launch's end (the launches overlap)
+    float f = 0;
+    cudaEventElapsedTime(&f, slot[0].evStart, slot[parts.size() - 1].evStop);
+    st.ms_score = f;
+  }
   const double w4 = now_ms();
 
   // What is left for the host: the output order, the decimal text of three percentages and of the Kimura divergence
   // (one logarithm per hit), names and pointers.  No per-column work.
   const double t_post = now_ms();
   struct Key {
-    int idx, qstart, qend;
+    int part, idx, qstart, qend;
   };
   std::vector<Key> keep;
-  keep.reserve(dh.size());
-  for (size_t i = 0; i < dh.size(); i++) {
-    const HitDev& h = dh[i];
-    if (!(h.flags & kHitKeep) || (h.flags & kHitDrop)) continue;
-    const int Q = h_qlen[h.q];
-    Key k;
-    k.idx = (int)i;
-    k.qstart = h.strand ? Q + 1 - h.i1 : h.i0;
-    k.qend = h.strand ? Q + 1 - h.i0 : h.i1;
-    keep.push_back(k);
-  }
+  for (size_t pi = 0; pi < parts.size(); pi++)
+    for (size_t i = 0; i < parts[pi].dh.size(); i++) {
+      const HitDev& h = parts[pi].dh[i];
+      if (!(h.flags & kHitKeep) || (h.flags & kHitDrop)) continue;
+      const int Q = h_qlen[h.q];
+      Key k;
+      k.part = (int)pi;
+      k.idx = (int)i;
+      k.qstart = h.strand ? Q + 1 - h.i1 : h.i0;
+      k.qend = h.strand ? Q + 1 - h.i0 : h.i1;
+      keep.push_back(k);
+    }
   // output order: query order, ascending query start, DESCENDING subject order, then subject start, query end, strand
   std::sort(keep.begin(), keep.end(), [&](const Key& x, const Key& y) {
-    const HitDev &a = dh[x.idx], &b = dh[y.idx];
+    const HitDev &a = parts[x.part].dh[x.idx], &b = parts[y.part].dh[y.idx];
     if (a.q != b.q) return a.q < b.q;
     if (x.qstart != y.qstart) return x.qstart < y.qstart;
     if (a.subject != b.subject) return a.subject > b.subject;
@@ -1596,10 +1695,11 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
   res->opaque = arena;
   res->n_hits = (int32_t)keep.size();
   res->hits = keep.empty() ? nullptr : new rmgpu_hit[keep.size()];
-  const char* rowBase = arena->keep_buffer(std::move(rows));
+  for (auto& P : parts) P.rowBase = arena->keep_buffer(std::move(P.rows));
   std::vector<const char*> qn(nQ, nullptr), sn(nS, nullptr);
   for (size_t k = 0; k < keep.size(); k++) {
-    const HitDev& h = dh[keep[k].idx];
+    const HitDev& h = parts[keep[k].part].dh[keep[k].idx];
+    const char* rowBase = parts[keep[k].part].rowBase;
     rmgpu_hit& o = res->hits[k];
     memset(&o, 0, sizeof(o));
     const int Q = h_qlen[h.q], L = (int)lib.seqs[h.subject].size();
@@ -1645,8 +1745,8 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
   st.ms_host_post = now_ms() - t_post;
   st.ms_total = now_ms() - t_begin + ms_h2d_queries;
   if (getenv("RMGPU_DEBUG_HOST"))
-    fprintf(stderr, "[host dbg] search_batch wall: setup %.2f  score %.2f (kernel %.2f)  origin %.2f  traceback %.2f (kernels %.2f)  finalize %.2f (kernels %.2f)  post %.2f ms\n",
-            w0 - t_begin, w1 - w0, st.ms_score, w2 - w1, w3 - w2, st.ms_traceback, w4 - w3, ms_finalize, st.ms_host_post);
+    fprintf(stderr, "[host dbg] search_batch wall: setup %.2f  device part %.2f (score span %.2f, %zu sub-batch(es); origin %.2f  traceback %.2f (kernels %.2f)  finalize %.2f (kernels %.2f))  post %.2f ms\n",
+            w0 - t_begin, w4 - w0, st.ms_score, parts.size(), wOrigin, wTrace, st.ms_traceback, wFinal, msFinal, st.ms_host_post);
   return res;
 }
 
@@ -1718,7 +1818,20 @@ rmgpu_session* rmgpu_session_open(int device) {
     s = new rmgpu_session();
     s->device = device;
     s->numSMs = prop.multiProcessorCount;
-    CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    {
+      // the score passes run at the lowest priority, everything after them at the highest: when a score-pass CTA retires,
+      // a waiting origin-pass / traceback CTA of the previous sub-batch gets its slot before another score-pass CTA does
+      int lo = 0, hi = 0;
+      CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_CHECK(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, hi));
+      for (int k = 0; k < 2; k++) {
+        auto& sl = s->slot[k];
+        // the first sub-batch's score pass one step above the second's: its pending CTAs are served first
+        CUDA_CHECK(cudaStreamCreateWithPriority(&sl.stream, cudaStreamNonBlocking, (k == 0 && lo - 1 > hi) ? lo - 1 : lo));
+        CUDA_CHECK(cudaEventCreate(&sl.evStart));
+        CUDA_CHECK(cudaEventCreate(&sl.evStop));
+      }
+    }
     {
       size_t freeB = 0, totalB = 0;
       CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
@@ -1743,6 +1856,11 @@ void rmgpu_session_close(rmgpu_session* s) {
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamDestroy(s->stream);
   if (s->stream2) cudaStreamDestroy(s->stream2);
+  for (auto& sl : s->slot) {
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+    if (sl.evStart) cudaEventDestroy(sl.evStart);
+    if (sl.evStop) cudaEventDestroy(sl.evStop);
+  }
   delete s;
 }
 

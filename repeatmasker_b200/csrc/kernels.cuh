@@ -179,6 +179,11 @@ struct ScoreArgs {
   int64_t ckRows;             // nGroups * R
   unsigned long long* dbg;    // optional [8]: cycles waiting on the producer, cycles waiting on a slot, tasks, task cycles,
                               // sum and max over warps of (exit time - first warp's start) in ns, -, base time
+  int quota;                  // tickets a warp takes before it retires (0: until none is left).  With a quota the grid holds
+                              // more CTAs than fit at once, so CTAs retire all along the launch and the block scheduler can
+                              // give their slots to a higher-priority kernel (the origin pass / traceback of the previous
+                              // sub-batch) instead of only at the very end; tickets are still claimed in order by running
+                              // warps, so a consumer never waits on a ticket nobody runs.
 };
 
 // Boundary elements are single 64-bit words {H | F' << 32}; every 16-bit half is < 32768, so bit 15 of each half is
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nTickets = a.nQueries * a.nStripes;
   if (a.dbg && lane == 0) atomicCAS(&a.dbg[7], 0ull, globaltimer_ns());  // time base: the first warp to get here
-  for (;;) {
+  for (int taken = 0; a.quota == 0 || taken < a.quota; taken++) {
     int t = 0;
     if (lane == 0) t = atomicAdd(a.ticket, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
@@ -555,44 +560,49 @@ __device__ __forceinline__ void origin_emit(const OriginArgs& a, int task, uint3
 }
 
 // One origin-propagating cell, branch-free (the tie-breaks of DESIGN.md section 3: E over F over diagonal, extension over
-// opening).  valid = the cell exists (query column and subject row inside the matrix).
+// opening).  Rows beyond the subject and columns beyond the window need no special case: their score is kPadScore, so
+// the diagonal never wins there, nothing in them is a candidate end, and what their E / F carry only flows further down
+// and right, away from every real cell.
+constexpr int kPadCode = 16;                 // residue code of a row / column outside the matrix
+constexpr int kPadScore = -(1 << 20);
+constexpr int kMatStride = 17;               // score table [17][17]: [subject code][query code], code 16 = pad
 struct OriginCell {
   int h;
   uint32_t o;
   bool viaDiag;
 };
-__device__ __forceinline__ OriginCell origin_cell(bool valid, int hl, uint32_t ol, int hu, uint32_t ou, int hd, uint32_t od,
-                                                  int s, uint32_t fresh, int& E, uint32_t& oE, int& f, uint32_t& of,
-                                                  int gap_init, int ins_ext, int del_ext) {
-  const int NEGI = -(1 << 28);
+__device__ __forceinline__ OriginCell origin_cell(int hl, uint32_t ol, int hu, uint32_t ou, int hd, uint32_t od, int s,
+                                                  uint32_t fresh, int& E, uint32_t& oE, int& f, uint32_t& of, int gap_init,
+                                                  int ins_ext, int del_ext) {
   const int e_ext = E + ins_ext, e_open = hl + gap_init;
   const bool eOpen = e_open > e_ext;
-  int e = max(e_ext, e_open);
-  uint32_t oe = eOpen ? ol : oE;
+  E = max(e_ext, e_open);
+  oE = eOpen ? ol : oE;
   const int f_ext = f + del_ext, f_open = hu + gap_init;
   const bool fOpen = f_open > f_ext;
-  int ff = max(f_ext, f_open);
-  uint32_t off = fOpen ? ou : of;
+  f = max(f_ext, f_open);
+  of = fOpen ? ou : of;
   const int d = hd + s;
   const uint32_t odd = hd > 0 ? od : fresh;
-  int h = e;
-  uint32_t o = oe;
-  const bool c1 = ff > h;
-  h = max(h, ff);
-  o = c1 ? off : o;
+  const bool c1 = f > E;
+  int h = max(E, f);
+  uint32_t o = c1 ? of : oE;
   const bool c2 = d > h;
   h = max(h, d);
   o = c2 ? odd : o;
-  const bool pos = valid && h > 0;
+  const bool pos = h > 0;
   OriginCell r;
-  r.h = pos ? h : 0;
+  r.h = max(h, 0);
   r.o = pos ? o : 0u;
   r.viaDiag = c2 && pos;
-  E = valid ? e : NEGI;
-  oE = valid ? oe : oE;
-  f = valid ? ff : NEGI;
-  of = valid ? off : of;
   return r;
+}
+
+__device__ __forceinline__ void load_score_table(int32_t* smat, const int32_t (*mat)[16]) {
+  for (int i = threadIdx.x; i < kMatStride * kMatStride; i += blockDim.x) {
+    const int sr = i / kMatStride, qc = i - sr * kMatStride;
+    smat[i] = (sr < 16 && qc < 16) ? mat[sr][qc] : kPadScore;
+  }
 }
 
 // Column blocks that K1 saw reach minscore (dilated by one block on either side by the host) are swept with origin
@@ -601,8 +611,8 @@ __device__ __forceinline__ OriginCell origin_cell(bool valid, int hl, uint32_t o
 // or any cell >= minscore met in score-only mode, flags the task and the host redoes it with mode = all ones.
 template <int R>
 __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
-  __shared__ int32_t smat[16 * 16];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
+  __shared__ int32_t smat[kMatStride * kMatStride];
+  load_score_table(smat, a.mat);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int NEGI = -(1 << 28);
@@ -622,7 +632,7 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
     const int row0 = (k * 32 + lane) * R;  // 0-based subject row of this lane's first row
     int srow[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) srow[r] = (row0 + r < L) ? (int)sc[row0 + r] * 16 : -1;
+    for (int r = 0; r < R; r++) srow[r] = ((row0 + r < L) ? (int)sc[row0 + r] : kPadCode) * kMatStride;
     int H[R], E[R];
     uint32_t oH[R], oE[R];
 #pragma unroll
@@ -667,7 +677,7 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
         break;
       }
     }
-    int outH = 0, outF = NEGI, curQ = -1;
+    int outH = 0, outF = NEGI, curQ = kPadCode;
     uint32_t outOH = 0, outOF = 0, diagO = kOriginLeft;  // only read when the diagonal source is alive (checkpoint start)
     OriginBoundary wb = {0, NEGI, 0, 0};
     uint32_t lastOrigin = kOriginLeft;  // nothing cached
@@ -675,7 +685,7 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
     bool prevMode = false, needFull = false;
     for (int b = 0; b < nBlocks; b++) {
       int col = b * 32 + lane;  // column offset inside the window
-      int qv = (col < W) ? (int)qc[tk.c0 + col] : -1;
+      int qv = (col < W) ? (int)qc[tk.c0 + col] : kPadCode;
       OriginBoundary bv = {0, NEGI, 0, 0};
       if (hasPrev && b < qBlocks) {
         // hysteresis: when the producer is not ahead, let it get kLag blocks ahead so that later blocks need no sleep
@@ -723,7 +733,6 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
         const int i1 = tk.c0 + cw + 1;     // 1-based query column of this lane at this step
         const bool mode = (j >= lane) ? modeCur : modeOld;
         int hd = diagH, hu = inH, f = inF;
-        const bool active = curQ >= 0;
         if (cw < 0) {
           // before its first column a lane keeps its (checkpointed) state untouched
         } else if (!mode) {
@@ -732,14 +741,13 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
 #pragma unroll
           for (int r = 0; r < R; r++) {
             const int hl = H[r];
-            const bool valid = active && srow[r] >= 0;
             const int e = max(E[r] + a.ins_ext, hl + a.gap_init);
             const int fn = max(f + a.del_ext, hu + a.gap_init);
-            const int d = hd + smat[(srow[r] + curQ) & 255];
-            const int hnew = valid ? max(max(e, fn), max(d, 0)) : 0;
-            E[r] = valid ? e : NEGI;
-            f = valid ? fn : NEGI;
-            needFull |= hnew >= a.minscore;
+            const int d = hd + smat[srow[r] + curQ];
+            const int hnew = max(max(e, fn), max(d, 0));
+            E[r] = e;
+            f = fn;
+            needFull |= hnew >= a.minscore;  // (a pad cell only reaches minscore below / right of a real cell that did)
             hd = hl;
             H[r] = hnew;
             hu = hnew;
@@ -759,15 +767,15 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
           }
           uint32_t od = diagO, ou = inOH, of = inOF;
           diagO = inOH;
+          const uint32_t freshBase = (uint32_t)(cw + 1) * Lp1 + (uint32_t)(row0 + 1);
           uint32_t ends = 0;  // candidate ends of this column, handled after the straight-line cells (see K2b)
 #pragma unroll
           for (int r = 0; r < R; r++) {
             const int hl = H[r];
             const uint32_t ol = oH[r];
-            const bool valid = active && srow[r] >= 0;
-            const int sc_ = smat[(srow[r] + curQ) & 255];
-            const OriginCell c = origin_cell(valid, hl, ol, hu, ou, hd, od, sc_, (uint32_t)(cw + 1) * Lp1 + (uint32_t)(row0 + r + 1),
-                                             E[r], oE[r], f, of, a.gap_init, a.ins_ext, a.del_ext);
+            const int sc_ = smat[srow[r] + curQ];
+            const OriginCell c = origin_cell(hl, ol, hu, ou, hd, od, sc_, freshBase + (uint32_t)r, E[r], oE[r], f, of, a.gap_init,
+                                             a.ins_ext, a.del_ext);
             ends |= (c.viaDiag && c.h >= a.minscore) ? (1u << r) : 0u;
             hd = hl;
             od = ol;
@@ -912,10 +920,13 @@ __device__ __forceinline__ void table_emit(unsigned long long* keys, unsigned lo
 }
 
 __global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
-  __shared__ int32_t smat[16 * 16];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) smat[i] = a.mat[i >> 4][i & 15];
+  __shared__ int32_t smat[kMatStride * kMatStride];
+  __shared__ int4 s_feed[4][32];   // per warp: (H, F, origin of H, origin of F) of the row above, one entry per column of the block
+  __shared__ int s_feedq[4][32];   //           query residue of the column
+  __shared__ int4 s_out[4][32];    //           last row of this stripe, collected column by column for the stripe below
+  load_score_table(smat, a.mat);
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   constexpr int R = kR2;
   const int NEGI = -(1 << 28);
   if (a.dbg && lane == 0) atomicCAS(&a.dbg[7], 0ull, globaltimer_ns());
@@ -959,7 +970,7 @@ __global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
     uint32_t oH[R], oE[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
-      srow[r] = (row0 + r < L) ? (int)sc[row0 + r] * 16 : -1;
+      srow[r] = ((row0 + r < L) ? (int)sc[row0 + r] : kPadCode) * kMatStride;
       H[r] = 0;
       E[r] = NEGI;
       oH[r] = 0;
@@ -983,64 +994,55 @@ __global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
         diagO = kPseudoBit | (uint32_t)row0;
       }
     }
-    int outH = 0, outF = NEGI, curQ = -1;
+    int outH = 0, outF = NEGI, curQ = kPadCode;
     uint32_t outOH = 0, outOF = 0;
-    OriginBoundary wb = {0, NEGI, 0, 0};
     for (int b = 0; b < nBlocks; b++) {
       const int col = b * 32 + lane;
-      const int qv = (col < W) ? (int)qc[tk.c0 + col] : -1;
-      OriginBoundary bv = {0, NEGI, 0, 0};
+      int4 fv = make_int4(0, NEGI, 0, 0);
       if (hasPrev && b < qBlocks) {
         const long long w0 = clock64();
         if (lane == 0 && ld_acquire(&a.progress[tProd]) < b + 1) wait_ge(&a.progress[tProd], b + 1, a.abort_flag);
         __syncwarp();
         waitCyc += clock64() - w0;
-        const int4 raw = __ldcg(reinterpret_cast<const int4*>(&bndIn[col]));
-        bv.h = raw.x;
-        bv.f = raw.y;
-        bv.oh = (uint32_t)raw.z;
-        bv.of = (uint32_t)raw.w;
+        fv = __ldcg(reinterpret_cast<const int4*>(&bndIn[col]));
       }
+      __syncwarp();  // everyone is done with the previous block's feed
+      s_feed[wib][lane] = fv;
+      s_feedq[wib][lane] = (col < W) ? (int)qc[tk.c0 + col] : kPadCode;
+      __syncwarp();
       for (int j = 0; j < 32; j++) {
+        // values moving one lane down per step; lane 0 takes the block's feed (one broadcast read of shared memory)
         int inQ = __shfl_up_sync(0xffffffffu, curQ, 1);
         int inH = __shfl_up_sync(0xffffffffu, outH, 1);
         int inF = __shfl_up_sync(0xffffffffu, outF, 1);
         uint32_t inOH = __shfl_up_sync(0xffffffffu, outOH, 1);
         uint32_t inOF = __shfl_up_sync(0xffffffffu, outOF, 1);
-        const int fq = __shfl_sync(0xffffffffu, qv, j);
-        const int fh = __shfl_sync(0xffffffffu, bv.h, j);
-        const int ff = __shfl_sync(0xffffffffu, bv.f, j);
-        const uint32_t foh = __shfl_sync(0xffffffffu, bv.oh, j);
-        const uint32_t fof = __shfl_sync(0xffffffffu, bv.of, j);
         if (lane == 0) {
-          inQ = fq;
-          inH = fh;
-          inF = ff;
-          inOH = foh;
-          inOF = fof;
+          const int4 fd = s_feed[wib][j];
+          inQ = s_feedq[wib][j];
+          inH = fd.x;
+          inF = fd.y;
+          inOH = (uint32_t)fd.z;
+          inOF = (uint32_t)fd.w;
         }
         curQ = inQ;
         const int cw = b * 32 + j - lane;  // column inside the block, 0-based
-        const int i1 = tk.c0 + cw + 1;     // 1-based query column
         int hd = diagH, hu = inH, f = inF;
         uint32_t od = diagO, ou = inOH, of = inOF;
-        const bool active = curQ >= 0;
         if (cw >= 0) {  // before its first column a lane must keep the checkpointed state untouched
           diagH = inH;
           diagO = inOH;
-          // the R cells of the column are straight-line code (the score lookup is unconditional, candidate ends are only
-          // marked in a bit mask), so the compiler can overlap the parts of different rows that do not depend on the
-          // cell above; the rare candidate ends are handled after the column
+          // the R cells of the column are straight-line code; the rare candidate ends are only marked and handled after
+          const uint32_t freshBase = (uint32_t)(cw + 1) * Lp1 + (uint32_t)(row0 + 1);
+          const int* scol = smat + curQ;
           uint32_t ends = 0;
 #pragma unroll
           for (int r = 0; r < R; r++) {
             const int hl = H[r];
             const uint32_t ol = oH[r];
-            const bool valid = active && srow[r] >= 0;
-            const int sc_ = smat[(srow[r] + curQ) & 255];
-            const OriginCell c = origin_cell(valid, hl, ol, hu, ou, hd, od, sc_, (uint32_t)(cw + 1) * Lp1 + (uint32_t)(row0 + r + 1),
-                                             E[r], oE[r], f, of, a.gap_init, a.ins_ext, a.del_ext);
-            ends |= (c.viaDiag && c.h >= a.minscore) ? (1u << r) : 0u;
+            const OriginCell c = origin_cell(hl, ol, hu, ou, hd, od, scol[srow[r]], freshBase + (uint32_t)r, E[r], oE[r], f, of,
+                                             a.gap_init, a.ins_ext, a.del_ext);
+            if (c.viaDiag && c.h >= a.minscore) ends |= 1u << r;
             hd = hl;
             od = ol;
             H[r] = c.h;
@@ -1049,6 +1051,7 @@ __global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
             ou = c.o;
           }
           if (ends) {
+            const int i1 = tk.c0 + cw + 1;  // 1-based query column
 #pragma unroll
             for (int r = 0; r < R; r++)
               if (ends & (1u << r)) {
@@ -1063,34 +1066,27 @@ __global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
                 }
               }
           }
+          if (cw == W - 1) {  // last column of the block: snapshot the origins of (H, E) for the next block's tasks
+            uint32_t* sn = a.snap + tk.snapOff;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+              if (row0 + r < L) {
+                sn[row0 + r] = oH[r];
+                sn[L + row0 + r] = oE[r];
+              }
+          }
         }
         outH = hu;
         outF = f;
         outOH = ou;
         outOF = of;
-        if (cw == W - 1) {  // last column of the block: snapshot the origins of (H, E) for the next block's tasks
-          uint32_t* sn = a.snap + tk.snapOff;
-#pragma unroll
-          for (int r = 0; r < R; r++)
-            if (row0 + r < L) {
-              sn[row0 + r] = oH[r];
-              sn[L + row0 + r] = oE[r];
-            }
-        }
         if (hasNext) {
-          const int oh = __shfl_sync(0xffffffffu, outH, 31);
-          const int of2 = __shfl_sync(0xffffffffu, outF, 31);
-          const uint32_t ooh = __shfl_sync(0xffffffffu, outOH, 31);
-          const uint32_t oof = __shfl_sync(0xffffffffu, outOF, 31);
+          // lane 31 has just finished column c = b*32 + j - 31 of the stripe's last row
           const int c = b * 32 + j - 31;
-          if (lane == (c & 31)) {
-            wb.h = oh;
-            wb.f = of2;
-            wb.oh = ooh;
-            wb.of = oof;
-          }
-          if (c >= 0 && (c & 31) == 31) {
-            *reinterpret_cast<int4*>(&bndOut[(c & ~31) + lane]) = make_int4(wb.h, wb.f, (int)wb.oh, (int)wb.of);
+          if (lane == 31) s_out[wib][c & 31] = make_int4(outH, outF, (int)outOH, (int)outOF);
+          if (c >= 0 && (c & 31) == 31) {  // a block of 32 columns is complete: one coalesced store, then publish it
+            __syncwarp();
+            *reinterpret_cast<int4*>(&bndOut[(c & ~31) + lane]) = s_out[wib][lane];
             __threadfence();
             __syncwarp();
             if (lane == 0) st_release(&a.progress[t], (c >> 5) + 1);

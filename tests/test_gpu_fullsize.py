@@ -173,6 +173,31 @@ def test_full_size_recall_of_implanted_copies(config2):
     assert weak_found >= 0.9 * weak, (weak_found, weak)
 
 
+def test_config3_slice_equals_oracle_hit_for_hit(tmp_path):
+    """BASELINE configuration 3 (1,500-family, 1.76 Mbp library, -s parameters) on the first 0.5 Mbp of its genome: every one of
+    the 9 fragments against the CPU arm (the oracle on all host cores), hit for hit.  tools/run_config3_slice.py --oracle does
+    the same on 4 Mbp (profiles/r2_config3_slice.txt)."""
+    from repeatmasker_b200 import sharding
+    from test_gpu_parity import assert_same_hits
+
+    snames, sseqs = synth.make_library(1002, n_families=1500)
+    genome, _ = synth.make_genome(1002, 500_000, sseqs, coverage=0.45)
+    qn, qs = synth.fragment(genome, "synth0", frag=60000, overlap=2000)
+    m = util.write_matrix("20p41g.matrix", str(tmp_path / "20p41g.matrix"))
+    s = engine.Session()
+    s.set_matrix(m)
+    s.set_library(sseqs, snames)
+    s.set_queries(qs, qn)
+    hits, st = s.search(engine.make_params(minmatch=8))
+    per = sharding.split_hits_by_fragment(hits, qn)
+    assert len(qs) == 9 and len(hits) > 200
+    for f in range(len(qs)):
+        q = str(tmp_path / "q.fa")
+        synth.write_fasta(q, [qn[f]], [qs[f]])
+        want = util.run_oracle_parallel(q, snames, sseqs, m, str(tmp_path), minmatch=8)
+        assert_same_hits(per[f], want)
+
+
 def test_many_family_library_against_oracle(tmp_path):
     """Configuration 5 in miniature: thousands of short families plus a few long ones, many small query records
     (several ticket-order groups, many fillers per stripe)."""
