@@ -1309,7 +1309,13 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
   while (!todo.empty()) {
     std::vector<int> next;
     // narrow bands first (one warp each), then wide bands (a team of up to 512 threads of a block each)
-    std::stable_sort(todo.begin(), todo.end(), [&](int x, int y) { return (band_of(x) > 64) < (band_of(y) > 64); });
+    // ... and the longest alignments of each kind first: a candidate is one dependent chain of 2n waves, so the longest one
+    // bounds the launch and must not be the last block the scheduler starts
+    std::stable_sort(todo.begin(), todo.end(), [&](int x, int y) {
+      const bool wx = band_of(x) > 64, wy = band_of(y) > 64;
+      if (wx != wy) return wx < wy;
+      return cands[x].i1 - cands[x].i0 > cands[y].i1 - cands[y].i0;
+    });
     size_t at = 0;
     while (at < todo.size()) {
       std::vector<TraceCand> tc;
