@@ -307,9 +307,12 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def finish(hits, st):
-        """End of a step: all records on rank 0, in fragment order (RepeatMasker:994-1017 concatenates .cat files so)."""
+    def finish(rec):
+        """End of a step: all records on rank 0, in fragment order (RepeatMasker:994-1017 concatenates .cat files so).
+        On one GPU they already are where the caller wants them: C records in host memory, as the XS glue reads them."""
+        st = rec.stats
         if world > 1:
+            hits = rec.to_dicts()
             per_frag = sharding.split_hits_by_fragment(hits, qn)
             gathered = [None] * world if rank == 0 else None
             dist.gather_object((mine, per_frag), gathered, dst=0, group=host_group)
@@ -321,7 +324,7 @@ def main():
                 assert all(h is not None for h in out)
                 n_hits[0] = sum(len(h) for h in out)
         else:
-            n_hits[0] = len(hits)
+            n_hits[0] = len(rec)
         return st
 
     def timed(fn, steps):
@@ -337,12 +340,12 @@ def main():
         return tot, stats
 
     def step_resident():
-        return finish(*sess.search(params))
+        return finish(sess.search_records(params))
 
     def step_e2e():  # host buffers in, host records out: library + batch upload, search, records (and the gather)
         sess.set_library(sseqs, snames)
         sess.set_queries(qs, qn)
-        return finish(*sess.search(params))
+        return finish(sess.search_records(params))
 
     timed(step_resident, args.warmup)
     sampler = ClockSampler(local)

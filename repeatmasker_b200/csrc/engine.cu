@@ -187,6 +187,10 @@ struct rmgpu_session {
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     int q0 = 0, nQ = 0, grid = 0, nslot = 0;
     bool dbg = false;
+    // the ring must be all zero (tag 0 = never written) when a launch starts: it is cleared right after a launch has been
+    // collected, on the slot's stream, i.e. behind the origin pass and the traceback of the same step
+    const void* cleanPtr = nullptr;
+    size_t cleanBytes = 0, usedBytes = 0;
   } slot[2];
   void build_order(ScoreSlot& sl, int nQ, int warps);
   void launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, int nQ, bool exact, bool quota);
@@ -680,9 +684,13 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
   CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), sl.stream));
   CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), sl.stream));
   CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), sl.stream));
-  CUDA_CHECK(cudaEventRecord(sl.evStart, sl.stream));
   // tag 0 = "never written": the boundary ring must not hold tags of an earlier launch
-  CUDA_CHECK(cudaMemsetAsync(a.bnd, 0, (size_t)nslot * bndStride * sizeof(unsigned long long), sl.stream));
+  sl.usedBytes = (size_t)nslot * bndStride * sizeof(unsigned long long);
+  if (sl.cleanPtr != (const void*)a.bnd || sl.cleanBytes < sl.usedBytes)
+    CUDA_CHECK(cudaMemsetAsync(a.bnd, 0, sl.usedBytes, sl.stream));
+  sl.cleanPtr = nullptr;
+  sl.cleanBytes = 0;
+  CUDA_CHECK(cudaEventRecord(sl.evStart, sl.stream));
   if (exact)
     swg_score_kernel<R, true><<<grid, kScoreWarps * 32, 0, sl.stream>>>(a);
   else
@@ -699,6 +707,10 @@ void rmgpu_session::collect_score(ScoreSlot& sl, std::vector<int32_t>& pairbest,
                              cudaMemcpyDeviceToHost, sl.stream));
   CUDA_CHECK(cudaStreamSynchronize(sl.stream));
   check_abort_on("K1", sl.d_abort.p, sl.stream);
+  // clear the ring for the next launch now: the copy runs beside the rest of this step
+  CUDA_CHECK(cudaMemsetAsync(sl.d_bnd.p, 0, sl.usedBytes, sl.stream));
+  sl.cleanPtr = sl.d_bnd.p;
+  sl.cleanBytes = sl.usedBytes;
   if (sl.dbg) {
     unsigned long long d[8];
     float ms = 0;
@@ -1749,7 +1761,7 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
     }
   }
   st.ms_host_post = now_ms() - t_post;
-  st.ms_total = now_ms() - t_begin + ms_h2d_queries;
+  st.ms_total = now_ms() - t_begin;
   if (getenv("RMGPU_DEBUG_HOST"))
     fprintf(stderr, "[host dbg] search_batch wall: setup %.2f  device part %.2f (score span %.2f, %zu sub-batch(es); origin %.2f  traceback %.2f (kernels %.2f)  finalize %.2f (kernels %.2f))  post %.2f ms\n",
             w0 - t_begin, w4 - w0, st.ms_score, parts.size(), wOrigin, wTrace, st.ms_traceback, wFinal, msFinal, st.ms_host_post);

@@ -70,6 +70,7 @@ struct Worker {
   std::deque<std::shared_ptr<Request>> queue;
   std::vector<Resident> resident;  // LRU of libraries on this GPU
   long served = 0, passes = 0, clock = 0;
+  int inflight = 0;  // calls of the pass that is running (guarded by mu)
   std::thread thread;
 };
 
@@ -209,8 +210,13 @@ void worker_loop(Worker* w) {
         } else
           ++it;
       }
+      w->inflight = (int)group.size();
     }
     run_group(w, group);
+    {
+      std::lock_guard<std::mutex> lk(w->mu);
+      w->inflight = 0;
+    }
   }
 }
 
@@ -242,12 +248,16 @@ void handle(int fd) {
   }
   req->libKey = file_key(req->subject);
   req->matKey = file_key(req->matrix);
-  // the GPU with the shortest queue; among equals the one that already holds the library
+  // the GPU with the least pending work (queued + in flight); the scan starts at a rotating index so that equally idle
+  // GPUs take turns
+  static std::atomic<unsigned> next{0};
+  const unsigned start = next++ % (unsigned)g_workers.size();
   Worker* best = nullptr;
   size_t bestLen = 0;
-  for (Worker* w : g_workers) {
+  for (size_t i = 0; i < g_workers.size(); i++) {
+    Worker* w = g_workers[(start + i) % g_workers.size()];
     std::lock_guard<std::mutex> lk(w->mu);
-    const size_t len = w->queue.size();
+    const size_t len = w->queue.size() + (size_t)w->inflight;
     if (!best || len < bestLen) {
       best = w;
       bestLen = len;

@@ -178,6 +178,25 @@ def _seq_arrays(names, seqs):
     return (n, (C.c_char_p * n)(*bn), (C.c_char_p * n)(*bs), (C.c_int32 * n)(*[len(b) for b in bs]))
 
 
+class Records:
+    """Host-side result of one search as the library returns it (rmgpu_result: flat rmgpu_hit records + row buffer)."""
+
+    def __init__(self, res):
+        self._res = res
+        self.stats = {k: getattr(res.contents.stats, k) for k, _ in Stats._fields_}
+
+    def __len__(self):
+        return self._res.contents.n_hits
+
+    def to_dicts(self):
+        return _hits_to_dicts(self._res)[0]
+
+    def __del__(self):
+        if self._res is not None:
+            lib().rmgpu_free(self._res)
+            self._res = None
+
+
 class Session:
     """One GPU worker: matrix + library resident in HBM, query batches streamed through (rmgpu_session_*)."""
 
@@ -215,6 +234,13 @@ class Session:
 
     def library_h2d_bytes(self):
         return lib().rmgpu_session_library_h2d_bytes(self._h)
+
+    def search_records(self, params):
+        """The search with the result left as the C records rmgpu_session_search() returns (what the XS glue walks):
+        a `Records` object -- len(), .stats, .to_dicts() -- that frees the result when it is dropped."""
+        res = C.POINTER(Result)()
+        _check(lib().rmgpu_session_search(self._h, C.byref(params), C.byref(res)))
+        return Records(res)
 
     def search(self, params):
         res = C.POINTER(Result)()

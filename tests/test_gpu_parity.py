@@ -185,6 +185,25 @@ def test_alphabet_edge_cases(tmp_path):
     assert_same_hits(got, want)
 
 
+def test_letters_outside_the_iupac_alphabet(tmp_path):
+    """Letters that are no nucleotide code (U, I, E ...) are scored as N, like the oracle does, but the rows show the original
+    letter and a mismatch is a difference of LETTERS (U against N counts): the device spells such records with N and the
+    host puts the letters back and recounts (rmgpu_session::respell_exotic)."""
+    rng = np.random.default_rng(19)
+    cons = synth.random_dna(rng, 500).tobytes().decode()
+    copy = list(synth.mutate(rng, cons, 0.08, 0.01))
+    for pos, ch in ((40, "U"), (41, "U"), (150, "I"), (300, "E"), (301, "N")):
+        copy[pos] = ch
+    cons_x = cons[:90] + "U" + cons[91:250] + "N" + cons[251:]
+    bg = synth.random_dna(rng, 2000).tobytes().decode()
+    q = bg[:500] + "".join(copy) + bg[500:1200] + synth.revcomp(synth.mutate(rng, cons, 0.1, 0.01)) + bg[1200:]
+    got, want, st = both(tmp_path, ["exotic", "plain"], [q, bg[:300] + synth.mutate(rng, cons, 0.05, 0.0) + bg[300:600]],
+                         ["consU#DNA/x"], [cons_x])
+    assert len(want) >= 3
+    assert any("U" in h["qaln"] for h in want) and any("U" in h["saln"] for h in want)
+    assert_same_hits(got, want)
+
+
 @pytest.mark.parametrize("matrix,gi,ie,de", [("14p41g.matrix", -35, -7, -6), ("18p41g.matrix", -30, -6, -5),
                                             ("25p41g.matrix", -27, -6, -5)])
 @pytest.mark.parametrize("raw", [False, True])
