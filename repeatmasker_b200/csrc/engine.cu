@@ -174,9 +174,7 @@ struct rmgpu_session {
   DevBuf<uint2> d_prof;
   DevBuf<int32_t> d_gsubject, d_slen;
   std::vector<uint8_t> h_sflags;
-  // One K1 launch in flight: its ticket order (depends on the number of query records), boundary ring and counters.  Two
-  // slots: search_batch() cuts a batch in two sub-batches whose score passes are both queued at once, and works on the first
-  // one's origin pass / traceback / rows while the second one's score pass has the integer pipes.
+  // One K1 launch: its ticket order (depends on the number of query records), boundary ring, counters and stream.
   struct ScoreSlot {
     DevBuf<int32_t> d_order, d_prodPos, d_consPos;
     int orderGroup = 0;   // max position distance between a stripe and the stripe below it in the ticket order
@@ -191,9 +189,9 @@ struct rmgpu_session {
     // collected, on the slot's stream, i.e. behind the origin pass and the traceback of the same step
     const void* cleanPtr = nullptr;
     size_t cleanBytes = 0, usedBytes = 0;
-  } slot[2];
+  } slot[1];
   void build_order(ScoreSlot& sl, int nQ, int warps);
-  void launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, int nQ, bool exact, bool quota);
+  void launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, int nQ, bool exact);
   void collect_score(ScoreSlot& sl, std::vector<int32_t>& pairbest, std::vector<unsigned long long>& hotmask);
   void prepare_score(const rmgpu_params& p, bool exact);
   DevBuf<int64_t> d_soff;
@@ -354,7 +352,7 @@ void rmgpu_session::set_library(SeqSet s) {
     }
   }
   h_sflags = sflags;
-  slot[0].orderForNQ = slot[1].orderForNQ = -1;
+  slot[0].orderForNQ = -1;
   // unpacked subject codes for K2 / K3
   h_soff.assign(n + 1, 0);
   std::vector<int32_t> slen(n);
@@ -611,7 +609,7 @@ void rmgpu_session::prepare_score(const rmgpu_params& p, bool exact) {
   CUDA_CHECK(cudaStreamSynchronize(stream));  // K0 and the cleared buffers are in place before any slot's stream starts
 }
 
-void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, int nQ, bool exact, bool quota) {
+void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, int nQ, bool exact) {
   const int nS = (int)lib.seqs.size();
   int blocksPerSM = 0;
   if (exact)
@@ -675,14 +673,7 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
     a.dbg = sl.d_dbg.ensure(8);
     CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 64, sl.stream));
   }
-  // CTAs: with a quota more than fit at once, each warp taking `quota` tickets; else one persistent wave
-  int grid;
-  a.quota = 0;
-  if (quota && nTickets > 2ll * resident * kScoreWarps) {
-    a.quota = 2;
-    grid = (int)((nTickets + (int64_t)kScoreWarps * a.quota - 1) / ((int64_t)kScoreWarps * a.quota));
-  } else
-    grid = (int)std::min<int64_t>(resident, (nTickets + kScoreWarps - 1) / kScoreWarps);
+  const int grid = (int)std::min<int64_t>(resident, (nTickets + kScoreWarps - 1) / kScoreWarps);  // one persistent wave
   sl.q0 = q0;
   sl.nQ = nQ;
   sl.grid = grid;
@@ -741,7 +732,7 @@ void rmgpu_session::run_score(const rmgpu_params& p, std::vector<int32_t>& pairb
   ms = 0;
   if (nQ == 0 || nS == 0) return;
   prepare_score(p, exact);
-  launch_score(p, slot[0], 0, nQ, exact, /*quota=*/false);
+  launch_score(p, slot[0], 0, nQ, exact);
   collect_score(slot[0], pairbest, hotmask);
   float f = 0;
   cudaEventElapsedTime(&f, slot[0].evStart, slot[0].evStop);
@@ -1538,7 +1529,7 @@ int rmgpu_session::query_capacity() const {
   // itself costs up to milliseconds per call)
   const long long freeNow = freeAtOpen - (g_devbuf_bytes[device & 63].load() - devbufAtOpen);
   const size_t freeB = (size_t)std::max<long long>(freeNow, 0);
-  const double budget = 0.45 * (double)(freeB + d_ck.cap * sizeof(uint2) + (slot[0].d_bnd.cap + slot[1].d_bnd.cap) * 8);
+  const double budget = 0.45 * (double)(freeB + d_ck.cap * sizeof(uint2) + slot[0].d_bnd.cap * 8);
   const double stride = (double)maxQ + 64.0;
   const double ckPerQuery = (double)kHotBlocks * nGroups * R * 8.0;
   // boundary ring: at most 15 tag generations per launch (run_score), i.e. nQ * nStripes / 14 slots, and never fewer than
@@ -1626,32 +1617,15 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
     st.cells = 2.0 * qb * sb;
   }
 
-  // The batch is cut in two sub-batches whose score passes are both queued at once (each on its own low-priority stream;
-  // the second one's CTAs take the SM slots the first one's retiring CTAs leave).  While the second score pass runs, the
-  // origin pass, traceback and rows of the first sub-batch are launched on high-priority streams: score-pass CTAs retire
-  // all along their launch (ScoreArgs::quota), so those kernels get slots next to it instead of waiting for its end.
-  struct Part {
+  struct Part {  // (one part: the two-sub-batch pipeline of round 2 was measured slower)
     int q0, q1;
     std::vector<HitDev> dh;
     std::vector<char> rows;
     const char* rowBase = nullptr;
   };
-  // Measured on the bench workload (profiles/r2_pipeline_experiment.txt): 267-279 ms per step with two sub-batches against
-  // 247 ms with one -- the origin pass and the traceback are latency-bound, so next to a score pass that owns every
-  // register of the SM they hold the slots they get four to five times longer, and the score pass loses more than they
-  // gain.  One sub-batch is therefore the default; RMGPU_PIPELINE=1 keeps the experiment reachable.
-  static const bool pipe = getenv("RMGPU_PIPELINE") != nullptr;
-  std::vector<Part> parts;
-  if (nQ >= 8 && pipe && nS > 0) {
-    parts.resize(2);
-    parts[0].q0 = 0;
-    parts[0].q1 = parts[1].q0 = (nQ + 1) / 2;
-    parts[1].q1 = nQ;
-  } else {
-    parts.resize(1);
-    parts[0].q0 = 0;
-    parts[0].q1 = nQ;
-  }
+  std::vector<Part> parts(1);
+  parts[0].q0 = 0;
+  parts[0].q1 = nQ;
   std::vector<int32_t> pairbest((size_t)nQ * nS * 2, 0);
   std::vector<unsigned long long> hotmask((size_t)nQ * nS * 2 * kHotWords, 0);
   const double w0 = now_ms();
@@ -1659,7 +1633,7 @@ rmgpu_result* rmgpu_session::search_batch(const rmgpu_params& p) {
   if (nQ > 0 && nS > 0) {
     prepare_score(p, /*exact=*/false);
     for (size_t k = 0; k < parts.size(); k++)
-      launch_score(p, slot[k], parts[k].q0, parts[k].q1 - parts[k].q0, /*exact=*/false, /*quota=*/parts.size() > 1);
+      launch_score(p, slot[k], parts[k].q0, parts[k].q1 - parts[k].q0, /*exact=*/false);
     st.launches += 2 * (int)parts.size();
     st.score_launches = (int)parts.size();
     st.d2h_bytes += (int64_t)pairbest.size() * 12;
@@ -1843,15 +1817,13 @@ rmgpu_session* rmgpu_session_open(int device) {
     s->device = device;
     s->numSMs = prop.multiProcessorCount;
     {
-      // the score passes run at the lowest priority, everything after them at the highest: when a score-pass CTA retires,
-      // a waiting origin-pass / traceback CTA of the previous sub-batch gets its slot before another score-pass CTA does
+      // the score pass on its own (lowest-priority) stream, so that clearing its ring for the next call runs beside the
+      // kernels that follow it
       int lo = 0, hi = 0;
       CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       CUDA_CHECK(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, hi));
-      for (int k = 0; k < 2; k++) {
-        auto& sl = s->slot[k];
-        // the first sub-batch's score pass one step above the second's: its pending CTAs are served first
-        CUDA_CHECK(cudaStreamCreateWithPriority(&sl.stream, cudaStreamNonBlocking, (k == 0 && lo - 1 > hi) ? lo - 1 : lo));
+      for (auto& sl : s->slot) {
+        CUDA_CHECK(cudaStreamCreateWithPriority(&sl.stream, cudaStreamNonBlocking, lo));
         CUDA_CHECK(cudaEventCreate(&sl.evStart));
         CUDA_CHECK(cudaEventCreate(&sl.evStop));
       }

@@ -180,11 +180,6 @@ struct ScoreArgs {
   unsigned long long* dbg;    // optional [8]: cycles waiting on the producer, cycles waiting on a slot, tasks, task cycles,
                               // sum and max over warps of (exit time - first warp's start) in ns, -, base time
   int nSeg;                   // column segments per (stripe, query): tickets are nSeg x nStripes x nQueries (1 without checkpoints)
-  int quota;                  // tickets a warp takes before it retires (0: until none is left).  With a quota the grid holds
-                              // more CTAs than fit at once, so CTAs retire all along the launch and the block scheduler can
-                              // give their slots to a higher-priority kernel (the origin pass / traceback of the previous
-                              // sub-batch) instead of only at the very end; tickets are still claimed in order by running
-                              // warps, so a consumer never waits on a ticket nobody runs.
 };
 
 // Boundary elements are single 64-bit words {H | F' << 32}; every 16-bit half is < 32768, so bit 15 of each half is
@@ -223,7 +218,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
   const int nPQ = a.nQueries * a.nStripes;   // tickets of one column segment
   const int nTickets = nPQ * a.nSeg;
   if (a.dbg && lane == 0) atomicCAS(&a.dbg[7], 0ull, globaltimer_ns());  // time base: the first warp to get here
-  for (int taken = 0; a.quota == 0 || taken < a.quota; taken++) {
+  for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(a.ticket, 1);
     t = __shfl_sync(0xffffffffu, t, 0);

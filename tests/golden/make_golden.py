@@ -183,8 +183,41 @@ print join( ",", @ids ) . "\n";
     return dict(source="SearchResultCollection.pm:198-358 (maskLevelFilter), :379-470 (filterContainedResults) executed by perl", sets=out)
 
 
+def simplebatcher():
+    """The reference's own fragmenting (FastaDB + SimpleBatcher, SimpleBatcher.pm:592-800) of seeded random sequences:
+    batch ids, lengths and content digests.  repeatmasker_b200/synth.py:fragment restates that arithmetic."""
+    import hashlib, random, tempfile
+    perl = r'''
+use lib "%s"; use FastaDB; use SimpleBatcher;
+my ($f, $tmp) = @ARGV;
+my $db = FastaDB->new( fileName => $f, openMode => SeqDBI::ReadOnly, maxIDLength => 50 );
+my $b = SimpleBatcher->new( $db, 60000, 2000 );
+for my $i (1 .. $b->getBatchCount()) {
+  $b->writeBatchFile($i, $tmp);
+  open(my $fh, "<", $tmp); my ($id, $seq) = ("", "");
+  while (<$fh>) { chomp; if (/^>(\S+)/) { $id = $1; } else { $seq .= $_; } }
+  close($fh);
+  print "$id $seq\n";
+}
+''' % REF
+    out = []
+    with tempfile.TemporaryDirectory() as d:
+        for n in (59999, 60001, 123457, 151062, 1000000):
+            rng = random.Random(n)
+            seq = "".join(rng.choice("ACGT") for _ in range(n))
+            open(f"{d}/s.fa", "w").write(">s\n" + seq + "\n")
+            r = subprocess.run(["perl", "-e", perl, f"{d}/s.fa", f"{d}/batch.fa"], capture_output=True, text=True, check=True)
+            frags = []
+            for ln in r.stdout.splitlines():
+                fid, fseq = ln.split()
+                frags.append([fid, len(fseq), hashlib.md5(fseq.upper().encode()).hexdigest()])
+            out.append(dict(length=n, seed=n, fragments=frags))
+    return dict(source="SimpleBatcher.pm:592-800 (frag 60000, overlap 2000) executed by perl on random.Random(length) sequences of ACGT", cases=out)
+
+
 def main():
     config1()
+    json.dump(simplebatcher(), open(f"{OUT}/simplebatcher.json", "w"))
     json.dump(hum1_sine(), open(f"{OUT}/hum1_sine.json", "w"))
     json.dump(masklevel(), open(f"{OUT}/masklevel.json", "w"))
     json.dump(parse_searchresult_t(), open(f"{OUT}/searchresult_t.json", "w"), indent=1)

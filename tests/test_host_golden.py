@@ -35,3 +35,24 @@ def test_matrix_reader_fails_loudly(tmp_path):
     (tmp_path / "bad.matrix").write_text("this is not a matrix\n")
     with pytest.raises(engine.RmgpuError, match="could not parse"):
         engine.matrix_info(str(tmp_path / "bad.matrix"))
+
+
+def test_fragment_arithmetic_equals_simplebatcher():
+    """synth.fragment (what bench.py and the full-size tests cut genomes with) against the reference's own SimpleBatcher
+    (tests/golden/simplebatcher.json: ids, lengths and content digests of its batches, made by running it under perl)."""
+    import hashlib
+    import json
+    import os
+    import random
+
+    from repeatmasker_b200 import synth
+
+    gold = json.load(open(os.path.join(util.GOLD, "simplebatcher.json")))
+    for case in gold["cases"]:
+        rng = random.Random(case["seed"])
+        seq = "".join(rng.choice("ACGT") for _ in range(case["length"]))
+        names, seqs = synth.fragment(seq, "s", frag=60000, overlap=2000)
+        got = [[n, len(x), hashlib.md5(x.encode()).hexdigest()] for n, x in zip(names, seqs)]
+        assert got == case["fragments"], case["length"]
+        offs = synth.fragment_offsets(case["length"])
+        assert all(seq[o:o + len(x)] == x for o, x in zip(offs, seqs))
