@@ -617,16 +617,11 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
   else
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R, false>, kScoreWarps * 32, 0));
   if (blocksPerSM < 1) throw Error("K1 does not fit on an SM");
-  // Column segments: a ticket = one stripe x one part of a query record's columns (cut at column checkpoints, which hand the
-  // state over), so that the last wave of the launch is a fraction of a stripe-sweep long instead of a whole one.  Needs
-  // the checkpoints.
-  static const char* segEnv = getenv("RMGPU_K1_SEGMENTS");
-  const int nSeg = (ckEnabled && !exact && maxQ >= 8192) ? std::max(1, std::min(8, segEnv ? atoi(segEnv) : 4)) : 1;
-  const int64_t nTickets = (int64_t)nQ * nStripes * nSeg;
+  const int64_t nTickets = (int64_t)nQ * nStripes;
   if (nTickets >= (1ll << 31)) throw Error("too many stripe tasks in one batch");
   const int resident = numSMs * blocksPerSM;
   // ticket order and ring are sized for the warps that can run at once
-  const int warps = (int)std::min<int64_t>((int64_t)resident * kScoreWarps, nTickets / nSeg);
+  const int warps = (int)std::min<int64_t>((int64_t)resident * kScoreWarps, nTickets);
   build_order(sl, nQ, warps);
   // ring slots: a slot is rewritten nslot tickets later; its reader is at most orderGroup * nQ tickets after its writer
   // ... and a boundary's 4-bit tag (generation = ticket / nslot, 15 values) must be unique within a launch: a slot keeps
@@ -665,7 +660,6 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
   a.abort_flag = sl.d_abort.ensure(1);
   a.ck = ckEnabled ? d_ck.p + (size_t)q0 * kHotBlocks * ((size_t)nGroups * R) : nullptr;
   a.ckRows = (int64_t)nGroups * R;
-  a.nSeg = nSeg;
   static const bool dbgOn = getenv("RMGPU_DEBUG_K1") != nullptr;
   sl.dbg = dbgOn;
   a.dbg = nullptr;

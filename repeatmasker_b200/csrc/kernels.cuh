@@ -179,7 +179,6 @@ struct ScoreArgs {
   int64_t ckRows;             // nGroups * R
   unsigned long long* dbg;    // optional [8]: cycles waiting on the producer, cycles waiting on a slot, tasks, task cycles,
                               // sum and max over warps of (exit time - first warp's start) in ns, -, base time
-  int nSeg;                   // column segments per (stripe, query): tickets are nSeg x nStripes x nQueries (1 without checkpoints)
 };
 
 // Boundary elements are single 64-bit words {H | F' << 32}; every 16-bit half is < 32768, so bit 15 of each half is
@@ -215,17 +214,14 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
                                              // + the selector of the next block's first column
   __shared__ uint2 s_out[kScoreWarps][32];   // last row's (H, F') of the last 32 columns lane 31 finished
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int nPQ = a.nQueries * a.nStripes;   // tickets of one column segment
-  const int nTickets = nPQ * a.nSeg;
+  const int nTickets = a.nQueries * a.nStripes;
   if (a.dbg && lane == 0) atomicCAS(&a.dbg[7], 0ull, globaltimer_ns());  // time base: the first warp to get here
   for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(a.ticket, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= nTickets) break;
-    // ticket = (column segment, position in the stripe order, query): all tickets of a segment come before those of the next
-    const int seg = t / nPQ, rem = t - seg * nPQ;
-    const int pos = rem / a.nQueries, q = rem - pos * a.nQueries;  // query fastest: a level of the order spans all queries
+    const int pos = t / a.nQueries, q = t - pos * a.nQueries;  // query fastest: a level of the order spans all queries
     const int k = a.order[pos];
     const int g = k * 32 + lane;
     const int Q = a.qlen[q];
@@ -233,21 +229,6 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     const bool hasPrev = sf & 1, hasNext = sf & 2;
     const bool startFlag = a.gflags[g] & 1;
     const uint16_t* sel = a.sel + a.selOff[q];
-    const int hotShift = a.hotShift[q];
-    const int ckBlkMask = (1 << hotShift) - 1;
-    const int qBlocks = (Q + 31) >> 5;
-    // the segment's 32-column blocks [b0, b1): segments are cut on checkpoint-block boundaries, so that a segment starts
-    // from the column checkpoint the previous one stored in its last block
-    int b0 = 0, b1 = qBlocks;
-    if (a.nSeg > 1) {
-      const int nCk = (qBlocks + ckBlkMask) >> hotShift;  // checkpoint blocks of this query
-      b0 = min(qBlocks, ((seg * nCk) / a.nSeg) << hotShift);
-      if (seg + 1 < a.nSeg) b1 = min(qBlocks, (((seg + 1) * nCk) / a.nSeg) << hotShift);
-    }
-    if (seg > 0 && b0 >= b1) {  // nothing left of a short query for this segment
-      if (lane == 0) st_release(&a.finished[t], 1);
-      continue;
-    }
     uint32_t Plo[R], Phi[R], H[R], E[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -257,10 +238,9 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
       H[r] = 0;
       E[r] = 0;
     }
-    const bool lastSeg = b1 == qBlocks;        // the block after the last one runs over the query's padding, else over
-    const int bEnd = b1 + 1;                   // pad selectors while the lanes drain (lane 31 reaches column b1*32 - 1)
-    const int cFirst = b0 * 32;
-    const int tProd = hasPrev ? seg * nPQ + a.prodPos[pos] * a.nQueries + q : 0;  // ticket of the stripe above (always older)
+    const int qBlocks = (Q + 31) >> 5;
+    const int nBlocks = qBlocks + 1;  // lane 31 reaches column qBlocks*32 >= Q
+    const int tProd = hasPrev ? a.prodPos[pos] * a.nQueries + q : 0;  // ticket of the stripe above (always older)
     const unsigned long long* bndIn = a.bnd + (int64_t)(tProd % a.nslot) * a.bndStride;
     unsigned long long* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
     const unsigned long long tagIn = tag_bits(tProd, a.nslot), tagOut = tag_bits(t, a.nslot);
@@ -268,43 +248,32 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
       // The slot still holds the boundary of the last ticket that WROTE it (t - nslot, t - 2 nslot, ... skipping
       // tickets whose stripe has no stripe below): its reader must be done before this ticket overwrites it.
       for (int tOld = t - a.nslot; tOld >= 0; tOld -= a.nslot) {
-        const int sOld = tOld / nPQ, rOld = tOld - sOld * nPQ;
-        const int pOld = rOld / a.nQueries;
+        const int pOld = tOld / a.nQueries;
         const int cOld = a.consPos[pOld];
         if (cOld < 0) continue;
         const long long w0 = clock64();
-        if (lane == 0) wait_ge(&a.finished[sOld * nPQ + cOld * a.nQueries + (rOld - pOld * a.nQueries)], 1, a.abort_flag);
+        if (lane == 0) wait_ge(&a.finished[cOld * a.nQueries + (tOld - pOld * a.nQueries)], 1, a.abort_flag);
         __syncwarp();
         if (a.dbg && lane == 0) atomicAdd(&a.dbg[1], (unsigned long long)(clock64() - w0));
         break;
       }
     }
-    const uint2* ckIn = nullptr;  // this lane's rows in the checkpoint the segment starts from
-    if (b0 > 0) {
-      // the previous segment of this stripe (and of the stripe above: its last row is the diagonal input of lane 0) has
-      // stored that checkpoint; both tickets are a whole segment older
-      if (lane == 0) {
-        wait_ge(&a.finished[t - nPQ], 1, a.abort_flag);
-        if (hasPrev) wait_ge(&a.finished[tProd - nPQ], 1, a.abort_flag);
-      }
-      __syncwarp();
-      ckIn = a.ck + ((int64_t)q * kHotBlocks + (b0 >> hotShift)) * a.ckRows + (int64_t)g * R;
-    }
     const long long task0 = clock64();
     long long waitCyc = 0;
+    const int hotShift = a.hotShift[q];
+    const int ckBlkMask = (1 << hotShift) - 1;
     const int sj = a.gsubject[g];
     uint32_t best = 0, bestBlk = 0, outH = 0, outF = 0, diag = 0, curSel = kPadSel;
-    uint32_t nextSel = lane == 0 ? (uint32_t)sel[cFirst] : kPadSel;  // selector of this lane's next column, one step ahead
+    uint32_t nextSel = lane == 0 ? (uint32_t)sel[0] : kPadSel;  // selector of this lane's next column, one step ahead
     // 0/1 factors, made opaque so that they stay multiplications
     uint32_t keepSel = lane != 0, feedSel = lane == 0, keepHF = lane != 0 && !startFlag, feedHF = lane == 0 && !startFlag;
     asm volatile("" : "+r"(keepSel), "+r"(feedSel), "+r"(keepHF), "+r"(feedHF));
     unsigned long long nextRaw = 0;
-    if (hasPrev) nextRaw = ld_relaxed_u64(&bndIn[cFirst + lane]);
-    for (int b = b0; b < bEnd; b++) {
-      const bool drain = b == b1 && !lastSeg;  // columns beyond the segment: pad selectors, nothing is read from above
-      uint32_t selv = drain ? kPadSel : (uint32_t)sel[b * 32 + lane];
+    if (hasPrev) nextRaw = ld_relaxed_u64(&bndIn[lane]);
+    for (int b = 0; b < nBlocks; b++) {
+      uint32_t selv = sel[b * 32 + lane];
       unsigned long long raw = 0;
-      if (hasPrev && b < b1) {
+      if (hasPrev && b < qBlocks) {
         raw = nextRaw;
         if (!__all_sync(0xffffffffu, (raw & kTagMask) == tagIn)) {
           // the prefetch was too early: look again before deciding that the producer really is not ahead
@@ -312,7 +281,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           if (!__all_sync(0xffffffffu, (raw & kTagMask) == tagIn)) {
             const long long w0 = clock64();
             // caught up with the producer: sleep until it is kLag blocks ahead (hysteresis), then take block b
-            const int far = min(b + kLag, b1 - 1);
+            const int far = min(b + kLag, qBlocks - 1);
             unsigned ns = 128;
             bool dead = false;
             for (;;) {
@@ -333,29 +302,25 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
             }
             if (dead && lane == 0) {
               if (atomicExch(a.abort_flag, 1) == 0)
-                printf("[K1 watchdog] ticket %d (seg %d q %d pos %d stripe %d) block %d/%d waits on producer ticket %d slot %d tagIn %llx raw %llx far %d\n", t, seg, q, pos, k, b, b1, tProd, tProd % a.nslot, tagIn, raw & kTagMask, far);
+                printf("[K1 watchdog] ticket %d (q %d pos %d stripe %d) block %d/%d waits on producer ticket %d slot %d tagIn %llx raw %llx far %d\n", t, q, pos, k, b, qBlocks, tProd, tProd % a.nslot, tagIn, raw & kTagMask, far);
             }
             waitCyc += clock64() - w0;
           }
         }
         raw &= ~kTagMask;
-        if (b + 1 < b1) nextRaw = ld_relaxed_u64(&bndIn[(b + 1) * 32 + lane]);  // prefetch, validated next block
+        if (b + 1 < qBlocks) nextRaw = ld_relaxed_u64(&bndIn[(b + 1) * 32 + lane]);  // prefetch, validated next block
       }
       // lane l reaches column b*32 at step j == l; that column starts a checkpointed block iff b is a multiple of CB/32
-      // (the first block of a later segment starts FROM that checkpoint instead of storing it)
-      const bool ldBlock = b == b0 && b0 > 0;
-      const bool ckBlock = a.ck != nullptr && b > 0 && !ldBlock && (b & ckBlkMask) == 0 && b * 32 < Q;
+      const bool ckBlock = a.ck != nullptr && b > 0 && (b & ckBlkMask) == 0 && b * 32 < Q;
       __syncwarp();  // everyone is done reading the previous block's feed
       s_feed[wib][lane] = make_uint4(selv, (uint32_t)raw, (uint32_t)(raw >> 32), 0u);
-      if (lane == 0) s_feed[wib][32].x = (b + 1 < bEnd && !(b + 1 == b1 && !lastSeg)) ? (uint32_t)sel[(b + 1) * 32] : kPadSel;
+      if (lane == 0) s_feed[wib][32].x = b + 1 < nBlocks ? (uint32_t)sel[(b + 1) * 32] : kPadSel;
       __syncwarp();
-      // The 32 columns of the block.  MODE 1: this block starts a checkpointed column block (rare) -- a separate
-      // instantiation keeps the test out of the common loop.  MODE 2: first block of a later segment: the lane takes its
-      // state from the checkpoint when it reaches the block's first column (until then it idles over pad columns).
-      auto columns = [&](auto modeTag) {
-        constexpr int MODE = decltype(modeTag)::value;
-        constexpr int U = MODE == 2 ? 2 : kK1Unroll;
-#pragma unroll U
+      // The 32 columns of the block.  CK: this block starts a checkpointed column block (rare) -- a separate
+      // instantiation keeps the test out of the common loop.
+      auto columns = [&](auto ckTag) {
+        constexpr bool CK = decltype(ckTag)::value;
+#pragma unroll kK1Unroll
         for (int j = 0; j < 32; j++) {
           // the selector does not depend on the sweep: it is passed down the lanes one step AHEAD, so a step never starts
           // by waiting for a shuffle
@@ -370,23 +335,11 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           nextSel = inSel * keepSel + fdSelNext * feedSel;
           inH = inH * keepHF + fd.y * feedHF;
           inF = inF * keepHF + fd.z * feedHF;
-          if (MODE == 1 && j == lane) {
+          if (CK && j == lane) {
             // column checkpoint for the origin pass: the (H, E') this lane holds before it starts column b*32 = cb*CB
             uint2* dst = a.ck + ((int64_t)q * kHotBlocks + (b >> hotShift)) * a.ckRows + (int64_t)g * R;
 #pragma unroll
             for (int r = 0; r < R; r++) dst[r] = make_uint2(H[r], E[r]);
-          }
-          if (MODE == 2 && j == lane) {
-            // the state before column b0*32, as the previous segment left it; the diagonal input of the first row is the
-            // H of the row above (previous lane's last row, or the last row of the stripe above)
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-              const uint2 v = __ldcg(&ckIn[r]);
-              H[r] = v.x;
-              E[r] = v.y;
-            }
-            diag = (!startFlag && (lane > 0 || hasPrev)) ? __ldcg(&ckIn[-1]).x : 0u;
-            bestBlk = 0;
           }
           uint32_t hd = diag, f = inF, h = 0;
           diag = inH;
@@ -413,7 +366,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
             // lane 31 has just finished column c = b*32 + j - 31
             const int c = b * 32 + j - 31;
             if (lane == 31) s_out[wib][c & 31] = make_uint2(outH, outF);
-            if (c >= cFirst && (c & 31) == 31) {  // column block complete: one coalesced, tagged 64-bit store per lane
+            if (c >= 0 && (c & 31) == 31) {  // column block complete: one coalesced, tagged 64-bit store per lane
               __syncwarp();
               const uint2 o = s_out[wib][lane];
               st_relaxed_u64(&bndOut[(c & ~31) + lane],
@@ -423,14 +376,12 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           }
         }
       };
-      if (ldBlock)
-        columns(std::integral_constant<int, 2>{});
-      else if (ckBlock)
-        columns(std::integral_constant<int, 1>{});
+      if (ckBlock)
+        columns(std::true_type{});
       else
-        columns(std::integral_constant<int, 0>{});
+        columns(std::false_type{});
       // column-block bookkeeping for the origin pass: which blocks hold a cell >= minscore
-      if ((((b + 1) >> hotShift) != (b >> hotShift)) || b == bEnd - 1) {
+      if ((((b + 1) >> hotShift) != (b >> hotShift)) || b == nBlocks - 1) {
         if (sj >= 0) {
           // per-half compare bestBlk >= minscore
           const bool hf = (int)(int16_t)(bestBlk & 0xffffu) >= a.minscore;
@@ -457,7 +408,6 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
       if (f > 0) atomicMax(pb, f);
       if (rc > 0) atomicMax(pb + 1, rc);
     }
-    __threadfence();  // the checkpoint this ticket stored is read by the next segment's ticket after it sees `finished`
     __syncwarp();
     if (lane == 0) {
       st_release(&a.finished[t], 1);
