@@ -20,6 +20,7 @@
 //     libraries between stages does not re-pack them; residue codes are matrix-independent, so a matrix change (GC bins
 //     per batch, RepeatMasker:4784-4821) only rebuilds the 8-byte row profiles on the device.
 #include <signal.h>
+#include <sys/prctl.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
 #include <sys/un.h>
@@ -292,7 +293,7 @@ void on_signal(int) {
 }
 
 int usage() {
-  fprintf(stderr, "usage: rmgpu_server --socket PATH [--gpus all|0,1,...] [--max-batch N] [--linger-ms T]\n%s\n", rmgpu_version());
+  fprintf(stderr, "usage: rmgpu_server --socket PATH [--gpus all|0,1,...] [--max-batch N] [--linger-ms T] [--die-with-parent]\n%s\n", rmgpu_version());
   return 2;
 }
 
@@ -309,6 +310,11 @@ int main(int argc, char** argv) {
       g_maxBatch = std::max(1, atoi(argv[++a]));
     else if (!strcmp(argv[a], "--linger-ms") && a + 1 < argc)
       g_lingerMs = atof(argv[++a]);
+    else if (!strcmp(argv[a], "--die-with-parent")) {
+      // started by GpuSearchEngine.pm: never outlive the RepeatMasker run that owns this worker
+      prctl(PR_SET_PDEATHSIG, SIGTERM);
+      if (getppid() == 1) return 0;
+    }
     else
       return usage();
   }

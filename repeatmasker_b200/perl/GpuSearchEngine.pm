@@ -117,7 +117,7 @@ sub _ensureServer {
   return unless ( defined $pid );
   if ( $pid == 0 ) {
     open( STDERR, ">", "/dev/null" ) unless ( $ENV{'RMGPU_SERVER_LOG'} );
-    exec( $bin, "--socket", $sock, "--gpus", $gpus ) or exit( 1 );
+    exec( $bin, "--socket", $sock, "--gpus", $gpus, "--die-with-parent" ) or exit( 1 );
   }
   for ( my $i = 0 ; $i < 400 ; $i++ ) {
     last if ( -S $sock && RMGpu::server_ping( $sock ) == 0 );
