@@ -83,6 +83,12 @@ int g_listen = -1;
 int g_maxBatch = 32;
 int g_maxResident = 4;
 double g_lingerMs = 0.0;
+FILE* g_trace = nullptr;  // --trace FILE: one line per pass (unix time of start and end, GPU, calls, records, hits)
+std::mutex g_traceMu;
+
+double unix_now() {
+  return std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
+}
 
 std::string file_key(const std::string& path) {
   struct stat st;
@@ -122,6 +128,7 @@ void run_group(Worker* w, std::vector<std::shared_ptr<Request>>& group) {
   Request& first = *group[0];
   int rc = 0;
   std::string err;
+  const double t0 = unix_now();
   Resident* res = nullptr;
   for (auto& r : w->resident)
     if (r.libKey == first.libKey) res = &r;
@@ -184,6 +191,12 @@ void run_group(Worker* w, std::vector<std::shared_ptr<Request>>& group) {
     r.err = err;
     r.done = true;
     r.cv.notify_all();
+  }
+  if (g_trace) {
+    std::lock_guard<std::mutex> lk(g_traceMu);
+    fprintf(g_trace, "%.3f %.3f gpu %d calls %zu records %d hits %d rc %d\n", t0, unix_now(), w->device, group.size(),
+            (int)firstRecord[group.size()], out ? out->n_hits : 0, rc);
+    fflush(g_trace);
   }
   if (out) rmgpu_free(out);
   w->served += (long)group.size();
@@ -293,7 +306,7 @@ void on_signal(int) {
 }
 
 int usage() {
-  fprintf(stderr, "usage: rmgpu_server --socket PATH [--gpus all|0,1,...] [--max-batch N] [--linger-ms T] [--die-with-parent]\n%s\n", rmgpu_version());
+  fprintf(stderr, "usage: rmgpu_server --socket PATH [--gpus all|0,1,...] [--max-batch N] [--linger-ms T] [--trace FILE] [--die-with-parent]\n%s\n", rmgpu_version());
   return 2;
 }
 
@@ -310,6 +323,8 @@ int main(int argc, char** argv) {
       g_maxBatch = std::max(1, atoi(argv[++a]));
     else if (!strcmp(argv[a], "--linger-ms") && a + 1 < argc)
       g_lingerMs = atof(argv[++a]);
+    else if (!strcmp(argv[a], "--trace") && a + 1 < argc)
+      g_trace = fopen(argv[++a], "a");
     else if (!strcmp(argv[a], "--die-with-parent")) {
       // started by GpuSearchEngine.pm: never outlive the RepeatMasker run that owns this worker
       prctl(PR_SET_PDEATHSIG, SIGTERM);

@@ -284,15 +284,17 @@ class Server:
     While it is open, RMGPU_SERVER points at it, so rmgpu_search() / search_files() / GpuSearchEngine.search() in this
     process and in its children run as thin clients."""
 
-    def __init__(self, socket_path, gpus=(0,)):
-        self.socket_path, self.gpus, self.proc, self._old = socket_path, list(gpus), None, None
+    def __init__(self, socket_path, gpus=(0,), trace=None):
+        self.socket_path, self.gpus, self.proc, self._old, self.trace = socket_path, list(gpus), None, None, trace
 
     def __enter__(self):
         import subprocess
         import time
 
-        self.proc = subprocess.Popen([SERVER_BIN, "--socket", self.socket_path, "--gpus", ",".join(map(str, self.gpus))],
-                                     stderr=subprocess.PIPE, text=True)
+        argv = [SERVER_BIN, "--socket", self.socket_path, "--gpus", ",".join(map(str, self.gpus))]
+        if self.trace:
+            argv += ["--trace", self.trace]
+        self.proc = subprocess.Popen(argv, stderr=subprocess.PIPE, text=True)
         for _ in range(200):
             if os.path.exists(self.socket_path) and lib().rmgpu_server_ping(self.socket_path.encode()) == 0:
                 break

@@ -27,7 +27,9 @@ while left > 0:  # generated 1 Mbp at a time, one sequence in the end
 genome = "".join(parts)
 synth.write_fasta(os.path.join(d, "lib.fa"), snames, sseqs)
 synth.write_fasta(os.path.join(d, "genome.fa"), ["synth0"], [genome], width=60)
-with engine.Server(os.path.join(d, "rmgpu.sock"), gpus=[int(x) for x in a.server_gpus.split(",")]) as srv:
+trace = os.path.join(d, "passes.txt")
+with engine.Server(os.path.join(d, "rmgpu.sock"), gpus=[int(x) for x in a.server_gpus.split(",")], trace=trace) as srv:
+    t_unix0 = time.time()
     cmd = f"source {H}/env.sh && cd {d} && perl $RM_HOME/RepeatMasker -engine gpu -lib lib.fa -gc 41 -pa {a.pa} {a.extra} genome.fa"
     t0 = time.perf_counter()
     res = subprocess.run(["bash", "-c", cmd], capture_output=True, text=True)
@@ -41,6 +43,18 @@ nN = sum(l.count("N") for l in masked.splitlines() if not l.startswith(">"))
 print(f"RepeatMasker -engine gpu -pa {a.pa} {a.extra}: {len(genome)} bp x {len(sseqs)} families: wall {wall:.1f} s, {len(out) - 3} annotation lines, "
       f"{100.0 * nN / len(genome):.1f} % masked")
 print("\n".join(l for l in (srv.log or "").splitlines() if "served" in l))
+if os.path.exists(trace):
+    # where the run's wall time goes: before the first search reaches a GPU (FastaDB index, batching), while searches are
+    # in flight, after the last one (ProcessRepeats, masking); busy = per-GPU sum of the passes' durations
+    P = [l.split() for l in open(trace)]
+    if P:
+        st, en = [float(x[0]) for x in P], [float(x[1]) for x in P]
+        busy = {}
+        for x in P:
+            busy[x[3]] = busy.get(x[3], 0.0) + float(x[1]) - float(x[0])
+        print(f"phases: {min(st) - t_unix0:.1f} s before the first search, {max(en) - min(st):.1f} s with searches in flight, "
+              f"{t_unix0 + wall - max(en):.1f} s after the last one; {len(P)} passes; GPU busy " +
+              ", ".join(f"gpu{g} {b:.1f} s" for g, b in sorted(busy.items())))
 print(open(os.path.join(d, "genome.fa.tbl")).read()[:700])
 if a.also_crossmatch:
     d2 = tempfile.mkdtemp()
