@@ -1377,16 +1377,22 @@ void rmgpu_session::run_traceback(const rmgpu_params& p, const std::vector<Candi
       st.d2h_bytes += (int64_t)nC * 4;
       static const bool dbgK3 = getenv("RMGPU_DEBUG_K3") != nullptr;
       if (dbgK3) {
-        int maxN = 0, failed = 0;
-        int64_t maxBand = 0, longBand = 0;
+        int maxN = 0, failed = 0, second = 0;
+        int64_t maxBand = 0, longBand = 0, cells = 0, rows = 0;
+        std::vector<int32_t> hst(nC);
+        CUDA_CHECK(cudaMemcpy(hst.data(), d_status.p, nC * sizeof(int32_t), cudaMemcpyDeviceToHost));
         for (auto& t : tc) {
           const int n = t.i1 - t.i0 + 1;
           if (n > maxN) maxN = n, longBand = band_of(t.id);
           maxBand = std::max(maxBand, band_of(t.id));
           failed += hlen[t.id] <= 0;
+          second += hst[t.id] > 1;
+          cells += (int64_t)n * band_of(t.id);
+          rows += n;
         }
-        fprintf(stderr, "[K3 dbg] %s launch: %zu candidates, %.2f ms, longest %d rows (band %lld), widest band %lld, %d to retry, dir bytes %.1f MB\n",
-                wide ? "block" : "warp", tc.size(), tm.ms(), maxN, (long long)longBand, (long long)maxBand, failed, dirTot / 1e6);
+        fprintf(stderr, "[K3 dbg] %s launch: %zu candidates, %.2f ms, longest %d rows (band %lld), widest band %lld, %d to retry, %d needed the doubled band, "
+                "%.1f M band cells, %lld rows, dir bytes %.1f MB\n",
+                wide ? "block" : "warp", tc.size(), tm.ms(), maxN, (long long)longBand, (long long)maxBand, failed, second, cells / 1e6, (long long)rows, dirTot / 1e6);
       }
       for (auto& t : tc) {
         const int id = t.id;

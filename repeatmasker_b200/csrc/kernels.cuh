@@ -1217,6 +1217,95 @@ constexpr int kTraceBlockBand = 2048;  // ints per array in block mode
 constexpr int kTraceSeqBlock = 10240;  // query / subject bytes of a candidate staged in shared memory (block mode)
 constexpr int kTraceSeqWarp = 1024;    // the same per warp in warp mode
 
+// The wave loop of traceback_kernel when the band fits the shared buffer.  One cell of each parity per thread and step
+// (J such pairs when the band is wider than the team): pair l owns k = 2l (wave 2s) and k = 2l + 1 (wave 2s + 1), which share their subject column
+// v = s - l - dlo and whose query rows are u = s + l and s + l + 1.  Even k live in slots [0, half), slot `half` is
+// a guard, odd k in [half + 1, half + 1 + bw/2), then a second guard: the neighbours outside the band read NEGI from
+// the guards (never written), so a wave is 5 shared loads, the recurrence, 3 stores and one direction byte.  The
+// substitution scores of step s + 1 are looked up during step s (they do not depend on the band), off the chain
+// load -> recurrence -> store -> barrier that bounds a candidate.
+template <int J, class Sync>
+__device__ __forceinline__ void paired_waves(int32_t* Hb, int32_t* Eb, int32_t* Fb, const uint8_t* qc, const uint8_t* sc,
+                                             const int32_t* smat, uint8_t* dir, int n, int m, int dlo, int bw, int tid, int T,
+                                             int gi, int ie, int de, Sync team_sync) {
+  constexpr int NEGI = -(1 << 28);
+  const int half = (bw + 1) >> 1;
+  const int sLo = (3 - bw) >> 1;  // floor: wave 2 sLo may be one before the first useful one
+  auto qat = [&](int u) { return (int)qc[min(max(u, 1), n) - 1]; };       // residue of query row u (clamped)
+  auto sat = [&](int v) { return (int)sc[min(max(v, 1), m) - 1] * 16; };  // score row of subject column v
+  // pair j of this thread: slot l = tid + j T, cells k = 2l and 2l + 1
+  int qo[J], se[J], so[J];
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int l = tid + j * T, ue = sLo + l, v = sLo - l - dlo;
+    qo[j] = qat(ue + 1);
+    se[j] = smat[sat(v) + qat(ue)];
+    so[j] = smat[sat(v) + qo[j]];
+  }
+  int64_t dE = (int64_t)(sLo + tid) * bw + 2 * tid;  // direction byte of pair 0's even cell
+  const int64_t dJ = (int64_t)T * (bw + 2);          // from one pair of the thread to the next
+  for (int s = sLo; s <= n; s++, dE += bw) {
+    int sen[J], qn[J], srn[J];
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      const int l = tid + j * T, ue = s + l, v = s - l - dlo;
+      // next step: rows ue + 1 (even; the odd cell's residue now) and ue + 2, column v + 1
+      qn[j] = qat(ue + 2);
+      srn[j] = sat(v + 1);
+      if (2 * l < bw && (unsigned)(ue - 1) < (unsigned)n) {
+        int32_t *He = Hb + l, *Ee = Eb + l, *Fe = Fb + l;
+        const int32_t *Ho = Hb + half + 1 + l, *Eo = Eb + half + 1 + l, *Fo = Fb + half + 1 + l;
+        int hnew = NEGI, enew = NEGI, fnew = NEGI;
+        if ((unsigned)(v - 1) < (unsigned)m) {
+          const int el = Eo[-1], hl = Ho[-1], fr = Fo[0], hr = Ho[0], hd = He[0];
+          const int e_ext = el + ie, e_open = hl + gi, f_ext = fr + de, f_open = hr + gi;
+          uint32_t bits = (e_ext >= e_open ? 4u : 0u) | (f_ext >= f_open ? 8u : 0u);
+          enew = max(max(e_ext, e_open), NEGI);
+          fnew = max(max(f_ext, f_open), NEGI);
+          // (1,1) needs no special case here: its E and F sources are row 0 / column 0, NEGI, and the clamp above
+          // gives exactly the NEGI the generic loop below assigns
+          const int D = hd + se[j];
+          hnew = max(max(enew, fnew), max(D, NEGI));
+          bits |= D > max(enew, fnew) ? 3u : (fnew > enew ? 2u : 1u);
+          dir[dE + j * dJ] = (uint8_t)bits;
+        }
+        He[0] = hnew;
+        Ee[0] = enew;
+        Fe[0] = fnew;
+      }
+      sen[j] = smat[srn[j] + qo[j]];
+    }
+    team_sync();
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      const int l = tid + j * T, ue = s + l, v = s - l - dlo;
+      if (2 * l + 1 < bw && (unsigned)ue < (unsigned)n) {  // u = ue + 1
+        const int32_t *He = Hb + l, *Ee = Eb + l, *Fe = Fb + l;
+        int32_t *Ho = Hb + half + 1 + l, *Eo = Eb + half + 1 + l, *Fo = Fb + half + 1 + l;
+        int hnew = NEGI, enew = NEGI, fnew = NEGI;
+        if ((unsigned)(v - 1) < (unsigned)m) {
+          const int el = Ee[0], hl = He[0], fr = Fe[1], hr = He[1], hd = Ho[0];
+          const int e_ext = el + ie, e_open = hl + gi, f_ext = fr + de, f_open = hr + gi;
+          uint32_t bits = (e_ext >= e_open ? 4u : 0u) | (f_ext >= f_open ? 8u : 0u);
+          enew = max(max(e_ext, e_open), NEGI);
+          fnew = max(max(f_ext, f_open), NEGI);
+          const int D = hd + so[j];
+          hnew = max(max(enew, fnew), max(D, NEGI));
+          bits |= D > max(enew, fnew) ? 3u : (fnew > enew ? 2u : 1u);
+          dir[dE + j * dJ + bw + 1] = (uint8_t)bits;
+        }
+        Ho[0] = hnew;
+        Eo[0] = enew;
+        Fo[0] = fnew;
+      }
+      so[j] = smat[srn[j] + qn[j]];
+      se[j] = sen[j];
+      qo[j] = qn[j];
+    }
+    team_sync();
+  }
+}
+
 template <bool BLOCK>
 __global__ void __launch_bounds__(BLOCK ? kTraceBlockThreads : kTraceWarps * 32) traceback_kernel(TraceArgs a) {
   constexpr int SB = BLOCK ? kTraceBlockBand : kTraceWarpBand;
@@ -1259,15 +1348,19 @@ __global__ void __launch_bounds__(BLOCK ? kTraceBlockThreads : kTraceWarps * 32)
     const int dlo = min(0, n - m) - W, dhi = max(0, n - m) + W;
     const int bw = dhi - dlo + 1;
     const int half = (bw + 1) >> 1;
-    // team: one thread per cell of a wave, whole warps
-    const int T = BLOCK ? min(kTraceBlockThreads, max(32, (half + 31) & ~31)) : 32;
+    // paired waves (paired_waves above) when the band plus two guard slots fits the shared buffer: then every thread has
+    // pairsPer (1, 2 or 4) cells of each parity; values further than 2^27 from NEGI cannot occur below 2^20 rows
+    const bool paired = bw + 2 <= SB && n < (1 << 20);
+    const int pairsPer = !paired ? 1 : BLOCK ? (half + kTraceBlockThreads - 1) / kTraceBlockThreads : (half <= 32 ? 1 : half <= 64 ? 2 : 4);
+    // team: one thread per cell (pairsPer cells) of a wave, whole warps
+    const int T = BLOCK ? min(kTraceBlockThreads, max(32, ((half + pairsPer - 1) / pairsPer + 31) & ~31)) : 32;
     auto team_sync = [&]() {
       if (BLOCK)
         asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
       else
         __syncwarp();
     };
-    auto ix = [&](int k) { return (k >> 1) + ((k & 1) ? half : 0); };
+    auto ix = [&](int k) { return (k >> 1) + ((k & 1) ? half + (paired ? 1 : 0) : 0); };
     int32_t *Hb, *Eb, *Fb;
     if (bw <= SB) {
       Hb = sband[wib][0];
@@ -1285,7 +1378,32 @@ __global__ void __launch_bounds__(BLOCK ? kTraceBlockThreads : kTraceWarps * 32)
         Eb[ix(k)] = NEGI;
         Fb[ix(k)] = NEGI;
       }
+      if (paired && tid == 0) {  // the two guard slots: never written, read as the neighbour outside the band
+        const int g0 = half, g1 = half + 1 + (bw >> 1);
+        Hb[g0] = Eb[g0] = Fb[g0] = NEGI;
+        Hb[g1] = Eb[g1] = Fb[g1] = NEGI;
+      }
       team_sync();
+      if (paired) {
+        // the band is in shared memory here; calling with the arrays themselves (and with the staged residues when
+        // they are) lets the compiler emit shared-memory loads instead of generic ones
+        const bool staged = qc == sseq[wib][0];
+#define RMGPU_PAIRED(JJ)                                                                                                   \
+  if (staged)                                                                                                              \
+    paired_waves<JJ>(sband[wib][0], sband[wib][1], sband[wib][2], sseq[wib][0], sseq[wib][1], smat, dir, n, m, dlo, bw, tid, \
+                     T, a.gap_init, a.ins_ext, a.del_ext, team_sync);                                                      \
+  else                                                                                                                     \
+    paired_waves<JJ>(sband[wib][0], sband[wib][1], sband[wib][2], qc, sc, smat, dir, n, m, dlo, bw, tid, T, a.gap_init,      \
+                     a.ins_ext, a.del_ext, team_sync);
+        if (pairsPer == 1) {
+          RMGPU_PAIRED(1)
+        } else if (pairsPer == 2) {
+          RMGPU_PAIRED(2)
+        } else {
+          RMGPU_PAIRED(4)
+        }
+#undef RMGPU_PAIRED
+      } else
       // waves: u >= 1, 0 <= k < bw  ->  w = 2u - k in [3 - bw, 2n]
       for (int w = 3 - bw; w <= 2 * n; w++) {
         // only k with 1 <= (w + k) / 2 <= n matter: k in [2 - w, 2n - w]

@@ -143,6 +143,29 @@ def test_int16_overflow_at_both_ends_of_the_query(tmp_path):
     assert_same_hits(got, want)
 
 
+def test_traceback_band_retries(tmp_path):
+    """Alignments whose path leaves the first traceback band W = bandwidth + max(n, m) / 32 (an insertion and, further
+    on, a deletion of the same size: the end points stay on the main diagonal, the path does not) are found with the
+    doubled or quadrupled band; both teams of the traceback kernel (one warp, a block), with one, two and -- in the
+    block team -- more cells per thread and wave, and the host-side reschedule after two failed widths."""
+    rng = np.random.default_rng(4242)
+    snames, sseqs, parts = [], [], []
+    # (subject length, excursion): W = 14 + L/32; the excursion decides how many doublings are needed
+    for i, (L, ex) in enumerate([(400, 40), (700, 60), (1100, 110), (3000, 150), (6000, 300), (8000, 400), (8000, 600), (5000, 700)]):
+        sq = synth.random_dna(rng, L).tobytes().decode()
+        snames.append(f"fam{i}#DNA/x")
+        sseqs.append(sq)
+        a, b = L // 3, 2 * L // 3
+        ins = synth.random_dna(rng, ex).tobytes().decode()
+        cp = synth.mutate(rng, sq[:a], 0.03, 0.0) + ins + synth.mutate(rng, sq[a:b], 0.03, 0.0) + synth.mutate(rng, sq[b + ex:], 0.03, 0.0)
+        parts.append(synth.random_dna(rng, 300).tobytes().decode() + (cp if i % 2 == 0 else synth.revcomp(cp)))
+    q = "".join(parts) + synth.random_dna(rng, 300).tobytes().decode()
+    got, want, st = both(tmp_path, ["q1"], [q], snames, sseqs)
+    # the flanks outscore the two gaps: each copy is one alignment through both
+    assert sum(h["qend"] - h["qstart"] > 0.9 * len(sseqs[int(h["sname"][3])]) for h in want) >= 6
+    assert_same_hits(got, want)
+
+
 def test_library_packing_edge_lengths(tmp_path):
     """Subject lengths around the packing units (16-row groups, 512-row stripes, 4-stripe runs): subjects that end
     exactly on a group / stripe / run boundary, one-base and 15-base subjects, a subject longer than a run whose last
