@@ -222,7 +222,7 @@ struct rmgpu_session {
   DevBuf<int32_t> d_pairbest;
   DevBuf<unsigned long long> d_hotmask;
   DevBuf<int32_t> d_hotShift;
-  DevBuf<unsigned long long> d_dbg;
+  DevBuf<unsigned long long> d_dbg, d_dbgC, d_pbest;
   DevBuf<int> d_abort, d_leftFlag;
   // second stream + scratch of the stripe-pipeline fallback, which runs concurrently with the block-parallel path
   cudaStream_t stream2 = nullptr;
@@ -882,10 +882,14 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)numSMs * blocksPerSM, ((int64_t)nTickets + 3) / 4));
     const int warps = grid * 4;
     // a slot's reader is at most one level (blockLevelWidth tickets) after its writer
-    const int nslot = (int)std::min<int64_t>(nTickets, std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)blockLevelWidth + 2));
     int64_t maxW = 0;
     for (auto& t : tasks) maxW = std::max<int64_t>(maxW, t.c1 - t.c0);
     const int64_t bndStride = ((maxW + 31) >> 5) * 32 + 32;
+    // ... but a boundary is only one column block wide (9 KB): up to 2 GB of ring every ticket simply keeps its own slot,
+    // and no ticket ever waits for the reader of an older one
+    const int64_t slotBytes = bndStride * (int64_t)sizeof(OriginBoundary);
+    const int nslot = (int)std::min<int64_t>(
+        nTickets, std::max<int64_t>(std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)blockLevelWidth + 2), (2ll << 30) / slotBytes));
     size_t tableSize = 1u << 23;  // first-level table (task, relative or pseudo origin): kept very sparse, probing is atomics
     for (;;) {
       const size_t ftableSize = tableSize >> 6;  // final table (triple, origin): the only one downloaded
@@ -925,6 +929,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       a.vals = d_vals.ensure(tableSize);
       a.tableMask = (uint32_t)tableSize - 1;
       a.overflow = d_overflow.ensure(1);
+      a.pbest = d_pbest.ensure((size_t)std::max<int64_t>(snapTot, 1));
+      CUDA_CHECK(cudaMemsetAsync(a.pbest, 0, (size_t)std::max<int64_t>(snapTot, 1) * 8, stream));
       a.dbg = nullptr;
       if (dbgK2) {
         a.dbg = d_dbg.ensure(72);
@@ -939,6 +945,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       CUDA_CHECK(cudaMemsetAsync(a.overflow, 0, sizeof(int), stream));
       ResolveArgs r;
       r.tasks = d_btasks.p;
+      r.nTasks = (int)tasks.size();
+      r.pbest = a.pbest;
       r.slen = d_slen.p;
       r.snap = a.snap;
       r.keys = a.keys;
@@ -982,6 +990,16 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         fprintf(stderr, "[K2 dbg] blocks: mean ticket %.0f cyc, producer-wait %.1f%% of ticket cycles, slot-wait %.2e cyc, warps busy until exit: mean %.1f%% of the last warp's (%.2f ms), levels %d, widest level %d\n",
                 (double)d[3] / (double)std::max(d[2], 1ull), 100.0 * (double)d[0] / (double)std::max(d[3], 1ull), (double)d[1],
                 100.0 * (double)d[4] / ((double)warps * (double)std::max(d[5], 1ull)), (double)d[5] * 1e-6, maxStripes, blockLevelWidth);
+        {
+          const int tk = (int)(d[6] & 0xFFFFFF);
+          const BlockTask& bt = tasks[ticketTask[tk]];
+          int tasksOfTriple = 0;
+          for (auto& t2 : tasks) tasksOfTriple += t2.triple == bt.triple;
+          fprintf(stderr, "[K2 dbg] blocks: slowest ticket %d of %d: %.0f kcyc, %.0f kcyc waiting for its producer; stripe %d of %d, columns [%d, %d), subject %d (%zu rows), "
+                  "triple with %d tasks, K1 best %d\n", tk, nTickets, (double)(d[6] >> 44) * 1.024, (double)((d[6] >> 24) & 0xFFFFF) * 1.024, ticketStripe[tk], bt.nStripes,
+                  bt.c0, bt.c1, bt.subject, lib.seqs[bt.subject].size(), tasksOfTriple,
+                  pairbest[((size_t)bt.q * nS + bt.subject) * 2 + bt.strand]);
+        }
       }
       st.launches += 2;
       st.d2h_bytes += (int64_t)ftableSize * 16;
@@ -1129,6 +1147,10 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         a.overflow = d_overflowC.ensure(1);
         a.abort_flag = d_abortC.ensure(1);
         a.dbg = nullptr;
+        if (dbgK2) {
+          a.dbg = d_dbgC.ensure(8);
+          CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 64, stream2));
+        }
         a.ck = d_ck.p;
         a.leftFlag = d_leftFlagC.ensure(tasks.size());
         CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream2));
@@ -1160,9 +1182,16 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         CUDA_CHECK(cudaStreamSynchronize(stream2));
         check_abort_on("K2", a.abort_flag, stream2);
         chainMs += tm.ms();
-        if (dbgK2)
-          fprintf(stderr, "[K2 dbg] chain: %zu triples %d tickets R=%d grid %d round %d  kernel %.2f ms (done at +%.2f ms)\n", trIdx.size(),
-                  nTickets, chainR, grid, round, tm.ms(), now_ms() - k2t0);
+        if (dbgK2) {
+          unsigned long long d[8];
+          CUDA_CHECK(cudaMemcpy(d, a.dbg, 64, cudaMemcpyDeviceToHost));
+          int64_t cols = 0, maxCols = 0, maxStr = 0;
+          for (auto& t : tasks) cols += t.c1 - t.c0, maxCols = std::max<int64_t>(maxCols, t.c1 - t.c0), maxStr = std::max<int64_t>(maxStr, t.nStripes);
+          fprintf(stderr, "[K2 dbg] chain: %zu triples %d tickets R=%d grid %d round %d  kernel %.2f ms (done at +%.2f ms); window columns mean %.0f max %lld, "
+                  "most stripes %lld; mean ticket %.0f cyc, producer-wait %.1f%%, slot-wait %.1f%% of ticket cycles\n", trIdx.size(),
+                  nTickets, chainR, grid, round, tm.ms(), now_ms() - k2t0, (double)cols / std::max<size_t>(tasks.size(), 1), (long long)maxCols, (long long)maxStr,
+                  (double)d[3] / std::max<double>((double)d[2], 1), 100.0 * d[1] / std::max<double>((double)d[3], 1), 100.0 * d[0] / std::max<double>((double)d[3], 1));
+        }
         chainLaunches += 1;
         chainD2H += (int64_t)tableSize * 16;
         if (overflow) {
@@ -1227,6 +1256,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     chainLaunched.store(1);
   });
   std::exception_ptr blockErr;
+  static const bool serialK2 = getenv("RMGPU_K2_SERIAL") != nullptr;  // measurement: the two paths one after the other
+  if (serialK2 && chainThread.joinable()) chainThread.join();
   try {
     run_blocks(blockTr, false, redo);
     if (!redo.empty()) {

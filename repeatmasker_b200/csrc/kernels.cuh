@@ -23,7 +23,7 @@ constexpr int kPadClass = 7;            // residue class whose score is very neg
 constexpr uint32_t kPadSel = 0xF7F7u;   // PRMT selector picking class 7 for both strands (sign-replicated)
 constexpr int kWarp = 32;
 constexpr int kLag = 4;                 // blocks of slack a K1 consumer stripe rebuilds whenever it catches its producer
-constexpr int kLagSweep = 2;            // the same for the latency-bound int32 sweeps of K2, whose pipelines are ~100
+constexpr int kLagSweep = 1;            // the same for the latency-bound int32 sweeps of K2, whose pipelines are ~100
                                         // stripes deep: their fill time is lag x depth
 constexpr int kHotWords = 2;                // 64-bit words of a hot mask
 constexpr int kHotBlocks = 64 * kHotWords;  // column blocks per query record = hot-mask bits = K1 column checkpoints
@@ -585,11 +585,13 @@ __device__ __forceinline__ OriginCell origin_cell(int hl, uint32_t ol, int hu, u
   const bool c2 = d > h;
   h = max(h, d);
   o = c2 ? odd : o;
-  const bool pos = h > 0;
+  // a cell that is not positive keeps whatever origin the selects left in it: nothing ever reads it (the diagonal
+  // restarts from `fresh` when hd <= 0, and an E or F opened from H = 0 is negative and never wins a positive cell);
+  // viaDiag is only meaningful for h >= minscore >= 1
   OriginCell r;
   r.h = max(h, 0);
-  r.o = pos ? o : 0u;
-  r.viaDiag = c2 && pos;
+  r.o = o;
+  r.viaDiag = c2;
   return r;
 }
 
@@ -824,7 +826,8 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
           }
           if (c >= 0 && (c & 31) == 31) {
             *reinterpret_cast<int4*>(&bndOut[(c & ~31) + lane]) = make_int4(wb.h, wb.f, (int)wb.oh, (int)wb.of);
-            __threadfence();
+            // the warp barrier orders every lane's store before lane 0's release store, and a release is cumulative:
+            // no fence of its own per lane (a MEMBAR.SC.GPU per 32 columns on the chain's critical path)
             __syncwarp();
             if (lane == 0) st_release(&a.progress[t], (c >> 5) + 1);
           }
@@ -892,10 +895,11 @@ struct BlockArgs {
   int* abort_flag;
   uint32_t* snap;
   int* ticket;
-  unsigned long long* keys;    // (task << 32 | task-relative or pseudo origin) -> best end
+  unsigned long long* keys;    // (task << 32 | task-relative origin) -> best end
   unsigned long long* vals;
   uint32_t tableMask;
   int* overflow;
+  unsigned long long* pbest;   // best end per PSEUDO origin, dense, laid out like snap: [snapOff + (E ? L : 0) + row]
   unsigned long long* dbg;     // optional [8]: producer-wait cycles, slot-wait cycles, tickets, ticket cycles, sum and max of
                                // (warp exit - first warp start) in ns, -, time base
 };
@@ -1051,12 +1055,19 @@ __global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
             for (int r = 0; r < R; r++)
               if (ends & (1u << r)) {
                 const unsigned long long val = cand_val(H[r], i1, row0 + r + 1);
-                if (oH[r] == lastOrigin) {
+                const uint32_t o = oH[r];
+                if (o & kPseudoBit) {
+                  // a path that entered through the left edge: one dense slot per boundary cell and a reduction that
+                  // returns nothing.  (To the right of a high-scoring alignment its decaying fan crosses the edge in
+                  // thousands of rows, each with its own pseudo origin: through the hash table every such end was a
+                  // compare-and-swap round trip to L2, and those tickets ran 15x longer than the others.)
+                  atomicMax(&a.pbest[tk.snapOff + ((o & kPseudoEBit) ? L : 0) + (int64_t)((o & 0xFFFFFu) - 1u)], val);
+                } else if (o == lastOrigin) {
                   lastVal = val > lastVal ? val : lastVal;
                 } else {
                   if (lastOrigin != 0xFFFFFFFFu)
                     table_emit(a.keys, a.vals, a.tableMask, a.overflow, ((unsigned long long)(uint32_t)ti << 32) | lastOrigin, lastVal);
-                  lastOrigin = oH[r];
+                  lastOrigin = o;
                   lastVal = val;
                 }
               }
@@ -1082,8 +1093,7 @@ __global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
           if (c >= 0 && (c & 31) == 31) {  // a block of 32 columns is complete: one coalesced store, then publish it
             __syncwarp();
             *reinterpret_cast<int4*>(&bndOut[(c & ~31) + lane]) = s_out[wib][lane];
-            __threadfence();
-            __syncwarp();
+            __syncwarp();  // (orders the lanes' stores before lane 0's cumulative release, see swg_origin_kernel)
             if (lane == 0) st_release(&a.progress[t], (c >> 5) + 1);
           }
         }
@@ -1098,6 +1108,9 @@ __global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
         atomicAdd(&a.dbg[0], (unsigned long long)waitCyc);
         atomicAdd(&a.dbg[2], 1ull);
         atomicAdd(&a.dbg[3], (unsigned long long)(clock64() - tk0));
+        // the slowest ticket: duration and producer wait in units of 1024 cycles, and which ticket it was
+        atomicMax(&a.dbg[6], ((unsigned long long)((clock64() - tk0) >> 10) << 44) | ((unsigned long long)((waitCyc >> 10) & 0xFFFFF) << 24) |
+                                 (unsigned long long)(t & 0xFFFFFF));
         // per stripe level (first 64): when its last ticket ended, relative to the first warp's start
         if (st < 64) atomicMax(&a.dbg[8 + st], globaltimer_ns() - *(volatile unsigned long long*)&a.dbg[7]);
       }
@@ -1115,11 +1128,13 @@ __global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
 // the triple for a redo with all blocks.
 struct ResolveArgs {
   const BlockTask* tasks;
+  int nTasks;
   const int32_t* slen;
   const uint32_t* snap;
   const unsigned long long* keys;
   const unsigned long long* vals;
   uint32_t tableSize;
+  const unsigned long long* pbest;  // dense bests of the pseudo origins (BlockArgs::pbest)
   unsigned long long* fkeys;   // (triple << 40 | i0 << 20 | j0)
   unsigned long long* fvals;
   uint32_t fmask;
@@ -1128,40 +1143,56 @@ struct ResolveArgs {
   int verbose;
 };
 
+__device__ __forceinline__ void resolve_one(const ResolveArgs& a, const int t0, const uint32_t o0, const unsigned long long val) {
+  int t = t0;
+  uint32_t o = o0;
+  const int triple = a.tasks[t].triple;
+  const int L = a.slen[a.tasks[t].subject];
+  bool ok = true;
+  for (int guard = 0; (o & kPseudoBit) && guard < 128; guard++) {
+    const int pt = a.tasks[t].prevTask;
+    if (pt < 0) {
+      ok = false;
+      break;
+    }
+    const uint32_t row = o & 0xFFFFFu;  // 1-based
+    const bool isE = o & kPseudoEBit;
+    o = a.snap[a.tasks[pt].snapOff + (isE ? L : 0) + (row - 1)];
+    t = pt;
+    if (o == 0) {
+      ok = false;
+      break;
+    }
+  }
+  if (!ok || (o & kPseudoBit)) {
+    if (atomicExch(&a.redo[triple], 1) == 0 && a.verbose)
+      printf("[resolve] triple %d: task %d (c0 %d) origin %x -> stuck at task %d (c0 %d prev %d) o %x val %llx\n", triple, t0, a.tasks[t0].c0, o0, t,
+             a.tasks[t].c0, a.tasks[t].prevTask, o, val);
+    return;
+  }
+  const uint32_t Lp1 = (uint32_t)L + 1u;
+  const unsigned long long i0 = (unsigned long long)(o / Lp1) + (unsigned long long)a.tasks[t].c0;
+  const unsigned long long j0 = o % Lp1;
+  table_emit(a.fkeys, a.fvals, a.fmask, a.overflow, ((unsigned long long)(uint32_t)triple << 40) | (i0 << 20) | j0, val);
+}
+
 __global__ void resolve_candidates_kernel(ResolveArgs a) {
+  // ends whose origin lies inside their own task (hash table) ...
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < a.tableSize; s += gridDim.x * blockDim.x) {
     const unsigned long long key = a.keys[s];
     if (key == kEmptyKey) continue;
-    int t = (int)(key >> 32);
-    uint32_t o = (uint32_t)key;
-    const int triple = a.tasks[t].triple;
+    resolve_one(a, (int)(key >> 32), (uint32_t)key, a.vals[s]);
+  }
+  // ... and ends of paths that entered their task through its left edge (dense, one slot per boundary cell)
+  for (int t = blockIdx.x; t < a.nTasks; t += gridDim.x) {
     const int L = a.slen[a.tasks[t].subject];
-    bool ok = true;
-    for (int guard = 0; (o & kPseudoBit) && guard < 128; guard++) {
-      const int pt = a.tasks[t].prevTask;
-      if (pt < 0) {
-        ok = false;
-        break;
-      }
-      const uint32_t row = o & 0xFFFFFu;  // 1-based
-      const bool isE = o & kPseudoEBit;
-      o = a.snap[a.tasks[pt].snapOff + (isE ? L : 0) + (row - 1)];
-      t = pt;
-      if (o == 0) {
-        ok = false;
-        break;
-      }
+    const unsigned long long* pb = a.pbest + a.tasks[t].snapOff;
+    for (int e = threadIdx.x; e < 2 * L; e += blockDim.x) {
+      const unsigned long long val = pb[e];
+      if (val == 0) continue;
+      const uint32_t o = kPseudoBit | (e >= L ? kPseudoEBit : 0u) | (uint32_t)((e >= L ? e - L : e) + 1);
+      resolve_one(a, t, o, val);
     }
-    if (!ok || (o & kPseudoBit)) {
-      if (atomicExch(&a.redo[triple], 1) == 0 && a.verbose)
-        printf("[resolve] triple %d: task %d (c0 %d) origin %x -> stuck at task %d (c0 %d prev %d) o %x val %llx\n", triple, (int)(key >> 32),
-               a.tasks[(int)(key >> 32)].c0, (uint32_t)key, t, a.tasks[t].c0, a.tasks[t].prevTask, o, a.vals[s]);
-      continue;
-    }
-    const uint32_t Lp1 = (uint32_t)L + 1u;
-    const unsigned long long i0 = (unsigned long long)(o / Lp1) + (unsigned long long)a.tasks[t].c0;
-    const unsigned long long j0 = o % Lp1;
-    table_emit(a.fkeys, a.fvals, a.fmask, a.overflow, ((unsigned long long)(uint32_t)triple << 40) | (i0 << 20) | j0, a.vals[s]);
   }
 }
 
