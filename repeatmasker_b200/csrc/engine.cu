@@ -128,6 +128,16 @@ struct HotMask {
     for (int k = 0; k < kHotWords; k++) m.w[k] = w[k] | o.w[k];
     return m;
   }
+  HotMask operator&(const HotMask& o) const {
+    HotMask m;
+    for (int k = 0; k < kHotWords; k++) m.w[k] = w[k] & o.w[k];
+    return m;
+  }
+  static HotMask range(int lo, int hi) {  // bits lo..hi
+    HotMask m;
+    for (int c = std::max(lo, 0); c <= hi && c < kHotBlocks; c++) m.w[c >> 6] |= 1ull << (c & 63);
+    return m;
+  }
   HotMask shr1() const {  // bit c -> c - 1
     HotMask m;
     for (int k = 0; k < kHotWords; k++) m.w[k] = (w[k] >> 1) | (k + 1 < kHotWords ? w[k + 1] << 63 : 0ull);
@@ -222,8 +232,7 @@ struct rmgpu_session {
   DevBuf<int32_t> d_pairbest;
   DevBuf<unsigned long long> d_hotmask;
   DevBuf<int32_t> d_hotShift;
-  DevBuf<unsigned long long> d_dbg, d_dbgC, d_pbest;
-  DevBuf<int> d_abort, d_leftFlag;
+  DevBuf<unsigned long long> d_dbgC;
   // second stream + scratch of the stripe-pipeline fallback, which runs concurrently with the block-parallel path
   cudaStream_t stream2 = nullptr;
   DevBuf<OriginTask> d_tasksC;
@@ -231,20 +240,26 @@ struct rmgpu_session {
   DevBuf<OriginBoundary> d_bndC;
   DevBuf<int> d_progressC, d_finishedC, d_ticketC, d_overflowC, d_abortC, d_leftFlagC;
   DevBuf<unsigned long long> d_keysC, d_valsC;
-  DevBuf<BlockTask> d_btasks;
-  DevBuf<uint32_t> d_snap;
-  DevBuf<int32_t> d_ticketStripe, d_prodTicket, d_consTicket;
-  int blockLevelWidth = 0;
-  DevBuf<unsigned long long> d_fkeys, d_fvals;
+  // Scratch of one block-parallel origin launch (K2b + resolve).  Two sets: the common triples run from the calling
+  // thread on `stream`, the triples whose int16 values wrapped run -- behind their int32 score pass -- from the second
+  // host thread on `stream2`, and the two launches share the machine.
+  struct BlockBufs {
+    DevBuf<BlockTask> d_btasks;
+    DevBuf<uint32_t> d_snap;
+    DevBuf<int32_t> d_ticketTask, d_ticketStripe, d_prodTicket, d_consTicket;
+    DevBuf<OriginBoundary> d_bnd2;
+    DevBuf<int> d_progress, d_finished, d_ticket, d_overflow, d_abort, d_redo;
+    DevBuf<unsigned long long> d_keys, d_vals, d_pbest, d_dbg, d_fkeys, d_fvals;
+  } bb[2];
+  // int32 score pass of the wrapped triples (swg_score32_kernel)
+  DevBuf<WideTask> d_wtasks;
+  DevBuf<int32_t> d_ticketTaskW;
+  DevBuf<int2> d_bndW, d_ck32;
+  DevBuf<int> d_progressW, d_finishedW, d_ticketW, d_abortW, d_edgeW;
+  DevBuf<unsigned long long> d_hot32;
   int32_t h_mat[16][16];
-  void check_abort(const char* what);
   void check_abort_on(const char* what, int* flag, cudaStream_t st);
   std::vector<int32_t> h_hotShift;
-  DevBuf<OriginBoundary> d_bnd2;
-  DevBuf<int> d_progress, d_finished, d_ticket, d_overflow;
-  DevBuf<unsigned long long> d_keys, d_vals;
-  DevBuf<OriginTask> d_tasks;
-  DevBuf<int32_t> d_ticketTask;
   DevBuf<TraceCand> d_cand;
   DevBuf<uint8_t> d_dir, d_ops;
   DevBuf<int32_t> d_rows, d_opsLen, d_status;
@@ -573,8 +588,6 @@ void rmgpu_session::build_order(ScoreSlot& sl, int nQ, int warps) {
   sl.orderForNQ = nQ;
 }
 
-void rmgpu_session::check_abort(const char* what) { check_abort_on(what, d_abort.p, stream); }  // K2b
-
 void rmgpu_session::check_abort_on(const char* what, int* flag, cudaStream_t stq) {
   int f = 0;
   CUDA_CHECK(cudaMemcpyAsync(&f, flag, sizeof(int), cudaMemcpyDeviceToHost, stq));
@@ -746,10 +759,17 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
                                rmgpu_stats& st) {
   const int nS = (int)lib.seqs.size();
   static const bool fullMode = getenv("RMGPU_K2_FULL") != nullptr;
+  static const bool noWide = getenv("RMGPU_NO_WIDE") != nullptr;  // wrapped triples take the one-sweep fallback (the round-1 path)
   struct Triple {
     int q, strand, subject;
     HotMask dil;
     bool chain;
+    // int16 wrap in K1: an int32 score pass (K2w) over the window [lo32, hi32] of column blocks supplies exact
+    // checkpoints and the exact hot mask, then the triple's hot blocks are K2b tasks like everyone else's
+    bool wide = false;
+    int lo32 = 0, hi32 = -1;
+    int64_t ck32Base = -1;
+    HotMask dil32;  // exact mask of the window (dilated like dil)
   };
   std::vector<Triple> triples;
   for (int q = q0; q < q1; q++)
@@ -771,6 +791,9 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         // checkpoints are exact only when K1 is (no merged residue class, no int16 wrap)
         t.chain = pairbest[idx] >= 32767 || fullMode || !ckEnabled || !classesExact || t.dil.none() ||
                   (CB + 2) * (L + 1) >= (1ll << 31);
+        t.wide = !noWide && pairbest[idx] >= 32767 && !fullMode && ckEnabled && classesExact && !t.dil.none() &&
+                 (CB + 2) * (L + 1) < (1ll << 31) && (Q + CB - 1) / CB <= kHotBlocks;
+        if (t.wide) t.chain = false;
         triples.push_back(t);
       }
   st.n_pairs_passed += (int)triples.size();
@@ -794,7 +817,14 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   const double k2t0 = now_ms();
   std::atomic<int> chainLaunched{0};  // set once the fallback sweep's kernel is in its stream (or there is none)
   // ------------------------------------------------------------------ block-parallel path
-  auto run_blocks = [&](const std::vector<int>& trIdx, bool allBlocks, std::vector<int>& redoOut) {
+  struct PathStats {  // what one host thread of the origin pass adds to rmgpu_stats (merged at the end)
+    int launches = 0, redo = 0;
+    int64_t d2h = 0;
+    double cells = 0;
+  };
+  // One block-parallel launch over the triples trIdx with the scratch set B on stream sq; candidates go to `out`.
+  auto run_blocks = [&](const std::vector<int>& trIdx, bool allBlocks, std::vector<int>& redoOut, BlockBufs& B, cudaStream_t sq,
+                        std::vector<std::pair<int, Candidate>>& out, PathStats& ps, bool afterChain) {
     std::vector<BlockTask> tasks;
     int64_t snapTot = 0;
     for (int tr : trIdx) {
@@ -803,9 +833,11 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       const int64_t CB = 32ll << h_hotShift[T.q];
       const int nblk = (int)((Q + CB - 1) / CB);
       int prev = -1;
-      for (int c = 0; c < nblk && c < kHotBlocks; c++) {
+      // a wrapped triple only has tasks inside the window of its int32 score pass (T.dil is that pass's exact mask)
+      const int cFirst = T.wide ? T.lo32 : 0, cLast = T.wide ? T.hi32 : std::min(nblk, kHotBlocks) - 1;
+      for (int c = cFirst; c <= cLast; c++) {
         // the last bit stands for every block from there on
-        const bool on = allBlocks || T.dil.test(std::min(c, kHotBlocks - 1));
+        const bool on = allBlocks || (T.wide ? T.dil32 : T.dil).test(std::min(c, kHotBlocks - 1));
         if (!on) {
           prev = -1;
           continue;
@@ -820,11 +852,13 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         t.c1 = (c == kHotBlocks - 1) ? (int)Q : (int)std::min<int64_t>(Q, (c + 1) * CB);
         t.prevTask = prev;
         t.ckOff = c > 0 ? ((int64_t)T.q * kHotBlocks + c) * ((int64_t)nGroups * R) + (int64_t)h_subjFirstGroup[T.subject] * R : -1;
+        // K1's checkpoint is exact at the left edge of the window (no cell has wrapped before it), K2w wrote the others
+        t.ck32Off = (T.wide && c > T.lo32) ? T.ck32Base + (int64_t)(c - T.lo32) * L : -1;
         t.snapOff = snapTot;
         snapTot += 2 * L;
         prev = (int)tasks.size();
         tasks.push_back(t);
-        st.origin_cells += (double)(t.c1 - t.c0) * (double)L;
+        ps.cells += (double)(t.c1 - t.c0) * (double)L;
       }
     }
     if (tasks.empty()) return;
@@ -847,7 +881,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     // levels, where a consumer stripe is claimed (nearly) a whole level after its producer and never polls, come last,
     // so the kernel ends on plenty of parallel work instead of a thin tail of long tasks
     std::vector<int32_t> ticketTask, ticketStripe, prodTicket, consTicket;
-    int maxStripes = 0;
+    int maxStripes = 0, blockLevelWidth = 0;
     for (auto& t : tasks) {
       t.nStripes = (int)((lib.seqs[t.subject].size() + kR2 * 32 - 1) / (kR2 * 32));
       maxStripes = std::max(maxStripes, t.nStripes);
@@ -894,16 +928,16 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     for (;;) {
       const size_t ftableSize = tableSize >> 6;  // final table (triple, origin): the only one downloaded
       BlockArgs a;
-      d_btasks.upload(tasks, stream);
-      d_ticketTask.upload(ticketTask, stream);
-      d_ticketStripe.upload(ticketStripe, stream);
-      d_prodTicket.upload(prodTicket, stream);
-      d_consTicket.upload(consTicket, stream);
-      a.tasks = d_btasks.p;
-      a.ticketTask = d_ticketTask.p;
-      a.ticketStripe = d_ticketStripe.p;
-      a.prodTicket = d_prodTicket.p;
-      a.consTicket = d_consTicket.p;
+      B.d_btasks.upload(tasks, sq);
+      B.d_ticketTask.upload(ticketTask, sq);
+      B.d_ticketStripe.upload(ticketStripe, sq);
+      B.d_prodTicket.upload(prodTicket, sq);
+      B.d_consTicket.upload(consTicket, sq);
+      a.tasks = B.d_btasks.p;
+      a.ticketTask = B.d_ticketTask.p;
+      a.ticketStripe = B.d_ticketStripe.p;
+      a.prodTicket = B.d_prodTicket.p;
+      a.consTicket = B.d_consTicket.p;
       a.nTickets = nTickets;
       a.codes_fwd = d_codes_fwd.p;
       a.codes_rc = d_codes_rc.p;
@@ -917,34 +951,35 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       a.del_ext = p.del_gap_ext;
       a.minscore = p.minscore;
       a.ck = d_ck.p;
-      a.bnd = d_bnd2.ensure((size_t)nslot * bndStride);
+      a.ck32 = (&B == &bb[1]) ? d_ck32.p : nullptr;  // only the wrapped triples' launch has int32 checkpoints
+      a.bnd = B.d_bnd2.ensure((size_t)nslot * bndStride);
       a.bndStride = bndStride;
       a.nslot = nslot;
-      a.progress = d_progress.ensure((size_t)nTickets);
-      a.finished = d_finished.ensure((size_t)nTickets);
-      a.abort_flag = d_abort.ensure(1);
-      a.snap = d_snap.ensure((size_t)std::max<int64_t>(snapTot, 1));
-      a.ticket = d_ticket.ensure(1);
-      a.keys = d_keys.ensure(tableSize);
-      a.vals = d_vals.ensure(tableSize);
+      a.progress = B.d_progress.ensure((size_t)nTickets);
+      a.finished = B.d_finished.ensure((size_t)nTickets);
+      a.abort_flag = B.d_abort.ensure(1);
+      a.snap = B.d_snap.ensure((size_t)std::max<int64_t>(snapTot, 1));
+      a.ticket = B.d_ticket.ensure(1);
+      a.keys = B.d_keys.ensure(tableSize);
+      a.vals = B.d_vals.ensure(tableSize);
       a.tableMask = (uint32_t)tableSize - 1;
-      a.overflow = d_overflow.ensure(1);
-      a.pbest = d_pbest.ensure((size_t)std::max<int64_t>(snapTot, 1));
-      CUDA_CHECK(cudaMemsetAsync(a.pbest, 0, (size_t)std::max<int64_t>(snapTot, 1) * 8, stream));
+      a.overflow = B.d_overflow.ensure(1);
+      a.pbest = B.d_pbest.ensure((size_t)std::max<int64_t>(snapTot, 1));
+      CUDA_CHECK(cudaMemsetAsync(a.pbest, 0, (size_t)std::max<int64_t>(snapTot, 1) * 8, sq));
       a.dbg = nullptr;
       if (dbgK2) {
-        a.dbg = d_dbg.ensure(72);
-        CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 72 * 8, stream));
+        a.dbg = B.d_dbg.ensure(72);
+        CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 72 * 8, sq));
       }
-      CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream));
-      CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream));
-      CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream));
-      CUDA_CHECK(cudaMemsetAsync(a.keys, 0xFF, tableSize * 8, stream));
-      CUDA_CHECK(cudaMemsetAsync(a.vals, 0, tableSize * 8, stream));
-      CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), stream));
-      CUDA_CHECK(cudaMemsetAsync(a.overflow, 0, sizeof(int), stream));
+      CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), sq));
+      CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), sq));
+      CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), sq));
+      CUDA_CHECK(cudaMemsetAsync(a.keys, 0xFF, tableSize * 8, sq));
+      CUDA_CHECK(cudaMemsetAsync(a.vals, 0, tableSize * 8, sq));
+      CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), sq));
+      CUDA_CHECK(cudaMemsetAsync(a.overflow, 0, sizeof(int), sq));
       ResolveArgs r;
-      r.tasks = d_btasks.p;
+      r.tasks = B.d_btasks.p;
       r.nTasks = (int)tasks.size();
       r.pbest = a.pbest;
       r.slen = d_slen.p;
@@ -952,33 +987,33 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       r.keys = a.keys;
       r.vals = a.vals;
       r.tableSize = (uint32_t)tableSize;
-      r.fkeys = d_fkeys.ensure(ftableSize);
-      r.fvals = d_fvals.ensure(ftableSize);
+      r.fkeys = B.d_fkeys.ensure(ftableSize);
+      r.fvals = B.d_fvals.ensure(ftableSize);
       r.fmask = (uint32_t)ftableSize - 1;
       r.overflow = a.overflow;
-      r.redo = d_leftFlag.ensure(triples.size());
+      r.redo = B.d_redo.ensure(triples.size());
       r.verbose = allBlocks ? 1 : 0;
-      CUDA_CHECK(cudaMemsetAsync(r.fkeys, 0xFF, ftableSize * 8, stream));
-      CUDA_CHECK(cudaMemsetAsync(r.fvals, 0, ftableSize * 8, stream));
-      CUDA_CHECK(cudaMemsetAsync(r.redo, 0, triples.size() * sizeof(int), stream));
+      CUDA_CHECK(cudaMemsetAsync(r.fkeys, 0xFF, ftableSize * 8, sq));
+      CUDA_CHECK(cudaMemsetAsync(r.fvals, 0, ftableSize * 8, sq));
+      CUDA_CHECK(cudaMemsetAsync(r.redo, 0, triples.size() * sizeof(int), sq));
       // let the (small, high-priority) fallback sweep take its SM slots first, then fill the rest of the machine
-      for (double w0 = now_ms(); !chainLaunched.load() && now_ms() - w0 < 100.0;) std::this_thread::yield();
+      for (double w0 = now_ms(); afterChain && !chainLaunched.load() && now_ms() - w0 < 100.0;) std::this_thread::yield();
       EventTimer tm;
-      tm.start(stream);
-      swg_origin_block_kernel<<<grid, 128, 0, stream>>>(a);
-      resolve_candidates_kernel<<<numSMs * 2, 256, 0, stream>>>(r);
-      tm.stop(stream);
+      tm.start(sq);
+      swg_origin_block_kernel<<<grid, 128, 0, sq>>>(a);
+      resolve_candidates_kernel<<<numSMs * 2, 256, 0, sq>>>(r);
+      tm.stop(sq);
       CUDA_CHECK(cudaGetLastError());
       int overflow = 0;
       std::vector<int> redoFlag(triples.size(), 0);
       std::vector<unsigned long long> keys(ftableSize), vals(ftableSize);
-      CUDA_CHECK(cudaStreamSynchronize(stream));  // as in run_chain: never block inside a pageable copy while the other path launches
-      CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaMemcpyAsync(redoFlag.data(), r.redo, triples.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaMemcpyAsync(keys.data(), r.fkeys, ftableSize * 8, cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaMemcpyAsync(vals.data(), r.fvals, ftableSize * 8, cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaStreamSynchronize(stream));
-      check_abort("K2b");
+      CUDA_CHECK(cudaStreamSynchronize(sq));  // as in run_chain: never block inside a pageable copy while the other path launches
+      CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, sq));
+      CUDA_CHECK(cudaMemcpyAsync(redoFlag.data(), r.redo, triples.size() * sizeof(int), cudaMemcpyDeviceToHost, sq));
+      CUDA_CHECK(cudaMemcpyAsync(keys.data(), r.fkeys, ftableSize * 8, cudaMemcpyDeviceToHost, sq));
+      CUDA_CHECK(cudaMemcpyAsync(vals.data(), r.fvals, ftableSize * 8, cudaMemcpyDeviceToHost, sq));
+      CUDA_CHECK(cudaStreamSynchronize(sq));
+      check_abort_on("K2b", B.d_abort.p, sq);
       if (dbgK2) {
         fprintf(stderr, "[K2 dbg] blocks: %zu triples %zu tasks %d tickets grid %d  kernels %.2f ms (done at +%.2f ms)\n", trIdx.size(),
                 tasks.size(), nTickets, grid, tm.ms(), now_ms() - k2t0);
@@ -1001,8 +1036,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
                   pairbest[((size_t)bt.q * nS + bt.subject) * 2 + bt.strand]);
         }
       }
-      st.launches += 2;
-      st.d2h_bytes += (int64_t)ftableSize * 16;
+      ps.launches += 2;
+      ps.d2h += (int64_t)ftableSize * 16;
       if (overflow) {  // a probe sequence got long in one of the two tables
         tableSize *= 4;
         if (tableSize > (1u << 28)) throw Error("candidate table overflow");
@@ -1024,7 +1059,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
         c.i0 = (int)((keys[i] >> 20) & 0xFFFFFu);
         c.j0 = (int)(keys[i] & 0xFFFFFu);
         decode_val(vals[i], c);
-        found.push_back({tr, c});
+        out.push_back({tr, c});
       }
       break;
     }
@@ -1241,15 +1276,159 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
     }
   };
 
-  std::vector<int> blockTr, chainTr, redo;
-  for (size_t i = 0; i < triples.size(); i++) (triples[i].chain ? chainTr : blockTr).push_back((int)i);
-  // the fallback sweeps are long and narrow (a few warps busy for tens of ms): run them on a second stream from a
-  // second host thread while the block-parallel path fills the machine
+  // ------------------------------------------------------------------ wrapped triples: int32 score pass, then K2b
+  std::vector<std::pair<int, Candidate>> foundWide;
+  PathStats psWide, psMain;
+  auto run_wide = [&](const std::vector<int>& trIdx, std::vector<int>& fallback) {
+    if (trIdx.empty()) return;
+    std::vector<WideTask> tasks;
+    std::vector<int32_t> ticketTask;
+    std::vector<int> taskTr;
+    int64_t ckTot = 0, maxW = 0;
+    for (int tr : trIdx) {
+      Triple& T = triples[tr];
+      const int64_t Q = h_qlen[T.q], L = (int64_t)lib.seqs[T.subject].size();
+      const int64_t CB = 32ll << h_hotShift[T.q];
+      const int nblk = (int)((Q + CB - 1) / CB);
+      // the window of the one-sweep fallback: from the first block of K1's (there still exact) mask to its last one,
+      // stretched because a wrap only ever LOWERS K1's values: to the right of the wrapped alignment K1 under-reports
+      // the decaying fan (true scores fall by ~5-6 per column along a gap).  Whatever is >= minscore when it leaves
+      // the window raises the edge flag, so exactness never depends on the stretch
+      HotMask fwd = T.dil;
+      const int stretch = (int)std::max<int64_t>(8, (8192 + CB - 1) / CB);
+      HotMask sh = T.dil;
+      for (int k = 1; k <= stretch; k++) {
+        sh = sh.shl1();
+        fwd = fwd | sh;
+      }
+      const int lo = fwd.lowest(), hi = std::min(fwd.highest(), nblk - 1);
+      const int64_t need = (int64_t)(hi - lo + 1) * L;
+      if (lo < 0 || hi < lo || ckTot + need > (1ll << 29)) {  // (4 GB of int32 checkpoints per pass at most)
+        fallback.push_back(tr);
+        continue;
+      }
+      WideTask t;
+      memset(&t, 0, sizeof(t));
+      t.q = T.q;
+      t.strand = T.strand;
+      t.subject = T.subject;
+      t.hotShift = h_hotShift[T.q];
+      t.c0 = (int)(lo * CB);
+      t.c1 = (hi >= nblk - 1) ? (int)Q : (int)((hi + 1) * CB);
+      t.ckOff = lo > 0 ? ((int64_t)T.q * kHotBlocks + lo) * ((int64_t)nGroups * R) + (int64_t)h_subjFirstGroup[T.subject] * R : -1;
+      t.ck32Off = ckTot;
+      ckTot += need;
+      T.lo32 = lo;
+      T.hi32 = hi;
+      T.ck32Base = t.ck32Off;
+      t.nStripes = (int)((L + kRW * 32 - 1) / (kRW * 32));
+      t.firstTicket = (int)ticketTask.size();
+      for (int k = 0; k < t.nStripes; k++) ticketTask.push_back((int32_t)tasks.size());
+      maxW = std::max<int64_t>(maxW, t.c1 - t.c0);
+      psWide.cells += (double)(t.c1 - t.c0) * (double)L;
+      taskTr.push_back(tr);
+      tasks.push_back(t);
+    }
+    std::vector<int> okTr;
+    if (!tasks.empty()) {
+      int blocksPerSM = 0;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score32_kernel, 128, 0));
+      if (blocksPerSM < 1) throw Error("K2w does not fit on an SM");
+      blocksPerSM = std::min(blocksPerSM, 4);
+      const int nTickets = (int)ticketTask.size();
+      const int grid = (int)std::min<int64_t>((int64_t)numSMs * blocksPerSM, ((int64_t)nTickets + 3) / 4);
+      const int warps = grid * 4;
+      const int nslot = std::min(nTickets, 2 * warps + 2);
+      const int64_t bndStride = ((maxW + 31) >> 5) * 32 + 32;
+      WideArgs a;
+      d_wtasks.upload(tasks, stream2);
+      d_ticketTaskW.upload(ticketTask, stream2);
+      a.tasks = d_wtasks.p;
+      a.ticketTask = d_ticketTaskW.p;
+      a.nTickets = nTickets;
+      a.codes_fwd = d_codes_fwd.p;
+      a.codes_rc = d_codes_rc.p;
+      a.qoff = d_qoff.p;
+      a.qlen = d_qlen.p;
+      a.scodes = d_scodes.p;
+      a.soff = d_soff.p;
+      a.slen = d_slen.p;
+      memcpy(a.mat, h_mat, sizeof(h_mat));
+      a.gap_init = p.gap_init;
+      a.ins_ext = p.ins_gap_ext;
+      a.del_ext = p.del_gap_ext;
+      a.minscore = p.minscore;
+      a.bnd = d_bndW.ensure((size_t)nslot * bndStride);
+      a.bndStride = bndStride;
+      a.nslot = nslot;
+      a.progress = d_progressW.ensure((size_t)nTickets);
+      a.finished = d_finishedW.ensure((size_t)nTickets);
+      a.ticket = d_ticketW.ensure(1);
+      a.abort_flag = d_abortW.ensure(1);
+      a.ck = d_ck.p;
+      a.ck32 = d_ck32.ensure((size_t)std::max<int64_t>(ckTot, 1));
+      a.hot32 = d_hot32.ensure(tasks.size() * kHotWords);
+      a.edgeFlag = d_edgeW.ensure(tasks.size());
+      CUDA_CHECK(cudaMemsetAsync(a.progress, 0, (size_t)nTickets * sizeof(int), stream2));
+      CUDA_CHECK(cudaMemsetAsync(a.finished, 0, (size_t)nTickets * sizeof(int), stream2));
+      CUDA_CHECK(cudaMemsetAsync(a.ticket, 0, sizeof(int), stream2));
+      CUDA_CHECK(cudaMemsetAsync(a.abort_flag, 0, sizeof(int), stream2));
+      CUDA_CHECK(cudaMemsetAsync(a.hot32, 0, tasks.size() * kHotWords * 8, stream2));
+      CUDA_CHECK(cudaMemsetAsync(a.edgeFlag, 0, tasks.size() * sizeof(int), stream2));
+      EventTimer tm;
+      tm.start(stream2);
+      swg_score32_kernel<<<grid, 128, 0, stream2>>>(a);
+      tm.stop(stream2);
+      chainLaunched.store(1);
+      CUDA_CHECK(cudaGetLastError());
+      std::vector<unsigned long long> hot(tasks.size() * kHotWords);
+      std::vector<int> edge(tasks.size());
+      CUDA_CHECK(cudaStreamSynchronize(stream2));  // (never block inside a pageable copy while the other thread launches)
+      CUDA_CHECK(cudaMemcpyAsync(hot.data(), a.hot32, hot.size() * 8, cudaMemcpyDeviceToHost, stream2));
+      CUDA_CHECK(cudaMemcpyAsync(edge.data(), a.edgeFlag, edge.size() * sizeof(int), cudaMemcpyDeviceToHost, stream2));
+      CUDA_CHECK(cudaStreamSynchronize(stream2));
+      check_abort_on("K2w", a.abort_flag, stream2);
+      psWide.launches += 1;
+      psWide.d2h += (int64_t)(hot.size() * 8 + edge.size() * 4);
+      int nEdge = 0;
+      for (size_t i = 0; i < tasks.size(); i++) {
+        Triple& T = triples[taskTr[i]];
+        if (edge[i]) {  // something >= minscore leaves the window: the one-sweep path handles it (with its own redo)
+          fallback.push_back(taskTr[i]);
+          nEdge++;
+          continue;
+        }
+        HotMask m;
+        for (int k = 0; k < kHotWords; k++) m.w[k] = hot[i * kHotWords + k];
+        T.dil32 = (m | m.shr1()) & HotMask::range(T.lo32, T.hi32);
+        okTr.push_back(taskTr[i]);
+      }
+      if (dbgK2)
+        fprintf(stderr, "[K2 dbg] wide: %zu triples %d tickets R=%d grid %d  kernel %.2f ms (done at +%.2f ms); widest window %lld columns, "
+                "%.1f MB of int32 checkpoints, %d left the window\n", tasks.size(), nTickets, kRW, grid, tm.ms(), now_ms() - k2t0, (long long)maxW,
+                (double)ckTot * 8e-6, nEdge);
+    }
+    std::vector<int> redoW;
+    run_blocks(okTr, false, redoW, bb[1], stream2, foundWide, psWide, false);
+    // a pseudo origin that leads out of the window (or into a block of it that was not swept): the one-sweep path
+    for (int tr : redoW) fallback.push_back(tr);
+    psWide.redo += (int)fallback.size();
+    for (int tr : fallback) triples[tr].wide = false;
+  };
+
+  std::vector<int> blockTr, chainTr, wideTr, redo;
+  for (size_t i = 0; i < triples.size(); i++) (triples[i].wide ? wideTr : triples[i].chain ? chainTr : blockTr).push_back((int)i);
+  // the latency-bound paths (one dependent chain of columns per triple: a few warps busy for milliseconds) run on a
+  // second stream from a second host thread while the block-parallel path fills the machine
   std::exception_ptr chainErr;
   std::thread chainThread([&] {
     try {
       if (cudaSetDevice(device) != cudaSuccess) throw Error("cudaSetDevice failed in the K2 fallback thread");
       run_chain(chainTr);
+      std::vector<int> fallback;
+      run_wide(wideTr, fallback);
+      chainLaunched.store(1);
+      run_chain(fallback);
     } catch (...) {
       chainErr = std::current_exception();
     }
@@ -1259,11 +1438,11 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   static const bool serialK2 = getenv("RMGPU_K2_SERIAL") != nullptr;  // measurement: the two paths one after the other
   if (serialK2 && chainThread.joinable()) chainThread.join();
   try {
-    run_blocks(blockTr, false, redo);
+    run_blocks(blockTr, false, redo, bb[0], stream, found, psMain, true);
     if (!redo.empty()) {
-      st.n_origin_redo += (int)redo.size();
+      psMain.redo += (int)redo.size();
       std::vector<int> none;
-      run_blocks(redo, true, none);
+      run_blocks(redo, true, none, bb[0], stream, found, psMain, false);
     }
   } catch (...) {
     blockErr = std::current_exception();
@@ -1271,6 +1450,13 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   if (chainThread.joinable()) chainThread.join();
   if (blockErr) std::rethrow_exception(blockErr);
   if (chainErr) std::rethrow_exception(chainErr);
+  found.insert(found.end(), foundWide.begin(), foundWide.end());
+  for (const PathStats* ps : {&psMain, &psWide}) {
+    st.launches += ps->launches;
+    st.d2h_bytes += ps->d2h;
+    st.n_origin_redo += ps->redo;
+    st.origin_cells += ps->cells;
+  }
   found.insert(found.end(), foundChain.begin(), foundChain.end());
   st.launches += chainLaunches;
   st.d2h_bytes += chainD2H;

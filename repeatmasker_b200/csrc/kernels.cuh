@@ -849,6 +849,195 @@ __global__ void __launch_bounds__(128) swg_origin_kernel(OriginArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// K2w: int32 score pass for the few triples whose int16 values wrapped in K1 (raw scores >= ~32,000).  K1's checkpoints
+// and hot mask are exact only left of the wrap, so such a triple could not use the block-parallel origin pass and was
+// swept by swg_origin_kernel in one dependent chain of ~170 instructions per column.  This kernel is the cheap part of
+// that chain only: the plain H/E/F recurrence in int32 (no origins, ~40 instructions per column at 2 rows per lane)
+// over the triple's window, started from K1's last exact checkpoint.  It writes what K1 could not: an exact (H, E)
+// checkpoint of every subject row at every column-block boundary of the window, the exact hot mask of the window, and
+// a flag when something >= minscore leaves the window on the right.  With those the triple's hot blocks become
+// ordinary K2b tasks that run in parallel.  Same stripe pipeline (ring + progress flags) as swg_origin_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRW = 2;  // subject rows per lane: the launch is one dependent chain per triple, so the per-column latency counts
+
+struct WideTask {
+  int32_t q, strand, subject;
+  int32_t firstTicket, nStripes;  // stripes of kRW*32 rows
+  int32_t c0, c1;                 // window [c0, c1) of query columns; c0 is a multiple of the checkpoint spacing
+  int32_t hotShift;               // column block = (column >> 5) >> hotShift
+  int64_t ckOff;                  // subject's first row in K1's (exact) checkpoint taken before column c0, or -1 (c0 == 0)
+  int64_t ck32Off;                // ck32[ck32Off + n * L + row] = (H, E) before column c0 + n * CB, n >= 1, CB = 32 << hotShift
+};
+
+struct WideArgs {
+  const WideTask* tasks;
+  const int32_t* ticketTask;
+  int nTickets;
+  const uint8_t* codes_fwd;
+  const uint8_t* codes_rc;
+  const int64_t* qoff;
+  const int32_t* qlen;
+  const uint8_t* scodes;
+  const int64_t* soff;
+  const int32_t* slen;
+  int32_t mat[16][16];
+  int32_t gap_init, ins_ext, del_ext, minscore;
+  int2* bnd;                     // [nslot * bndStride] (H, F) of the stripe's last row per column
+  int64_t bndStride;
+  int nslot;
+  int* progress;
+  int* finished;
+  int* ticket;
+  int* abort_flag;
+  const uint2* ck;               // K1 checkpoints
+  int2* ck32;                    // out: int32 checkpoints
+  unsigned long long* hot32;     // out: [nTasks * kHotWords] bit c: a cell of column block c reached minscore (filed, like
+                                 //      K1's mask, under the block the warp is in: the cell's own block or the one after)
+  int* edgeFlag;                 // out: [nTasks] a cell >= minscore in the last column of a window that ends before the query
+};
+
+__global__ void __launch_bounds__(128) swg_score32_kernel(WideArgs a) {
+  __shared__ int32_t smat[kMatStride * kMatStride];
+  __shared__ int4 s_feed[4][32];  // per warp: (query code, H above, F above) for the 32 columns of the block
+  __shared__ int2 s_out[4][32];   //           last row's (H, F) of the 32 columns lane 31 finished last
+  load_score_table(smat, a.mat);
+  __syncthreads();
+  constexpr int R = kRW;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int NEGI = -(1 << 28);
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= a.nTickets) break;
+    const int ti = a.ticketTask[t];
+    const WideTask tk = a.tasks[ti];
+    const int k = t - tk.firstTicket;
+    const int Q = a.qlen[tk.q], L = a.slen[tk.subject];
+    const uint8_t* qc = (tk.strand ? a.codes_rc : a.codes_fwd) + a.qoff[tk.q];
+    const uint8_t* sc = a.scodes + a.soff[tk.subject];
+    const bool hasPrev = k > 0, hasNext = k + 1 < tk.nStripes;
+    const int row0 = (k * 32 + lane) * R;
+    int srow[R], H[R], E[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      srow[r] = ((row0 + r < L) ? (int)sc[row0 + r] : kPadCode) * kMatStride;
+      H[r] = 0;
+      E[r] = NEGI;
+    }
+    int diagH = 0;
+    if (tk.ckOff >= 0) {
+      const uint2* ck = a.ck + tk.ckOff;
+      const int sh = tk.strand ? 16 : 0;
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        if (row0 + r < L) {
+          const uint2 v = ck[row0 + r];
+          H[r] = (int)((v.x >> sh) & 0xffffu);
+          E[r] = (int)((v.y >> sh) & 0xffffu) + a.gap_init;
+        }
+      if (row0 > 0 && row0 - 1 < L) diagH = (int)((ck[row0 - 1].x >> sh) & 0xffffu);
+    }
+    const int W = tk.c1 - tk.c0;
+    const int qBlocks = (W + 31) >> 5, nBlocks = qBlocks + 1;
+    const int ckMask = (32 << tk.hotShift) - 1, ckShift = 5 + tk.hotShift;
+    const int b0 = tk.c0 >> 5;
+    const int2* bndIn = a.bnd + (int64_t)((t - 1 + a.nslot) % a.nslot) * a.bndStride;
+    int2* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
+    if (hasNext) {
+      // the reader (ticket + 1) of the last ticket that wrote this ring slot must be done
+      for (int tOld = t - a.nslot; tOld >= 0; tOld -= a.nslot) {
+        const WideTask& ot = a.tasks[a.ticketTask[tOld]];
+        if (tOld - ot.firstTicket + 1 >= ot.nStripes) continue;  // that ticket had no stripe below: it wrote nothing
+        if (lane == 0) wait_ge(&a.finished[tOld + 1], 1, a.abort_flag);
+        __syncwarp();
+        break;
+      }
+    }
+    int outH = 0, outF = NEGI, curQ = kPadCode, blkMax = 0;
+    bool edge = false;
+    for (int b = 0; b < nBlocks; b++) {
+      const int col = b * 32 + lane;
+      int4 fv = make_int4((col < W) ? (int)qc[tk.c0 + col] : kPadCode, 0, NEGI, 0);
+      if (hasPrev && b < qBlocks) {
+        if (lane == 0 && ld_acquire(&a.progress[t - 1]) < b + 1) wait_ge(&a.progress[t - 1], min(b + kLagSweep, qBlocks), a.abort_flag);
+        __syncwarp();
+        const int2 raw = __ldcg(&bndIn[col]);
+        fv.y = raw.x;
+        fv.z = raw.y;
+      }
+      __syncwarp();  // everyone is done with the previous block's feed
+      s_feed[wib][lane] = fv;
+      __syncwarp();
+#pragma unroll 4
+      for (int j = 0; j < 32; j++) {
+        const int4 fd = s_feed[wib][j];  // broadcast read; only lane 0 uses it
+        int inQ = __shfl_up_sync(0xffffffffu, curQ, 1);
+        int inH = __shfl_up_sync(0xffffffffu, outH, 1);
+        int inF = __shfl_up_sync(0xffffffffu, outF, 1);
+        inQ = lane == 0 ? fd.x : inQ;
+        inH = lane == 0 ? fd.y : inH;
+        inF = lane == 0 ? fd.z : inF;
+        curQ = inQ;
+        const int cw = b * 32 + j - lane;  // column inside the window, 0-based
+        int hu = inH, f = inF;
+        if (cw >= 0) {  // before its first column a lane keeps its (checkpointed) state untouched
+          if (cw > 0 && (cw & ckMask) == 0 && cw < W) {
+            int2* dst = a.ck32 + tk.ck32Off + (int64_t)(cw >> ckShift) * L;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+              if (row0 + r < L) dst[row0 + r] = make_int2(H[r], E[r]);
+          }
+          int hd = diagH;
+          diagH = inH;
+          const int* scol = smat + curQ;
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const int hl = H[r];
+            const int e = max(E[r] + a.ins_ext, hl + a.gap_init);
+            const int fn = max(f + a.del_ext, hu + a.gap_init);
+            const int d = hd + scol[srow[r]];
+            const int hnew = max(max(e, fn), max(d, 0));
+            E[r] = e;
+            f = fn;
+            hd = hl;
+            H[r] = hnew;
+            hu = hnew;
+            blkMax = max(blkMax, hnew);
+          }
+          if (cw == W - 1 && tk.c1 < Q) {
+#pragma unroll
+            for (int r = 0; r < R; r++) edge |= (row0 + r < L) && H[r] >= a.minscore;
+          }
+        }
+        outH = hu;
+        outF = f;
+        if (hasNext) {
+          const int c = b * 32 + j - 31;  // the column lane 31 has just finished
+          if (lane == 31) s_out[wib][c & 31] = make_int2(outH, outF);
+          if (c >= 0 && (c & 31) == 31) {
+            __syncwarp();
+            bndOut[(c & ~31) + lane] = s_out[wib][lane];
+            __syncwarp();  // orders the lanes' stores before lane 0's cumulative release (see swg_origin_kernel)
+            if (lane == 0) st_release(&a.progress[t], (c >> 5) + 1);
+          }
+        }
+      }
+      if (((((b0 + b + 1) >> tk.hotShift) != ((b0 + b) >> tk.hotShift)) || b == nBlocks - 1)) {
+        if (blkMax >= a.minscore) {
+          const int blk = min((b0 + b) >> tk.hotShift, kHotBlocks - 1);
+          atomicOr(&a.hot32[(int64_t)ti * kHotWords + (blk >> 6)], 1ull << (blk & 63));
+        }
+        blkMax = 0;
+      }
+    }
+    if (__any_sync(0xffffffffu, edge) && lane == 0) atomicExch(&a.edgeFlag[ti], 1);
+    __syncwarp();
+    if (lane == 0) st_release(&a.finished[t], 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K2b: block-parallel origin pass (the common path).  A task = one (query, strand, subject) triple x one hot column
 // block [c0, c1) (CB columns, CB = the K1 checkpoint spacing).  Every task starts from K1's exact (H, E') column
 // checkpoint, so all blocks of a triple run in parallel; the subject's 256-row stripes of a task are tickets that
@@ -868,6 +1057,7 @@ struct BlockTask {
   int32_t firstTicket, nStripes;  // one ticket per 256-row stripe; the stripes of a task form a pipeline
   int32_t pad_;
   int64_t ckOff;      // subject's first row in the K1 checkpoint taken before column c0, or -1 (c0 == 0)
+  int64_t ck32Off;    // >= 0: start from this int32 checkpoint of swg_score32_kernel instead (ck32[ck32Off + row] = (H, E))
   int64_t snapOff;    // this task's origin snapshot: snap[snapOff + row] = oH, snap[snapOff + L + row] = oE (0-based row)
 };
 
@@ -887,6 +1077,7 @@ struct BlockArgs {
   int32_t mat[16][16];
   int32_t gap_init, ins_ext, del_ext, minscore;
   const uint2* ck;
+  const int2* ck32;            // int32 checkpoints of the triples whose K1 values wrapped (swg_score32_kernel)
   OriginBoundary* bnd;         // [nslot * bndStride] stripe boundary ring (same protocol as swg_origin_kernel)
   int64_t bndStride;
   int nslot;
@@ -977,7 +1168,22 @@ __global__ void __launch_bounds__(128, 4) swg_origin_block_kernel(BlockArgs a) {
     }
     int diagH = 0;
     uint32_t diagO = 0;
-    if (tk.ckOff >= 0) {
+    if (tk.ck32Off >= 0) {
+      const int2* ck = a.ck32 + tk.ck32Off;
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        if (row0 + r < L) {
+          const int2 v = ck[row0 + r];
+          H[r] = v.x;
+          E[r] = v.y;
+          oH[r] = kPseudoBit | (uint32_t)(row0 + r + 1);
+          oE[r] = kPseudoBit | kPseudoEBit | (uint32_t)(row0 + r + 1);
+        }
+      if (row0 > 0 && row0 - 1 < L) {
+        diagH = ck[row0 - 1].x;
+        diagO = kPseudoBit | (uint32_t)row0;
+      }
+    } else if (tk.ckOff >= 0) {
       const uint2* ck = a.ck + tk.ckOff;
 #pragma unroll
       for (int r = 0; r < R; r++)
