@@ -998,6 +998,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       CUDA_CHECK(cudaMemsetAsync(r.redo, 0, triples.size() * sizeof(int), sq));
       // let the (small, high-priority) fallback sweep take its SM slots first, then fill the rest of the machine
       for (double w0 = now_ms(); afterChain && !chainLaunched.load() && now_ms() - w0 < 100.0;) std::this_thread::yield();
+      const double tLaunch = now_ms() - k2t0;
       EventTimer tm;
       tm.start(sq);
       swg_origin_block_kernel<<<grid, 128, 0, sq>>>(a);
@@ -1008,6 +1009,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       std::vector<int> redoFlag(triples.size(), 0);
       std::vector<unsigned long long> keys(ftableSize), vals(ftableSize);
       CUDA_CHECK(cudaStreamSynchronize(sq));  // as in run_chain: never block inside a pageable copy while the other path launches
+      const double tSync = now_ms() - k2t0;
       CUDA_CHECK(cudaMemcpyAsync(&overflow, a.overflow, sizeof(int), cudaMemcpyDeviceToHost, sq));
       CUDA_CHECK(cudaMemcpyAsync(redoFlag.data(), r.redo, triples.size() * sizeof(int), cudaMemcpyDeviceToHost, sq));
       CUDA_CHECK(cudaMemcpyAsync(keys.data(), r.fkeys, ftableSize * 8, cudaMemcpyDeviceToHost, sq));
@@ -1015,8 +1017,8 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
       CUDA_CHECK(cudaStreamSynchronize(sq));
       check_abort_on("K2b", B.d_abort.p, sq);
       if (dbgK2) {
-        fprintf(stderr, "[K2 dbg] blocks: %zu triples %zu tasks %d tickets grid %d  kernels %.2f ms (done at +%.2f ms)\n", trIdx.size(),
-                tasks.size(), nTickets, grid, tm.ms(), now_ms() - k2t0);
+        fprintf(stderr, "[K2 dbg] blocks: %zu triples %zu tasks %d tickets grid %d  kernels %.2f ms (launched at +%.2f, done at +%.2f, results on the host at +%.2f ms)\n",
+                trIdx.size(), tasks.size(), nTickets, grid, tm.ms(), tLaunch, tSync, now_ms() - k2t0);
         unsigned long long d[72];
         CUDA_CHECK(cudaMemcpy(d, a.dbg, 72 * 8, cudaMemcpyDeviceToHost));
         fprintf(stderr, "[K2 dbg] blocks: last ticket of stripe level k ended at (ms):");
@@ -1438,7 +1440,7 @@ void rmgpu_session::run_origin(const rmgpu_params& p, const std::vector<int32_t>
   static const bool serialK2 = getenv("RMGPU_K2_SERIAL") != nullptr;  // measurement: the two paths one after the other
   if (serialK2 && chainThread.joinable()) chainThread.join();
   try {
-    run_blocks(blockTr, false, redo, bb[0], stream, found, psMain, true);
+    run_blocks(blockTr, false, redo, bb[0], stream, found, psMain, !chainTr.empty());
     if (!redo.empty()) {
       psMain.redo += (int)redo.size();
       std::vector<int> none;

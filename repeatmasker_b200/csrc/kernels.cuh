@@ -969,60 +969,69 @@ __global__ void __launch_bounds__(128) swg_score32_kernel(WideArgs a) {
       __syncwarp();  // everyone is done with the previous block's feed
       s_feed[wib][lane] = fv;
       __syncwarp();
+      // The 32 columns of the block.  SLOW: the first block (lanes wait for their first column), a block that starts with
+      // a checkpoint, and the last two (edge test); every other block runs without those per-column tests.
+      auto columns = [&](auto slowTag) {
+        constexpr bool SLOW = decltype(slowTag)::value;
 #pragma unroll 4
-      for (int j = 0; j < 32; j++) {
-        const int4 fd = s_feed[wib][j];  // broadcast read; only lane 0 uses it
-        int inQ = __shfl_up_sync(0xffffffffu, curQ, 1);
-        int inH = __shfl_up_sync(0xffffffffu, outH, 1);
-        int inF = __shfl_up_sync(0xffffffffu, outF, 1);
-        inQ = lane == 0 ? fd.x : inQ;
-        inH = lane == 0 ? fd.y : inH;
-        inF = lane == 0 ? fd.z : inF;
-        curQ = inQ;
-        const int cw = b * 32 + j - lane;  // column inside the window, 0-based
-        int hu = inH, f = inF;
-        if (cw >= 0) {  // before its first column a lane keeps its (checkpointed) state untouched
-          if (cw > 0 && (cw & ckMask) == 0 && cw < W) {
-            int2* dst = a.ck32 + tk.ck32Off + (int64_t)(cw >> ckShift) * L;
+        for (int j = 0; j < 32; j++) {
+          const int4 fd = s_feed[wib][j];  // broadcast read; only lane 0 uses it
+          int inQ = __shfl_up_sync(0xffffffffu, curQ, 1);
+          int inH = __shfl_up_sync(0xffffffffu, outH, 1);
+          int inF = __shfl_up_sync(0xffffffffu, outF, 1);
+          inQ = lane == 0 ? fd.x : inQ;
+          inH = lane == 0 ? fd.y : inH;
+          inF = lane == 0 ? fd.z : inF;
+          curQ = inQ;
+          const int cw = b * 32 + j - lane;  // column inside the window, 0-based
+          int hu = inH, f = inF;
+          if (!SLOW || cw >= 0) {  // before its first column a lane keeps its (checkpointed) state untouched
+            if (SLOW && cw > 0 && (cw & ckMask) == 0 && cw < W) {
+              int2* dst = a.ck32 + tk.ck32Off + (int64_t)(cw >> ckShift) * L;
 #pragma unroll
-            for (int r = 0; r < R; r++)
-              if (row0 + r < L) dst[row0 + r] = make_int2(H[r], E[r]);
+              for (int r = 0; r < R; r++)
+                if (row0 + r < L) dst[row0 + r] = make_int2(H[r], E[r]);
+            }
+            int hd = diagH;
+            diagH = inH;
+            const int* scol = smat + curQ;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              const int hl = H[r];
+              const int e = max(E[r] + a.ins_ext, hl + a.gap_init);
+              const int fn = max(f + a.del_ext, hu + a.gap_init);
+              const int d = hd + scol[srow[r]];
+              const int hnew = max(max(e, fn), max(d, 0));
+              E[r] = e;
+              f = fn;
+              hd = hl;
+              H[r] = hnew;
+              hu = hnew;
+              blkMax = max(blkMax, hnew);
+            }
+            if (SLOW && cw == W - 1 && tk.c1 < Q) {
+#pragma unroll
+              for (int r = 0; r < R; r++) edge |= (row0 + r < L) && H[r] >= a.minscore;
+            }
           }
-          int hd = diagH;
-          diagH = inH;
-          const int* scol = smat + curQ;
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            const int hl = H[r];
-            const int e = max(E[r] + a.ins_ext, hl + a.gap_init);
-            const int fn = max(f + a.del_ext, hu + a.gap_init);
-            const int d = hd + scol[srow[r]];
-            const int hnew = max(max(e, fn), max(d, 0));
-            E[r] = e;
-            f = fn;
-            hd = hl;
-            H[r] = hnew;
-            hu = hnew;
-            blkMax = max(blkMax, hnew);
-          }
-          if (cw == W - 1 && tk.c1 < Q) {
-#pragma unroll
-            for (int r = 0; r < R; r++) edge |= (row0 + r < L) && H[r] >= a.minscore;
+          outH = hu;
+          outF = f;
+          if (hasNext) {
+            const int c = b * 32 + j - 31;  // the column lane 31 has just finished
+            if (lane == 31) s_out[wib][c & 31] = make_int2(outH, outF);
+            if (c >= 0 && (c & 31) == 31) {
+              __syncwarp();
+              bndOut[(c & ~31) + lane] = s_out[wib][lane];
+              __syncwarp();  // orders the lanes' stores before lane 0's cumulative release (see swg_origin_kernel)
+              if (lane == 0) st_release(&a.progress[t], (c >> 5) + 1);
+            }
           }
         }
-        outH = hu;
-        outF = f;
-        if (hasNext) {
-          const int c = b * 32 + j - 31;  // the column lane 31 has just finished
-          if (lane == 31) s_out[wib][c & 31] = make_int2(outH, outF);
-          if (c >= 0 && (c & 31) == 31) {
-            __syncwarp();
-            bndOut[(c & ~31) + lane] = s_out[wib][lane];
-            __syncwarp();  // orders the lanes' stores before lane 0's cumulative release (see swg_origin_kernel)
-            if (lane == 0) st_release(&a.progress[t], (c >> 5) + 1);
-          }
-        }
-      }
+      };
+      if (b == 0 || ((b * 32) & ckMask) == 0 || b >= qBlocks - 1)
+        columns(std::true_type{});
+      else
+        columns(std::false_type{});
       if (((((b0 + b + 1) >> tk.hotShift) != ((b0 + b) >> tk.hotShift)) || b == nBlocks - 1)) {
         if (blkMax >= a.minscore) {
           const int blk = min((b0 + b) >> tk.hotShift, kHotBlocks - 1);

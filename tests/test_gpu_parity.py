@@ -143,6 +143,45 @@ def test_int16_overflow_at_both_ends_of_the_query(tmp_path):
     assert_same_hits(got, want)
 
 
+def test_int16_overflow_fan_leaves_the_window(tmp_path):
+    """A 100,000-point alignment (12 kbp subject) followed by 40 kbp of background: the decaying fan to its right (-6 per
+    column) is still above minscore where the stretched window of the int32 score pass (K2w) ends, so the pass raises
+    its edge flag and the triple takes the one-sweep path (with that path's own full-width redo); a second, shorter
+    wrapped copy on the other strand of a second subject stays on the K2w + block-parallel path.  Subject lengths are
+    not multiples of the 64-row stripes."""
+    rng = np.random.default_rng(79)
+    long_s = synth.random_dna(rng, 12011).tobytes().decode()
+    long_t = synth.random_dna(rng, 6521).tobytes().decode()
+    copy1 = synth.mutate(rng, long_s[200:11800], 0.01, 0.001)
+    copy2 = synth.revcomp(synth.mutate(rng, long_t[100:6400], 0.05, 0.004))
+    bg = synth.random_dna(rng, 52000).tobytes().decode()
+    q = bg[:1500] + copy1 + bg[1500:41500] + copy2 + bg[41500:44000]
+    got, want, st = both(tmp_path, ["q1"], [q], ["longS#LINE/L1", "longT#LINE/L1"], [long_s, long_t])
+    assert sum(h["score"] > 32767 for h in want) == 2 and max(h["score"] for h in want) > 95000
+    assert_same_hits(got, want)
+    assert st["n_origin_redo"] >= 1
+
+
+def test_many_wrapped_triples_share_one_int32_pass(tmp_path):
+    """Six query records, each with a > 32767-point copy of one of three long subjects at a different offset (first
+    column block, middle, last block) and strand: all wrapped triples go through one K2w launch and one K2b launch."""
+    rng = np.random.default_rng(80)
+    subj = [synth.random_dna(rng, n).tobytes().decode() for n in (7000, 7777, 8191)]
+    qn, qs = [], []
+    for i in range(6):
+        sq = subj[i % 3]
+        cp = synth.mutate(rng, sq[50:len(sq) - 50], 0.02 + 0.01 * (i % 3), 0.002)
+        if i & 1:
+            cp = synth.revcomp(cp)
+        bg = synth.random_dna(rng, 16000).tobytes().decode()
+        off = (0, 7000, 16000)[i % 3] if i < 3 else (16000, 0, 7000)[i % 3]
+        qn.append(f"q{i}")
+        qs.append(bg[:off] + cp + bg[off:])
+    got, want, st = both(tmp_path, qn, qs, [f"L{i}#LINE/L1" for i in range(3)], subj)
+    assert sum(h["score"] > 32767 for h in want) == 6
+    assert_same_hits(got, want)
+
+
 def test_traceback_band_retries(tmp_path):
     """Alignments whose path leaves the first traceback band W = bandwidth + max(n, m) / 32 (an insertion and, further
     on, a deletion of the same size: the end points stay on the main diagonal, the path does not) are found with the
