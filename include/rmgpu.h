@@ -126,6 +126,13 @@ int rmgpu_session_set_queries_fasta(rmgpu_session *s, const char *query_fasta);
  * children, RepeatMasker:1040-1180): records of file f are first_record[f] .. first_record[f+1]-1 of the batch
  * (first_record holds n_files + 1 entries); rmgpu_hit::query_index tells the results apart. */
 int rmgpu_session_set_queries_fasta_multi(rmgpu_session *s, int32_t n_files, const char *const *files, int32_t *first_record);
+/* Stage chain on a resident batch: mask what a stage found -- n ranges, record index as in
+ * rmgpu_hit::query_index, 1-based inclusive coordinates -- with X, on the device, as RepeatMasker does between two
+ * stages of a -species run (`$seqDB->setSubstr( $name, $begin - 1, $len, 'X' x $len )`, RepeatMasker:6036-6090; stage
+ * chain :4115-4654).  The next rmgpu_session_search (usually after rmgpu_session_set_library* with the next stage's
+ * library, which may already be resident) sees the masked batch; nothing is uploaded again.  (Added in ABI 3.) */
+int rmgpu_session_mask_queries(rmgpu_session *s, int32_t n, const int32_t *query_index, const int32_t *qstart,
+                               const int32_t *qend);
 /* Run the search on the resident batch x resident library. */
 int rmgpu_session_search(rmgpu_session *s, const rmgpu_params *p, rmgpu_result **out);
 /* K1 only, on resident data: best raw Smith-Waterman-Gotoh score per (query, subject, strand).

@@ -266,6 +266,8 @@ struct rmgpu_session {
 
   void set_library(SeqSet s);
   void set_queries(SeqSet s);
+  void mask_queries(int32_t n, const int32_t* qi, const int32_t* qstart, const int32_t* qend);
+  DevBuf<int32_t> d_maskRanges;
   void build_classes_and_profile();
   void run_score(const rmgpu_params& p, std::vector<int32_t>& pairbest, std::vector<unsigned long long>& hotmask,
                  double& ms, int& launches, bool exact);  // the whole batch in one launch, waited for
@@ -417,7 +419,7 @@ void rmgpu_session::set_queries(SeqSet s) {
     h_hotShift.push_back(sh);
   }
   selTotal = h_selOff[n];
-  std::vector<uint8_t> packed((size_t)(h_qoff[n] / 2 + 1), 0);
+  std::vector<uint8_t> packed((size_t)(((h_qoff[n] / 2 + 1) + 7) & ~3ll), 0);  // whole 32-bit words (mask_queries works on words)
   for (auto& c : canonCounts) c = 0;
   {
     // every record starts on a byte of `packed` (even nibble offsets), so records are packed independently
@@ -455,6 +457,49 @@ void rmgpu_session::set_queries(SeqSet s) {
   CUDA_CHECK(cudaStreamSynchronize(stream));
   ms_h2d_queries = now_ms() - t0;
   h2d_bytes_queries = (int64_t)packed.size() + (int64_t)(n + 1) * 24;
+}
+
+// Masks ranges of the resident batch with X on the device and in the host copy (the rows of later hits are spelled from
+// it): the engine's half of RepeatMasker's stage chain, which masks what a stage found before the next stage searches
+// the same batch against another library (RepeatMasker:4115-4654, :6036-6090).  1-based inclusive coordinates, as in
+// rmgpu_hit; ranges may overlap.  The residue statistics, class map and K0 streams are rebuilt before the next search.
+void rmgpu_session::mask_queries(int32_t n, const int32_t* qi, const int32_t* qstart, const int32_t* qend) {
+  if (!haveQueries) throw Error("mask_queries: no query batch is resident");
+  const CanonTables& ct = canon();
+  const uint8_t X = ct.of_letter[(unsigned char)'X'];
+  std::vector<int32_t> ranges;
+  for (int32_t r = 0; r < n; r++) {
+    if (qi[r] < 0 || qi[r] >= (int32_t)queries.seqs.size()) throw Error("mask_queries: query index out of range");
+    std::string& q = queries.seqs[qi[r]];
+    const int64_t p0 = std::max<int64_t>((int64_t)qstart[r] - 1, 0), p1 = std::min<int64_t>((int64_t)qend[r], (int64_t)q.size());
+    if (p0 >= p1) continue;
+    for (int64_t k = p0; k < p1; k++) {
+      const uint8_t c = ct.of_letter[(unsigned char)q[k]];
+      if (c != X || q[k] != 'X') {
+        canonCounts[c]--;
+        canonCounts[ct.comp[c]]--;
+        canonCounts[X]++;
+        canonCounts[ct.comp[X]]++;
+        q[k] = 'X';
+      }
+    }
+    ranges.push_back(qi[r]);
+    ranges.push_back((int32_t)p0);
+    ranges.push_back((int32_t)p1);
+  }
+  if (ranges.empty()) return;
+  d_maskRanges.upload(ranges, stream);
+  MaskArgs a;
+  a.qpacked = reinterpret_cast<uint32_t*>(d_qpacked.p);
+  a.qoff = d_qoff.p;
+  a.ranges = d_maskRanges.p;
+  a.n = (int)(ranges.size() / 3);
+  a.code = X;
+  mask_queries_kernel<<<std::min(a.n, numSMs * 8), 256, 0, stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  queries.mark_exotic();
+  streamsValid = false;
 }
 
 // Residue classes of the score pass and the per-column selector / code streams (K0).  Depends on the matrix (which letters
@@ -2139,6 +2184,13 @@ int rmgpu_session_set_queries_fasta_multi(rmgpu_session* s, int32_t n_files, con
     }
     first_record[n_files] = (int32_t)all.seqs.size();
     s->set_queries(std::move(all));
+  });
+}
+
+int rmgpu_session_mask_queries(rmgpu_session* s, int32_t n, const int32_t* query_index, const int32_t* qstart, const int32_t* qend) {
+  return guarded([&] {
+    CUDA_CHECK(cudaSetDevice(s->device));
+    s->mask_queries(n, query_index, qstart, qend);
   });
 }
 

@@ -138,6 +138,32 @@ __global__ void build_profile_kernel(ProfileArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// K0m: mask ranges of the RESIDENT query batch (what RepeatMasker's stage chain does between two searches of the same
+// batch, RepeatMasker:6036-6090: `$seqDB->setSubstr( $name, $begin - 1, $len, 'X' x $len )`).  One block per range; a
+// position is one nibble of the packed batch, set with two idempotent atomics (ranges may overlap or share a word).
+// ---------------------------------------------------------------------------------------------------------------
+struct MaskArgs {
+  uint32_t* qpacked;        // the packed batch viewed as 32-bit words (8 nibbles each)
+  const int64_t* qoff;      // nibble offset of each record
+  const int32_t* ranges;    // [n * 3]: record, first position (0-based), end position (exclusive)
+  int n;
+  uint32_t code;            // canonical code written (X)
+};
+
+__global__ void mask_queries_kernel(MaskArgs a) {
+  for (int r = blockIdx.x; r < a.n; r += gridDim.x) {
+    const int q = a.ranges[3 * r], p0 = a.ranges[3 * r + 1], p1 = a.ranges[3 * r + 2];
+    const int64_t base = a.qoff[q];
+    for (int p = p0 + (int)threadIdx.x; p < p1; p += (int)blockDim.x) {
+      const int64_t nib = base + p;
+      const int sh = (int)(nib & 7) * 4;
+      atomicAnd(&a.qpacked[nib >> 3], ~(0xFu << sh));
+      atomicOr(&a.qpacked[nib >> 3], a.code << sh);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K1: score pass.  Each lane owns R consecutive subject rows (a "group"); the two 16-bit halves of every register
 // are the forward and the reverse-complement strand of the same query (identical dimensions, so they pair
 // perfectly).  With E' = E - gap_init and F' = F - gap_init every state value is >= 0:

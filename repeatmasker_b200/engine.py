@@ -58,7 +58,8 @@ EXPORTS = ["rmgpu_version", "rmgpu_abi_version", "rmgpu_last_error", "rmgpu_sear
            "rmgpu_session_search", "rmgpu_session_score_only", "rmgpu_session_counts", "rmgpu_measure_dpx_peak",
            "rmgpu_server_ping", "rmgpu_server_quit", "rmgpu_kimura_divergence", "rmgpu_matrix_info",
            "rmgpu_adjusted_score", "rmgpu_masklevel_filter", "rmgpu_contained_filter",
-           "rmgpu_session_library_h2d_bytes", "rmgpu_session_set_queries_fasta_multi", "rmgpu_device_count"]
+           "rmgpu_session_library_h2d_bytes", "rmgpu_session_set_queries_fasta_multi", "rmgpu_device_count",
+           "rmgpu_session_mask_queries"]
 
 
 def lib():
@@ -87,6 +88,7 @@ def lib():
     L.rmgpu_session_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)]
     L.rmgpu_session_library_h2d_bytes.argtypes = [C.c_void_p]
+    L.rmgpu_session_mask_queries.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rmgpu_session_library_h2d_bytes.restype = C.c_int64
     L.rmgpu_measure_dpx_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     fargs = [C.c_int, C.c_int32] + [C.POINTER(C.c_int32)] * 4 + [C.c_int32, C.POINTER(C.c_uint8)]
@@ -226,6 +228,13 @@ class Session:
 
     def set_queries_fasta(self, path):
         _check(lib().rmgpu_session_set_queries_fasta(self._h, path.encode()))
+
+    def mask_queries(self, ranges):
+        """Mask (query index, qstart, qend) ranges -- 1-based inclusive, as in the hit records -- of the RESIDENT batch
+        with X on the device: what RepeatMasker does to a batch between two stages (RepeatMasker:6036-6090)."""
+        n = len(ranges)
+        arr = lambda k: (C.c_int32 * max(n, 1))(*[int(r[k]) for r in ranges])
+        _check(lib().rmgpu_session_mask_queries(self._h, n, arr(0), arr(1), arr(2)))
 
     def counts(self):
         nq, ns, qb, sb = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
