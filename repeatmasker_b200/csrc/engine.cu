@@ -669,11 +669,27 @@ void rmgpu_session::prepare_score(const rmgpu_params& p, bool exact) {
 
 void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, int nQ, bool exact) {
   const int nS = (int)lib.seqs.size();
+  // the instantiation: gap penalties of RepeatMasker's crossmatch recipes as immediates, anything else from registers
+  using ScoreKernel = void (*)(ScoreArgs);
+  const int gi = p.gap_init, ie = p.ins_gap_ext, df = std::max(p.del_gap_ext, p.gap_init);
+  static const bool noImm = getenv("RMGPU_K1_NO_IMMEDIATES") != nullptr;
+  ScoreKernel kern = exact ? (ScoreKernel)swg_score_kernel<R, true> : (ScoreKernel)swg_score_kernel<R, false>;
+  if (!exact && !noImm) {
+    // the (gap_init, ins_gap_ext, del_gap_ext) of the crossmatch recipes (RepeatMasker:2127-2480; all but the low-complexity
+    // stage's -10/-3/-3, which runs the generic instantiation)
+#define RMGPU_K1_IMM(G, I, D) \
+  if (gi == (G) && ie == (I) && df == (D)) kern = swg_score_kernel<R, false, (G), (I), (D)>;
+    RMGPU_K1_IMM(-30, -6, -5)
+    RMGPU_K1_IMM(-27, -6, -5)
+    RMGPU_K1_IMM(-35, -7, -6)
+    RMGPU_K1_IMM(-33, -5, -4)
+    RMGPU_K1_IMM(-27, -5, -5)
+    RMGPU_K1_IMM(-40, -15, -15)
+    RMGPU_K1_IMM(-35, -10, -10)
+#undef RMGPU_K1_IMM
+  }
   int blocksPerSM = 0;
-  if (exact)
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R, true>, kScoreWarps * 32, 0));
-  else
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, swg_score_kernel<R, false>, kScoreWarps * 32, 0));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, kScoreWarps * 32, 0));
   if (blocksPerSM < 1) throw Error("K1 does not fit on an SM");
   const int64_t nTickets = (int64_t)nQ * nStripes;
   if (nTickets >= (1ll << 31)) throw Error("too many stripe tasks in one batch");
@@ -740,10 +756,7 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
   sl.cleanPtr = nullptr;
   sl.cleanBytes = 0;
   CUDA_CHECK(cudaEventRecord(sl.evStart, sl.stream));
-  if (exact)
-    swg_score_kernel<R, true><<<grid, kScoreWarps * 32, 0, sl.stream>>>(a);
-  else
-    swg_score_kernel<R, false><<<grid, kScoreWarps * 32, 0, sl.stream>>>(a);
+  kern<<<grid, kScoreWarps * 32, 0, sl.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(sl.evStop, sl.stream));
 }

@@ -234,8 +234,15 @@ constexpr int kK1Unroll = 8;  // columns per trip of K1's inner loop (4: +3 % ti
 // a sample sees every H of the previous 8 columns of its row less at most 7*|ins_ext|; the host lowers its thresholds
 // by that slack (ScoreArgs::minscore already includes it), which keeps the filter free of false negatives and saves
 // 6 of the 104 integer-pipe instructions per lane-column.
-template <int R, bool EXACT>
+// GI / IE / DF != 0: gap_init, ins_gap_ext and max(del_gap_ext, gap_init) are compile-time constants, so the four
+// VIADDMNMX of a packed cell carry them as 32-bit immediates (two register reads instead of three, three registers
+// free); instantiated for the gap penalties of RepeatMasker's crossmatch recipes (RepeatMasker:2146-2366), any other
+// penalties run the generic instantiation with the constants in registers.
+template <int R, bool EXACT, int GI = 0, int IE = 0, int DF = 0>
 __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArgs a) {
+  const uint32_t gi2 = GI ? (uint32_t)(uint16_t)GI * 0x10001u : a.gi2;
+  const uint32_t ie2 = IE ? (uint32_t)(uint16_t)IE * 0x10001u : a.ie2;
+  const uint32_t df2 = DF ? (uint32_t)(uint16_t)DF * 0x10001u : a.df2;
   __shared__ uint4 s_feed[kScoreWarps][33];  // (selector, H above, F' above) for the 32 columns of the current block
                                              // + the selector of the next block's first column
   __shared__ uint2 s_out[kScoreWarps][32];   // last row's (H, F') of the last 32 columns lane 31 finished
@@ -373,11 +380,11 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           for (int r = 0; r < R; r++) {
             const uint32_t s = prmt(Plo[r], Phi[r], curSel);
             const uint32_t hl = H[r];
-            E[r] = __viaddmax_s16x2(E[r], a.ie2, hl);                  // E'[i][j]
+            E[r] = __viaddmax_s16x2(E[r], ie2, hl);                    // E'[i][j]
             const uint32_t d = __vadd2(hd, s);                         // H[i-1][j-1] + s
-            const uint32_t tt = __viaddmax_s16x2_relu(E[r], a.gi2, d);  // T = max(0, diag, E'+gi): H without F
-            h = __viaddmax_s16x2(f, a.gi2, tt);                        // H = max(T, F'+gi)          (off the chain)
-            f = __viaddmax_s16x2(f, a.df2, tt);                        // F' of the next row         (the only chain)
+            const uint32_t tt = __viaddmax_s16x2_relu(E[r], gi2, d);    // T = max(0, diag, E'+gi): H without F
+            h = __viaddmax_s16x2(f, gi2, tt);                          // H = max(T, F'+gi)          (off the chain)
+            f = __viaddmax_s16x2(f, df2, tt);                          // F' of the next row         (the only chain)
             hd = hl;
             H[r] = h;
             if (EXACT) bestBlk = __vmaxs2(bestBlk, h);

@@ -266,8 +266,13 @@ def test_letters_outside_the_iupac_alphabet(tmp_path):
     assert_same_hits(got, want)
 
 
+# the score pass has an instantiation per gap-penalty set of the crossmatch recipes (RepeatMasker:2127-2480), with the
+# penalties as immediates, and a generic one (last two rows: penalties no recipe uses, del_gap_ext below gap_init)
 @pytest.mark.parametrize("matrix,gi,ie,de", [("14p41g.matrix", -35, -7, -6), ("18p41g.matrix", -30, -6, -5),
-                                            ("25p41g.matrix", -27, -6, -5)])
+                                            ("25p41g.matrix", -27, -6, -5), ("20p41g.matrix", -33, -5, -4),
+                                            ("20p41g.matrix", -27, -5, -5), ("20p41g.matrix", -40, -15, -15),
+                                            ("18p41g.matrix", -35, -10, -10),
+                                            ("20p41g.matrix", -28, -4, -3), ("18p41g.matrix", -25, -5, -30)])
 @pytest.mark.parametrize("raw", [False, True])
 def test_matrix_sweep(tmp_path, matrix, gi, ie, de, raw):
     """BASELINE config 4 in miniature: GC-binned matrices x recipes (RepeatMasker:2146-2366), adjusted and -raw,

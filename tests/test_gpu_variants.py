@@ -2,7 +2,8 @@
 RMGPU_K2_FULL=1 sweeps every passing triple with origins over the whole fragment; RMGPU_NO_CHECKPOINTS=1 uses the
 score-only / origin mode mask from column 0; RMGPU_QUERY_CHUNK=2 forces the memory-bounded chunking of query records;
 RMGPU_NO_WIDE=1 sends the triples whose int16 scores wrapped through the one-sweep path instead of the int32 score pass
-(K2w) + block-parallel origin pass.  The switches are read once per process, hence the subprocesses."""
+(K2w) + block-parallel origin pass; RMGPU_K1_NO_IMMEDIATES=1 runs the generic instantiation of the score pass (gap
+penalties in registers) where a recipe's penalties would select one with immediates.  The switches are read once per process, hence the subprocesses."""
 import os
 import subprocess
 import sys
@@ -15,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("var,val", [("RMGPU_K2_FULL", "1"), ("RMGPU_NO_CHECKPOINTS", "1"), ("RMGPU_QUERY_CHUNK", "2"),
-                                     ("RMGPU_NO_WIDE", "1")])
+                                     ("RMGPU_NO_WIDE", "1"), ("RMGPU_K1_NO_IMMEDIATES", "1")])
 def test_origin_pass_fallbacks_match_oracle(var, val):
     env = dict(os.environ, **{var: val})
     res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
