@@ -410,6 +410,84 @@ __global__ void cellLp(uint32_t* out, int iters, uint32_t seed, uint32_t gi2, ui
   out[blockIdx.x * blockDim.x + threadIdx.x] = best;
 }
 
+
+// ---- the same cells with the gap constants as compile-time literals: VIADDMNMX / VIADD.16x2 take them as 32-bit immediates
+// (two register operands instead of three).  Ai = cell A, Li / Lpi = the VIMNMX3 cells (4 alu-pipe instructions per packed cell).
+template <int R>
+__global__ void cellAi(uint32_t* out, int iters, uint32_t seed) {
+  constexpr uint32_t gi2 = 0xffe2ffe2u, ie2 = 0xfffafffau, de2 = 0xfffbfffbu;
+  uint32_t Plo[R], Phi[R], H[R], E[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    Plo[r] = 0x090af1f0u + r * 0x01010101u + threadIdx.x;
+    Phi[r] = 0xf1f60a09u ^ (r * 0x00010001u);
+    H[r] = 0;
+    E[r] = 0;
+  }
+  uint32_t best = 0, sel = 0x9180u | (seed & 0x0303u), diag = 0, hu = 0, f = 0;
+  for (int it = 0; it < iters; it++) {
+    uint32_t hd = diag;
+    diag = hu;
+    sel = ((sel + 0x0101u) & 0x0303u) | 0x9180u;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      uint32_t s = prmt(Plo[r], Phi[r], sel);
+      uint32_t hl = H[r];
+      E[r] = __viaddmax_s16x2(E[r], ie2, hl);
+      uint32_t d = __vadd2(hd, s);
+      uint32_t tt = __viaddmax_s16x2_relu(E[r], gi2, d);
+      uint32_t h = __viaddmax_s16x2(f, gi2, tt);
+      f = __viaddmax_s16x2(f, de2, tt);
+      hd = hl;
+      H[r] = h;
+      hu = h;
+    }
+    if ((it & 7) == 7) {
+#pragma unroll
+      for (int r = 0; r < R; r++) best = __vmaxs2(best, E[r]);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = best;
+}
+
+template <int R, bool LAUNDER>
+__global__ void cellLi(uint32_t* out, int iters, uint32_t seed, uint32_t one) {
+  constexpr uint32_t gi2 = 0xffe2ffe2u, ie2 = 0xfffafffau, de2 = 0xfffbfffbu;
+  uint32_t Plo[R], Phi[R], Hg[R], E[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    Plo[r] = 0x090a0100u + r * 0x01010101u + (threadIdx.x & 3);
+    Phi[r] = 0x01060a09u ^ (r * 0x00010001u);
+    Hg[r] = gi2;
+    E[r] = gi2;
+  }
+  uint32_t best = 0, sel = 0x9180u | (seed & 0x0303u), diag = gi2, hgu = gi2, f = gi2;
+  for (int it = 0; it < iters; it++) {
+    uint32_t hd = diag;
+    diag = hgu;
+    sel = ((sel + 0x0101u) & 0x0303u) | 0x9180u;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      uint32_t s = prmt(Plo[r], Phi[r], sel);
+      uint32_t hl = Hg[r];
+      E[r] = __viaddmax_s16x2(E[r], ie2, hl);
+      uint32_t d = __vadd2(hd, s);
+      if (LAUNDER) d *= one;
+      uint32_t h = __vimax3_s16x2_relu(d, E[r], f);
+      uint32_t hg = __vadd2(h, gi2);
+      f = __viaddmax_s16x2(f, de2, hg);
+      hd = hl;
+      Hg[r] = hg;
+      hgu = hg;
+    }
+    if ((it & 7) == 7) {
+#pragma unroll
+      for (int r = 0; r < R; r++) best = __vmaxs2(best, E[r]);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = best;
+}
+
 // S: round-1 recurrence with the score looked up in shared memory instead of PRMT: a table of packed (forward, reverse)
 // scores per (subject residue, query class pair), replicated per lane (entry stride 128 B: bank = lane, no conflicts);
 // address = row term (fixed per row and ticket) + column term (changes per column).  IMADADDR: the address add as an IMAD
@@ -580,7 +658,8 @@ static void run_rate(uint32_t* d, int sms, double clk_hz, int warpsPerSM) {
 
 int main(int argc, char** argv) {
   const bool full = argc > 1 && argv[1][0] == 'f';
-  const bool cellsOnly = argc > 1 && argv[1][0] == 'c';  // for ncu: one pass of the cell loops at 24 warps/SM
+  const bool immOnly = argc > 1 && argv[1][0] == 'i';     // only the cells with immediate gap constants
+  const bool cellsOnly = (argc > 1 && argv[1][0] == 'c') || immOnly;  // for ncu: one pass of the cell loops at 24 warps/SM
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, 0);
   int clk_khz = 0;
@@ -622,7 +701,8 @@ int main(int argc, char** argv) {
   cudaEventCreate(&b);
   const uint32_t gi2 = 0xffe2ffe2u, ie2 = 0xfffafffau, de2 = 0xfffbfffbu, twoG2 = 0x003c003cu;
   for (int warps : {16, 20, 24, 32}) {
-    if (cellsOnly && warps != 24) continue;
+    if (cellsOnly && !immOnly && warps != 24) continue;
+    if (immOnly && warps != 16) continue;
     const int threads = 128, blocks = sms * (warps * 32 / threads), iters = 20000;
     auto report = [&](const char* name, int R, double ms) {
       printf("%-28s R=%2d warps/SM %2d  %8.3f ms  %8.1f GCUPS\n", name, R, warps, ms, (double)blocks * threads * R * (double)iters * 2.0 / (ms * 1e-3) / 1e9);
@@ -637,6 +717,11 @@ int main(int argc, char** argv) {
     best = fmin(best, time_ms(a, b));      \
   }                                        \
   report(NAME, R, best);
+    RUN("cell Ai (A, immediates)", 16, (cellAi<16><<<blocks, threads>>>(d, iters, rep)));
+    RUN("cell Li (VIMNMX3, immediates)", 16, (cellLi<16, false><<<blocks, threads>>>(d, iters, rep, 1u)));
+    RUN("cell Lpi (VIMNMX3 forced, imm.)", 16, (cellLi<16, true><<<blocks, threads>>>(d, iters, rep, 1u)));
+    RUN("cell Lpi (VIMNMX3 forced, imm.)", 12, (cellLi<12, true><<<blocks, threads>>>(d, iters, rep, 1u)));
+    if (immOnly) continue;
     RUN("cell A (round 1)", 8, (cellA<8><<<blocks, threads>>>(d, iters, rep, gi2, ie2, de2)));
     RUN("cell A (round 1)", 16, (cellA<16><<<blocks, threads>>>(d, iters, rep, gi2, ie2, de2)));
     RUN("cell A1 (E split)", 16, (cellA1<16><<<blocks, threads>>>(d, iters, rep, gi2, ie2, de2)));
