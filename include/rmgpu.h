@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RMGPU_ABI_VERSION 3
+#define RMGPU_ABI_VERSION 4
 
 /* Search parameters.  Replaces the argv that CrossmatchSearchEngine.pm:277-363 (getParameters) builds from the
  * SearchEngineI.pm:132-681 setters:
@@ -183,6 +183,21 @@ void rmgpu_kimura_divergence(const char *qaln, const char *saln, int strand, cha
  * raw score over the aligned query letters of one alignment (SearchResult.pm:2111-2150).  Both return 0 on success. */
 int rmgpu_matrix_info(const char *matrix_file, int32_t *n, char alphabet[17], double *lambda, double freqs[16]);
 int rmgpu_adjusted_score(const char *matrix_file, int32_t raw, const char *qaln, const char *saln, int32_t *adjusted);
+
+/* Host-only: the alignment block of one .cat entry, i.e. everything SearchResult::_toCrossMatchFormat
+ * (SearchResult.pm:2486-2834) appends to the annotation line in mode AlignWithQuerySeq -- the 50-column chunks with
+ * coordinates, the line of difference marks (i v - ?) between the rows, and the Matrix / Kimura / transitions /
+ * gap statistics trailer -- from the fields a SearchResult object holds: names, rows with the query forward
+ * (SearchResult::getQueryString / getSubjString), 1-based coordinates, strand 1 = orientation "C" (subject coordinates
+ * descend).  matrix_name, pct_kimura, cpg_sites, pct_raw_kimura may be NULL (undef in the object; the last two are printed
+ * only together).  Writes at most cap-1 bytes + NUL into out (out may be NULL) and returns the full length, or -1 when
+ * the rows differ in length.  GpuSearchEngine.pm's GpuSearchResult::_toCrossMatchFormat calls it, so the driver's own
+ * `$collection->write( $catfile, SearchResult::AlignWithQuerySeq )` (RepeatMasker:1489) no longer walks every column in
+ * Perl.  (Added in ABI 4.) */
+int64_t rmgpu_format_alignment(const char *query_name, const char *subject_name, const char *qaln, const char *saln,
+                               int64_t qstart, int64_t qend, int64_t sstart, int64_t send, int strand,
+                               const char *matrix_name, const char *pct_kimura, const char *cpg_sites,
+                               const char *pct_raw_kimura, char *out, int64_t cap);
 
 #ifdef __cplusplus
 }

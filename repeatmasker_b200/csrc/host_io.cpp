@@ -6,6 +6,7 @@
 #include <fstream>
 #include <sstream>
 
+#include "../../include/rmgpu.h"
 #include "host.hpp"
 
 namespace rmgpu {
@@ -292,4 +293,164 @@ int complexity_adjust(int raw, const int64_t counts[kMaxAlpha], const ScoreMatri
   return v < 0 ? 0 : v;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// The alignment block of a .cat file entry.  What SearchResult::_toCrossMatchFormat
+// (SearchResult.pm:2486-2834) appends to the annotation line in mode AlignWithQuerySeq: 50-column chunks of
+// "  <name 13> <start 10> <row> <end>", the line of difference marks between them (i transition, v transversion,
+// - gap, ? a pair with an ambiguity code), then the Matrix / Kimura / transition / gap statistics.  The reference walks
+// every column in Perl; the batch children of a run spend more time here than the GPU spends searching.
+// Rows are the ones the SearchResult object holds (query forward; for orientation C the subject coordinates descend).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+inline bool ambiguity_code(int c) {  // the reference's /[BDHVRYKMSWNX]/i
+  switch (c) {
+    case 'B': case 'D': case 'H': case 'V': case 'R': case 'Y': case 'K': case 'M': case 'S': case 'W': case 'N': case 'X':
+      return true;
+  }
+  return false;
+}
+
+// the reference's %mutChar (SearchResult.pm:2438-2484) as a rule: purine<->purine / pyrimidine<->pyrimidine 'i', other
+// A/C/G/T pairs 'v', one of the 16 nucleotide codes against '-' a gap; 0 = not in the table
+inline char difference_mark(int q, int s) {
+  auto base = [](int c) { return c == 'A' ? 0 : c == 'G' ? 1 : c == 'C' ? 2 : c == 'T' ? 3 : -1; };
+  const int bq = base(q), bs = base(s);
+  if (bq >= 0 && bs >= 0) return (bq >> 1) == (bs >> 1) ? 'i' : 'v';
+  auto code = [&](int c) { return base(c) >= 0 || ambiguity_code(c); };
+  if ((q == '-' && code(s)) || (s == '-' && code(q))) return '-';
+  return 0;
+}
+
+void name_field(std::string& out, const char* name) {  // up to 13 characters, padded, and the separating blank
+  const size_t n = std::min<size_t>(strlen(name), 13);
+  out.append(name, n);
+  out.append(13 - n + 1, ' ');
+}
+
+void number_field(std::string& out, long long v) {  // right-aligned in 10 columns (wider numbers are not cut)
+  const std::string t = std::to_string(v);
+  if (t.size() < 10) out.append(10 - t.size(), ' ');
+  out += t;
+}
+
+}  // namespace
 }  // namespace rmgpu
+
+extern "C" int64_t rmgpu_format_alignment(const char* query_name, const char* subject_name, const char* qaln, const char* saln,
+                                          int64_t qstart, int64_t qend, int64_t sstart, int64_t send, int strand,
+                                          const char* matrix_name, const char* pct_kimura, const char* cpg_sites,
+                                          const char* pct_raw_kimura, char* out, int64_t cap) {
+  using namespace rmgpu;
+  const size_t len = strlen(qaln);
+  if (strlen(saln) != len) return -1;
+  std::string r;
+  r.reserve(len * 5 + 512);
+  r += '\n';
+  long long qStart = qstart, qEnd = 0, sStart = strand ? send : sstart, sEnd = 0;
+  long long transitions = 0, transversions = 0, gapChars = 0, gaps = 0;
+  for (size_t off = 0; off < len; off += 50) {
+    const size_t n = std::min<size_t>(50, len - off);
+    const char *q = qaln + off, *s = saln + off;
+    const long long insertions = std::count(q, q + n, '-'), deletions = std::count(s, s + n, '-');
+    if (sEnd > 0) {  // every chunk but the first (the reference tests the previous subject end, :2680)
+      const long long qIncr = (long long)n > insertions, sIncr = (long long)n > deletions;
+      qStart = qEnd + qIncr;
+      sStart = strand ? sEnd - sIncr : sEnd + sIncr;
+    }
+    qEnd = (long long)n == insertions ? qStart : qStart + (long long)n - 1 - insertions;
+    r += "  ";
+    name_field(r, query_name);
+    number_field(r, qStart);
+    r += ' ';
+    r.append(q, n);
+    r += ' ';
+    r += std::to_string(qEnd);
+    r += '\n';
+    r.append(27, ' ');
+    for (size_t j = 0; j < n; j++) {
+      const int a = std::toupper((unsigned char)q[j]), b = std::toupper((unsigned char)s[j]);
+      char mark = ' ';
+      if (a != b) {
+        const char mc = difference_mark(a, b);
+        if (mc) {
+          mark = mc;
+          if (mc == 'i') transitions++;
+          if (mc == 'v') transversions++;
+          if (mc == '-') {
+            gapChars++;
+            // a gap "opens" where the previous QUERY column of the chunk is no gap; for the chunk's first column the
+            // reference's `$qChars[ ( $j - 1 ) | 0 ]` (:2723) is index -1, the chunk's LAST column
+            if (q[j ? j - 1 : n - 1] != '-') gaps++;
+          }
+        } else if (ambiguity_code(a) || ambiguity_code(b)) {
+          mark = '?';
+        }
+      }
+      r += mark;
+    }
+    r += '\n';
+    if (strand) {
+      r += "C ";
+      sEnd = sStart - (long long)n + 1 + deletions;
+    } else {
+      r += "  ";
+      sEnd = sStart + (long long)n - 1 - deletions;
+    }
+    name_field(r, subject_name);
+    number_field(r, sStart);
+    r += ' ';
+    r.append(s, n);
+    r += ' ';
+    r += std::to_string(sEnd);
+    r += "\n\n";
+  }
+  r += "Matrix = ";
+  r += matrix_name ? matrix_name : "Unknown";
+  r += '\n';
+  if (pct_kimura) {
+    r += "Kimura (with divCpGMod) = ";
+    r += pct_kimura;
+    r += '\n';
+  }
+  if (cpg_sites && pct_raw_kimura) {
+    r += "CpG sites = ";
+    r += cpg_sites;
+    r += ", Kimura (unadjusted) = ";
+    r += pct_raw_kimura;
+    r += '\n';
+  }
+  char buf[64];
+  r += "Transitions / transversions = ";
+  if (transversions) {
+    snprintf(buf, sizeof buf, "%0.2f", (double)transitions / (double)transversions);
+    r += buf;
+  } else {
+    r += "1.00";
+  }
+  r += " (" + std::to_string(transitions) + "/" + std::to_string(transversions) + ")\n";
+  const long long span = qend - qstart;
+  if (span > 0) {
+    snprintf(buf, sizeof buf, "%0.2f", (double)gaps / (double)span);
+    r += "Gap_init rate = ";
+    r += buf;
+    r += " (" + std::to_string(gaps) + " / " + std::to_string(span) + ")";
+  } else {
+    r += "Gap_init rate = 0.0 ( " + std::to_string(gaps) + " / 0 )";
+  }
+  if (gaps > 0) {
+    snprintf(buf, sizeof buf, "%0.2f", (double)gapChars / (double)gaps);
+    r += ", avg. gap size = ";
+    r += buf;
+    r += " (" + std::to_string(gapChars) + " / " + std::to_string(gaps) + ")\n\n";
+  } else {
+    r += ", avg. gap size = 0.0 (0 / 0)\n\n";
+  }
+  if (out && cap > 0) {
+    const size_t n = std::min<size_t>(r.size(), (size_t)cap - 1);
+    memcpy(out, r.data(), n);
+    out[n] = 0;
+  }
+  return (int64_t)r.size();
+}

@@ -59,7 +59,7 @@ EXPORTS = ["rmgpu_version", "rmgpu_abi_version", "rmgpu_last_error", "rmgpu_sear
            "rmgpu_server_ping", "rmgpu_server_quit", "rmgpu_kimura_divergence", "rmgpu_matrix_info",
            "rmgpu_adjusted_score", "rmgpu_masklevel_filter", "rmgpu_contained_filter",
            "rmgpu_session_library_h2d_bytes", "rmgpu_session_set_queries_fasta_multi", "rmgpu_device_count",
-           "rmgpu_session_mask_queries"]
+           "rmgpu_session_mask_queries", "rmgpu_format_alignment"]
 
 
 def lib():
@@ -144,6 +144,25 @@ def kimura_divergence(qaln, saln, strand_c=False):
     f.restype = None
     f(qaln.encode(), saln.encode(), 1 if strand_c else 0, text, C.byref(ti), C.byref(tv), C.byref(wcb), C.byref(cpg))
     return text.value.decode(), ti.value, tv.value, wcb.value, cpg.value
+
+
+def format_alignment(query_name, subject_name, qaln, saln, qstart, qend, sstart, send, strand_c=False, matrix_name=None,
+                     pct_kimura=None, cpg_sites=None, pct_raw_kimura=None):
+    """rmgpu_format_alignment(): the alignment block of a .cat entry (SearchResult.pm:2486-2834, mode AlignWithQuerySeq)
+    from the fields a SearchResult holds (rows with the query forward).  Host-only, needs no GPU."""
+    f = lib().rmgpu_format_alignment
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                  C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64]
+    f.restype = C.c_int64
+    opt = [None if v is None else str(v).encode() for v in (matrix_name, pct_kimura, cpg_sites, pct_raw_kimura)]
+    args = [query_name.encode(), subject_name.encode(), qaln.encode(), saln.encode(), qstart, qend, sstart, send,
+            1 if strand_c else 0] + opt
+    need = f(*args, None, 0)
+    if need < 0:
+        raise ValueError("alignment rows differ in length")
+    buf = C.create_string_buffer(need + 1)
+    f(*args, buf, need + 1)
+    return buf.value.decode()
 
 
 def matrix_info(path):

@@ -265,7 +265,7 @@ sub recordsToCollection {
                            id             => ( $rec->{'star'} ? "*" : undef ),
                            overlap        => undef
     );
-    my $result = SearchResult->new( %nameValuePairs );
+    my $result = GpuSearchResult->new( %nameValuePairs );
 
     if ( defined $rec->{'queryString'} ) {
       my $querySeq = $rec->{'queryString'};
@@ -300,6 +300,63 @@ sub recordsToCollection {
     }
   }
   return $resultColl;
+}
+
+##---------------------------------------------------------------------------##
+## GpuSearchResult: the SearchResult the engine hands out.  Same object, same
+## fields; only the query-oriented alignment text -- what the batch children
+## write into the .cat file, RepeatMasker:1489 -> SearchResultCollection::write
+## -> toStringFormatted( AlignWithQuerySeq ) -- comes from the library
+## (rmgpu_format_alignment) instead of the per-column Perl loop of
+## SearchResult.pm:2639-2834.  The annotation line is the inherited routine's.
+## It is rendered when asked for, from the fields the object holds at that
+## moment, so everything the driver changes in between (names, offsets of a
+## fragment, ids) shows.  Every other format, rows of unequal length and rows
+## with a character outside the nucleotide codes take the inherited routine.
+##---------------------------------------------------------------------------##
+package GpuSearchResult;
+use strict;
+use SearchResult;
+use vars qw(@ISA);
+@ISA = qw(SearchResult);
+
+sub _toCrossMatchFormat {
+  my $obj           = shift;
+  my $alignmentMode = shift;
+  my $displayParams = shift;
+
+  my $query   = $obj->getQueryString();
+  my $subject = $obj->getSubjString();
+  if (
+       defined $alignmentMode
+    && (    $alignmentMode == SearchResult::AlignWithQuerySeq
+         || $alignmentMode == SearchResult::N_AlignWithQuerySeq )
+    && defined $query
+    && defined $subject
+    && $query ne ""
+    && length( $query ) == length( $subject )
+    && $query !~ /[^ACGTBDHVRYKMSWNXacgtbdhvrykmswnx-]/
+    && $subject !~ /[^ACGTBDHVRYKMSWNXacgtbdhvrykmswnx-]/
+      )
+  {
+    # the annotation line alone, with the id order of the requested mode
+    my $header = $obj->SUPER::_toCrossMatchFormat(
+                          $alignmentMode == SearchResult::AlignWithQuerySeq
+                          ? SearchResult::NoAlign
+                          : SearchResult::N_NoAlign
+    );
+    my $block = RMGpu::format_alignment(
+                          $obj->getQueryName(),  $obj->getSubjName(),
+                          $query,                $subject,
+                          $obj->getQueryStart(), $obj->getQueryEnd(),
+                          $obj->getSubjStart(),  $obj->getSubjEnd(),
+                          ( $obj->getOrientation() eq "C" ? 1 : 0 ),
+                          $obj->getMatrixName(), $obj->getPctKimuraDiverge(),
+                          $obj->getCpGSites(),   $obj->getPctRawKimuraDiverge()
+    );
+    return $header . $block if ( defined $block );
+  }
+  return $obj->SUPER::_toCrossMatchFormat( $alignmentMode, $displayParams );
 }
 
 1;

@@ -37,6 +37,50 @@ server_quit(socket_path)
   OUTPUT:
     RETVAL
 
+SV *
+format_alignment(query_name, subject_name, qaln, saln, qstart, qend, sstart, send, strand, matrix_name, pct_kimura, cpg_sites, pct_raw_kimura)
+    const char *query_name
+    const char *subject_name
+    const char *qaln
+    const char *saln
+    IV qstart
+    IV qend
+    IV sstart
+    IV send
+    int strand
+    SV *matrix_name
+    SV *pct_kimura
+    SV *cpg_sites
+    SV *pct_raw_kimura
+  PREINIT:
+    const char *mn, *pk, *cs, *rk;
+    int64_t cap, need;
+    SV *out;
+  CODE:
+    /* undef stays undef (NULL): the reference prints those lines only for defined fields (SearchResult.pm:2786-2800) */
+    mn = SvOK(matrix_name) ? SvPV_nolen(matrix_name) : NULL;
+    pk = SvOK(pct_kimura) ? SvPV_nolen(pct_kimura) : NULL;
+    cs = SvOK(cpg_sites) ? SvPV_nolen(cpg_sites) : NULL;
+    rk = SvOK(pct_raw_kimura) ? SvPV_nolen(pct_raw_kimura) : NULL;
+    cap = (int64_t)strlen(qaln) * 6 + 1024 + (mn ? (int64_t)strlen(mn) : 0);
+    out = newSV((STRLEN)cap);
+    need = rmgpu_format_alignment(query_name, subject_name, qaln, saln, (int64_t)qstart, (int64_t)qend, (int64_t)sstart,
+                                  (int64_t)send, strand, mn, pk, cs, rk, SvPVX(out), cap);
+    if (need >= cap) { /* cannot happen with the bound above unless the optional texts are huge: size exactly */
+      SvGROW(out, (STRLEN)need + 1);
+      need = rmgpu_format_alignment(query_name, subject_name, qaln, saln, (int64_t)qstart, (int64_t)qend, (int64_t)sstart,
+                                    (int64_t)send, strand, mn, pk, cs, rk, SvPVX(out), need + 1);
+    }
+    if (need < 0) {
+      SvREFCNT_dec(out);
+      XSRETURN_UNDEF;
+    }
+    SvPOK_only(out);
+    SvCUR_set(out, (STRLEN)need);
+    RETVAL = out;
+  OUTPUT:
+    RETVAL
+
 void
 search(query, subject, matrix, gap_init, ins_gap_ext, del_gap_ext, minscore, masklevel, minmatch, bandwidth, raw, word_raw, alignments, device)
     const char *query

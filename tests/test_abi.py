@@ -20,7 +20,7 @@ def test_library_builds_and_exports_header_symbols():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/rmgpu.h but not exported"
     assert set(engine.EXPORTS) <= declared
-    assert L.rmgpu_abi_version() == 3
+    assert L.rmgpu_abi_version() == 4
     assert b"rmgpu version" in L.rmgpu_version()
 
 

@@ -50,3 +50,38 @@ def test_records_to_collection_equals_reference_parse(tmp_path, library_kimura):
                           util.ORACLE_BIN, m, q, s, str(tmp_path / "recs.json")], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.strip() == f"OK {len(hits)}"
+
+
+def test_alignment_text_from_the_library_equals_reference_perl(tmp_path):
+    """SURVEY 8f.1, the .cat blocks: GpuSearchResult::toStringFormatted (alignment block rendered by
+    rmgpu_format_alignment) == SearchResult::toStringFormatted (SearchResult.pm:2486-2834) byte for byte, on the 244
+    golden alignments, hand-made edge cases and 300 random rows; inherited formats, fallbacks, setters and clone()."""
+    subprocess.run(["make", "-C", PERL_DIR], check=True, capture_output=True)
+    cases = json.load(open(os.path.join(util.ROOT, "tests", "golden", "kimura.json")))["cases"]
+    # the fixture holds rows as rmgpu_hit does (strand C: query reverse-complemented); the object holds the query forward
+    comp = str.maketrans("ACGTYRMKHBVD", "TGCARYKMDVBH")
+    rows = []
+    for c in cases:
+        q, s = c["qaln"], c["saln"]
+        if c["strand"]:
+            q, s = q[::-1].translate(comp), s[::-1].translate(comp)
+        rows.append({"q": q, "s": s, "strand": c["strand"]})
+    (tmp_path / "rows.json").write_text(json.dumps(rows))
+    res = subprocess.run(["perl", f"-I{REF}", f"-I{PERL_DIR}", os.path.join(util.ROOT, "tests", "perl", "compare_alignment_text.pl"),
+                          str(tmp_path / "rows.json")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.startswith(f"OK {2 * (len(rows) + 13 + 300)} texts"), res.stdout
+
+
+def test_alignment_text_python_binding_matches_perl_binding(tmp_path):
+    """The ctypes mirror calls the same C entry point as the XS glue."""
+    from repeatmasker_b200 import engine
+    subprocess.run(["make", "-C", PERL_DIR], check=True, capture_output=True)
+    q, s = "ACGT" * 20 + "--AC" + "RYN" * 5, "ACTT" * 20 + "GGAC" + "RCN" * 5
+    py = engine.format_alignment("chr1", "AluY#SINE/Alu", q, s, 101, 101 + 96, 5, 5 + 98, True, "25p41g.matrix", "3.21")
+    pl = subprocess.run(["perl", f"-I{PERL_DIR}", "-MRMGpu", "-e",
+                         'print RMGpu::format_alignment("chr1", "AluY#SINE/Alu", $ARGV[0], $ARGV[1], 101, 197, 5, 103, 1, '
+                         '"25p41g.matrix", "3.21", undef, undef)', q, s], capture_output=True, text=True, check=True).stdout
+    assert py == pl and py.startswith("\n  chr1 ") and "C AluY#SINE/Alu" in py and "Matrix = 25p41g.matrix\n" in py
+    with pytest.raises(ValueError):
+        engine.format_alignment("q", "s", "ACGT", "ACG", 1, 4, 1, 3)
