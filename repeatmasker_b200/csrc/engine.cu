@@ -98,6 +98,7 @@ struct EventTimer {
 constexpr int kTraceAttempts = 2;  // band widths K3 tries per launch (W, 2W) before the host reschedules a candidate
 constexpr int kPackRunStripes = 4;  // library packing: subjects are laid end to end in runs of at most this many stripes
 constexpr int64_t kCheckpointBudget = 48ll << 30;  // K1 column checkpoints: at most this many bytes per pass
+constexpr int64_t kSegStateBudget = 2ll << 30;     // K1 column segments: registers of every ticket between two segments (5 KB each)
 
 static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -190,7 +191,10 @@ struct rmgpu_session {
     int orderGroup = 0;   // max position distance between a stripe and the stripe below it in the ticket order
     int orderForNQ = -1;  // batch size the order was built for
     DevBuf<unsigned long long> d_bnd, d_dbg;
-    DevBuf<int> d_finished, d_ticket, d_abort;
+    DevBuf<int> d_finished, d_ticket, d_abort, d_segDone;
+    DevBuf<uint16_t> d_level;
+    DevBuf<uint32_t> d_segState;
+    int maxLevel = 0;     // deepest stripe of a chain
     cudaStream_t stream = nullptr;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     int q0 = 0, nQ = 0, grid = 0, nslot = 0;
@@ -606,7 +610,9 @@ void rmgpu_session::build_order(ScoreSlot& sl, int nQ, int warps) {
   std::vector<std::vector<Chain>> grp(nGroupsT);
   for (size_t c = 0; c < chains.size(); c++) grp[c % nGroupsT].push_back(chains[c]);
   std::vector<int32_t> order, posOf(nStripes, -1);
+  std::vector<uint16_t> levelOf;
   sl.orderGroup = 0;
+  sl.maxLevel = 0;
   for (auto& gchains : grp) {
     int tot = 0, maxLen = 0;
     for (auto& c : gchains) {
@@ -619,6 +625,8 @@ void rmgpu_session::build_order(ScoreSlot& sl, int nQ, int warps) {
         if (level < c.len) {
           posOf[c.first + level] = (int32_t)order.size();
           order.push_back(c.first + level);
+          levelOf.push_back((uint16_t)std::min(level, 65535));
+          sl.maxLevel = std::max(sl.maxLevel, level);
         }
   }
   std::vector<int32_t> prodPos(nStripes, -1), consPos(nStripes, -1);
@@ -630,6 +638,7 @@ void rmgpu_session::build_order(ScoreSlot& sl, int nQ, int warps) {
   sl.d_order.upload(order, sl.stream);
   sl.d_prodPos.upload(prodPos, sl.stream);
   sl.d_consPos.upload(consPos, sl.stream);
+  sl.d_level.upload(levelOf, sl.stream);
   sl.orderForNQ = nQ;
 }
 
@@ -700,8 +709,24 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
   // ring slots: a slot is rewritten nslot tickets later; its reader is at most orderGroup * nQ tickets after its writer
   // ... and a boundary's 4-bit tag (generation = ticket / nslot, 15 values) must be unique within a launch: a slot keeps
   // the boundary of its last WRITER, which may be many generations old when the tickets in between had no stripe below
+  // column segments (kernels.cuh, swg_score_kernel): tickets dealt in quarters when there are several waves of them, so
+  // that the last wave does not run half empty; RMGPU_K1_SEGMENTS=1 switches them off, =n sets another count
+  static const char* segEnv = getenv("RMGPU_K1_SEGMENTS");
+  int nSeg = segEnv ? std::max(1, atoi(segEnv)) : 4;
+  const int segMinBlocks = nSeg * (sl.maxLevel + 8);  // every segment of a split record keeps >= 8 blocks at any chain depth
+  if ((!segEnv && nTickets <= warps) || nTickets * nSeg >= (1ll << 31) || sl.maxLevel >= 65535 ||
+      (((int64_t)maxQ + 31) >> 5) + 1 < segMinBlocks ||
+      nTickets * (int64_t)(kSegStateWords * 32 * sizeof(uint32_t)) > kSegStateBudget)
+    nSeg = 1;
+  // windows of the claim order: as equal as possible, each at least two rounds of the resident warps
+  const int64_t nWindows = std::max<int64_t>(1, nTickets / (2 * (int64_t)warps));
+  const int segWindow = (int)((nTickets + nWindows - 1) / nWindows);
+  // ring slots: with segments the tickets of a window run interleaved, so the old reader of a slot must lie a whole
+  // window back for it to have been claimed first (2 windows + the writer-reader distance)
+  const int64_t segSlots = nSeg > 1 ? 2 * (int64_t)segWindow + (int64_t)sl.orderGroup * nQ + 2 : 0;
   const int nslot = (int)std::min<int64_t>(
-      nTickets, std::max<int64_t>(std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)sl.orderGroup * nQ + 2), nTickets / 14 + 1));
+      nTickets, std::max<int64_t>(std::max<int64_t>(std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)sl.orderGroup * nQ + 2), segSlots),
+                                  nTickets / 14 + 1));
   if ((nTickets + nslot - 1) / nslot > 15) throw Error("K1 boundary ring: more than 15 tag generations in one launch");
   const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
   ScoreArgs a;
@@ -732,6 +757,17 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
   a.minscore = std::max(1, std::min(p.minscore, ovfThresh) - scoreSlack);
   a.ovfThresh = ovfThresh;
   a.abort_flag = sl.d_abort.ensure(1);
+  a.nSeg = nSeg;
+  a.segWindow = segWindow;
+  a.segMinBlocks = segMinBlocks;
+  a.level = sl.d_level.p;
+  a.segState = nullptr;
+  a.segDone = nullptr;
+  if (nSeg > 1) {
+    a.segState = sl.d_segState.ensure((size_t)nTickets * kSegStateWords * 32);
+    a.segDone = sl.d_segDone.ensure((size_t)nTickets);
+    CUDA_CHECK(cudaMemsetAsync(a.segDone, 0, (size_t)nTickets * sizeof(int), sl.stream));
+  }
   a.ck = ckEnabled ? d_ck.p + (size_t)q0 * kHotBlocks * ((size_t)nGroups * R) : nullptr;
   a.ckRows = (int64_t)nGroups * R;
   static const bool dbgOn = getenv("RMGPU_DEBUG_K1") != nullptr;
@@ -741,7 +777,7 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
     a.dbg = sl.d_dbg.ensure(8);
     CUDA_CHECK(cudaMemsetAsync(a.dbg, 0, 64, sl.stream));
   }
-  const int grid = (int)std::min<int64_t>(resident, (nTickets + kScoreWarps - 1) / kScoreWarps);  // one persistent wave
+  const int grid = (int)std::min<int64_t>(resident, (nTickets * nSeg + kScoreWarps - 1) / kScoreWarps);  // one persistent wave
   sl.q0 = q0;
   sl.nQ = nQ;
   sl.grid = grid;

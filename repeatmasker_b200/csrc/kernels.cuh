@@ -205,7 +205,16 @@ struct ScoreArgs {
   int64_t ckRows;             // nGroups * R
   unsigned long long* dbg;    // optional [8]: cycles waiting on the producer, cycles waiting on a slot, tasks, task cycles,
                               // sum and max over warps of (exit time - first warp's start) in ns, -, base time
+  // column segments (see swg_score_kernel): a ticket is claimed as nSeg sub-tickets, one after the other
+  int nSeg;                   // 1 = whole tickets
+  int segWindow;              // tickets per window of the claim order (segment 0 of a window's tickets, then segment 1, ...)
+  int segMinBlocks;           // a query record with fewer 32-column blocks than this runs as one segment
+  const uint16_t* level;      // [nStripes] ticket position -> depth of the stripe in its chain (0 = no stripe above)
+  uint32_t* segState;         // [nTickets][kSegStateWords][32 lanes] a ticket's registers between two of its segments
+  int* segDone;               // [nTickets] segments of the ticket that are finished
 };
+
+constexpr int kSegStateWords = 40;  // H[16], E[16], best, bestBlk, outH, outF, diag, curSel, nextSel (+1 spare)
 
 // Boundary elements are single 64-bit words {H | F' << 32}; every 16-bit half is < 32768, so bit 15 of each half is
 // free and carries a 4-bit generation tag: a consumer simply re-reads an element until the tag is the one its
@@ -234,6 +243,18 @@ constexpr int kK1Unroll = 8;  // columns per trip of K1's inner loop (4: +3 % ti
 // a sample sees every H of the previous 8 columns of its row less at most 7*|ins_ext|; the host lowers its thresholds
 // by that slack (ScoreArgs::minscore already includes it), which keeps the filter free of false negatives and saves
 // 6 of the 104 integer-pipe instructions per lane-column.
+// Column segments (ScoreArgs::nSeg > 1).  A ticket is 22 ms of work on the bench and a warp gets 8.7 of them: the last of
+// the nine waves runs at 74 % occupancy.  With segments a ticket is claimed as nSeg sub-tickets: the warp that finishes
+// segment s writes the lanes' registers (kSegStateWords words per lane, each lane in the middle of its own column: the
+// wavefront is frozen as it stands) to segState and publishes segDone = s + 1; whoever claims segment s + 1 waits for that,
+// reads the registers back and continues the SAME loop at the next 32-column block -- no variant of the hot loop, the
+// segment code is all outside it.  Claim order: windows of segWindow tickets, inside a window segment 0 of every ticket,
+// then segment 1 of every ticket, ...; a window is at least twice the resident warps, so a segment's predecessor finished
+// long before it is claimed, and the work is dealt in quarter tickets.  Deadlock freedom: a stripe of depth l in its chain
+// cuts its segments l blocks EARLIER than a stripe of depth 0 (segment s = blocks [s*len - l, (s+1)*len - l)): the
+// consumer of block b needs its producer's block b + 1, so segment s of a consumer needs exactly the producer's
+// segments <= s, and everything a sub-ticket waits for (own segment s-1, producer's segment s, the old reader of its ring
+// slot) was claimed before it: the oldest unfinished sub-ticket can always run.
 // GI / IE / DF != 0: gap_init, ins_gap_ext and max(del_gap_ext, gap_init) are compile-time constants, so the four
 // VIADDMNMX of a packed cell carry them as 32-bit immediates (two register reads instead of three, three registers
 // free); instantiated for the gap penalties of RepeatMasker's crossmatch recipes (RepeatMasker:2146-2366), any other
@@ -248,12 +269,22 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
   __shared__ uint2 s_out[kScoreWarps][32];   // last row's (H, F') of the last 32 columns lane 31 finished
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nTickets = a.nQueries * a.nStripes;
+  const int nSeg = a.nSeg;
+  const long long nClaims = (long long)nTickets * nSeg;
   if (a.dbg && lane == 0) atomicCAS(&a.dbg[7], 0ull, globaltimer_ns());  // time base: the first warp to get here
   for (;;) {
-    int t = 0;
+    int t = 0, seg = 0;
     if (lane == 0) t = atomicAdd(a.ticket, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= nTickets) break;
+    if (t >= nClaims) break;
+    if (nSeg > 1) {
+      // claim number -> (ticket, segment): windows of segWindow tickets, segment-major inside a window
+      const int perWin = a.segWindow * nSeg;
+      const int w = t / perWin, r = t - w * perWin;
+      const int nW = min(a.segWindow, nTickets - w * a.segWindow);
+      seg = r / nW;
+      t = w * a.segWindow + (r - seg * nW);
+    }
     const int pos = t / a.nQueries, q = t - pos * a.nQueries;  // query fastest: a level of the order spans all queries
     const int k = a.order[pos];
     const int g = k * 32 + lane;
@@ -273,11 +304,23 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     }
     const int qBlocks = (Q + 31) >> 5;
     const int nBlocks = qBlocks + 1;  // lane 31 reaches column qBlocks*32 >= Q
+    // this sub-ticket's blocks [bs, be)
+    int bs = 0, be = nBlocks;
+    if (nSeg > 1) {
+      if (nBlocks < a.segMinBlocks) {
+        if (seg > 0) continue;  // a short record: segment 0 is the whole ticket
+      } else {
+        const int segLen = (nBlocks + nSeg - 1) / nSeg, lvl = a.level[pos];
+        if (seg > 0) bs = seg * segLen - lvl;
+        if (seg < nSeg - 1) be = (seg + 1) * segLen - lvl;
+      }
+    }
+    const bool lastSeg = be == nBlocks;
     const int tProd = hasPrev ? a.prodPos[pos] * a.nQueries + q : 0;  // ticket of the stripe above (always older)
     const unsigned long long* bndIn = a.bnd + (int64_t)(tProd % a.nslot) * a.bndStride;
     unsigned long long* bndOut = a.bnd + (int64_t)(t % a.nslot) * a.bndStride;
     const unsigned long long tagIn = tag_bits(tProd, a.nslot), tagOut = tag_bits(t, a.nslot);
-    if (hasNext) {
+    if (hasNext && bs == 0) {
       // The slot still holds the boundary of the last ticket that WROTE it (t - nslot, t - 2 nslot, ... skipping
       // tickets whose stripe has no stripe below): its reader must be done before this ticket overwrites it.
       for (int tOld = t - a.nslot; tOld >= 0; tOld -= a.nslot) {
@@ -301,9 +344,33 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     // 0/1 factors, made opaque so that they stay multiplications
     uint32_t keepSel = lane != 0, feedSel = lane == 0, keepHF = lane != 0 && !startFlag, feedHF = lane == 0 && !startFlag;
     asm volatile("" : "+r"(keepSel), "+r"(feedSel), "+r"(keepHF), "+r"(feedHF));
+    if (nSeg > 1) {
+      if (bs > 0) {
+        const uint32_t* segSt = a.segState + (int64_t)t * (kSegStateWords * 32) + lane;
+        // the registers the previous segment left behind (written by another SM: read past L1)
+        if (lane == 0) wait_ge(&a.segDone[t], seg, a.abort_flag);
+        __syncwarp();
+        __threadfence();
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          H[r] = __ldcg(segSt + r * 32);
+          E[r] = __ldcg(segSt + (R + r) * 32);
+        }
+        best = __ldcg(segSt + (2 * R + 0) * 32);
+        bestBlk = __ldcg(segSt + (2 * R + 1) * 32);
+        outH = __ldcg(segSt + (2 * R + 2) * 32);
+        outF = __ldcg(segSt + (2 * R + 3) * 32);
+        diag = __ldcg(segSt + (2 * R + 4) * 32);
+        curSel = __ldcg(segSt + (2 * R + 5) * 32);
+        nextSel = __ldcg(segSt + (2 * R + 6) * 32);
+        // lane 31 had finished column bs*32 when the previous segment stopped: the pending entry of the output line
+        if (lane == 31) s_out[wib][0] = make_uint2(outH, outF);
+        __syncwarp();
+      }
+    }
     unsigned long long nextRaw = 0;
-    if (hasPrev) nextRaw = ld_relaxed_u64(&bndIn[lane]);
-    for (int b = 0; b < nBlocks; b++) {
+    if (hasPrev && bs < qBlocks) nextRaw = ld_relaxed_u64(&bndIn[bs * 32 + lane]);
+    for (int b = bs; b < be; b++) {
       uint32_t selv = sel[b * 32 + lane];
       unsigned long long raw = 0;
       if (hasPrev && b < qBlocks) {
@@ -314,7 +381,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
           if (!__all_sync(0xffffffffu, (raw & kTagMask) == tagIn)) {
             const long long w0 = clock64();
             // caught up with the producer: sleep until it is kLag blocks ahead (hysteresis), then take block b
-            const int far = min(b + kLag, qBlocks - 1);
+            const int far = min(min(b + kLag, qBlocks - 1), be - 1);  // never beyond what this segment itself will need
             unsigned ns = 128;
             bool dead = false;
             for (;;) {
@@ -430,6 +497,33 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
         best = __vmaxs2(best, bestBlk);
         bestBlk = 0;
       }
+    }
+    if (!lastSeg) {
+      // hand the frozen wavefront to the next segment of this ticket
+      uint32_t* segSt = a.segState + (int64_t)t * (kSegStateWords * 32) + lane;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        __stcg(segSt + r * 32, H[r]);
+        __stcg(segSt + (R + r) * 32, E[r]);
+      }
+      __stcg(segSt + (2 * R + 0) * 32, best);
+      __stcg(segSt + (2 * R + 1) * 32, bestBlk);
+      __stcg(segSt + (2 * R + 2) * 32, outH);
+      __stcg(segSt + (2 * R + 3) * 32, outF);
+      __stcg(segSt + (2 * R + 4) * 32, diag);
+      __stcg(segSt + (2 * R + 5) * 32, curSel);
+      __stcg(segSt + (2 * R + 6) * 32, nextSel);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        st_release(&a.segDone[t], seg + 1);
+        if (a.dbg) {
+          atomicAdd(&a.dbg[0], (unsigned long long)waitCyc);
+          atomicAdd(&a.dbg[2], 1ull);
+          atomicAdd(&a.dbg[3], (unsigned long long)(clock64() - task0));
+        }
+      }
+      continue;
     }
     // per (query, subject, strand) best
     if (sj >= 0) {
