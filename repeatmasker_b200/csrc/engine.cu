@@ -98,6 +98,7 @@ struct EventTimer {
 constexpr int kTraceAttempts = 2;  // band widths K3 tries per launch (W, 2W) before the host reschedules a candidate
 constexpr int kPackRunStripes = 4;  // library packing: subjects are laid end to end in runs of at most this many stripes
 constexpr int64_t kCheckpointBudget = 48ll << 30;  // K1 column checkpoints: at most this many bytes per pass
+constexpr int kSegWindowRounds = 4;                 // K1 column segments: window of the claim order, in rounds of the resident warps
 constexpr int64_t kSegStateBudget = 2ll << 30;     // K1 column segments: registers of every ticket between two segments (5 KB each)
 
 static double now_ms() {
@@ -190,7 +191,8 @@ struct rmgpu_session {
     DevBuf<int32_t> d_order, d_prodPos, d_consPos;
     int orderGroup = 0;   // max position distance between a stripe and the stripe below it in the ticket order
     int orderForNQ = -1;  // batch size the order was built for
-    DevBuf<unsigned long long> d_bnd, d_dbg;
+    DevBuf<unsigned long long> d_bnd, d_dbg, d_trace;
+    size_t traceWords = 0;
     DevBuf<int> d_finished, d_ticket, d_abort, d_segDone;
     DevBuf<uint16_t> d_level;
     DevBuf<uint32_t> d_segState;
@@ -718,8 +720,12 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
       (((int64_t)maxQ + 31) >> 5) + 1 < segMinBlocks ||
       nTickets * (int64_t)(kSegStateWords * 32 * sizeof(uint32_t)) > kSegStateBudget)
     nSeg = 1;
-  // windows of the claim order: as equal as possible, each at least two rounds of the resident warps
-  const int64_t nWindows = std::max<int64_t>(1, nTickets / (2 * (int64_t)warps));
+  // windows of the claim order: as equal as possible, each at least kSegWindowRounds rounds of the resident warps.  The
+  // warps of a sub-partition do not progress evenly (a quarter ticket takes 3 ms on one warp and 15-25 ms on a starved
+  // neighbour, profiles/r2_k1_segments.txt): a segment's predecessor must have that long before the segment is claimed
+  static const char* winEnv = getenv("RMGPU_K1_SEGWIN");
+  const int64_t winRounds = winEnv ? std::max(1, atoi(winEnv)) : kSegWindowRounds;
+  const int64_t nWindows = std::max<int64_t>(1, nTickets / (winRounds * (int64_t)warps));
   const int segWindow = (int)((nTickets + nWindows - 1) / nWindows);
   // ring slots: with segments the tickets of a window run interleaved, so the old reader of a slot must lie a whole
   // window back for it to have been claimed first (2 windows + the writer-reader distance)
@@ -768,6 +774,14 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
     a.segDone = sl.d_segDone.ensure((size_t)nTickets);
     CUDA_CHECK(cudaMemsetAsync(a.segDone, 0, (size_t)nTickets * sizeof(int), sl.stream));
   }
+  static const char* traceEnv = getenv("RMGPU_K1_TRACE");
+  a.trace = nullptr;
+  sl.traceWords = 0;
+  if (traceEnv) {
+    sl.traceWords = (size_t)nTickets * nSeg * 4;
+    a.trace = sl.d_trace.ensure(sl.traceWords);
+    CUDA_CHECK(cudaMemsetAsync(a.trace, 0, sl.traceWords * 8, sl.stream));
+  }
   a.ck = ckEnabled ? d_ck.p + (size_t)q0 * kHotBlocks * ((size_t)nGroups * R) : nullptr;
   a.ckRows = (int64_t)nGroups * R;
   static const bool dbgOn = getenv("RMGPU_DEBUG_K1") != nullptr;
@@ -809,6 +823,14 @@ void rmgpu_session::collect_score(ScoreSlot& sl, std::vector<int32_t>& pairbest,
   CUDA_CHECK(cudaMemsetAsync(sl.d_bnd.p, 0, sl.usedBytes, sl.stream));
   sl.cleanPtr = sl.d_bnd.p;
   sl.cleanBytes = sl.usedBytes;
+  if (sl.traceWords) {  // RMGPU_K1_TRACE=<file>: per sub-ticket (ticket * 16 + segment, claim, start, end in ns), last launch wins
+    std::vector<unsigned long long> tr(sl.traceWords);
+    CUDA_CHECK(cudaMemcpy(tr.data(), sl.d_trace.p, sl.traceWords * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(getenv("RMGPU_K1_TRACE"), "wb")) {
+      fwrite(tr.data(), 8, tr.size(), f);
+      fclose(f);
+    }
+  }
   if (sl.dbg) {
     unsigned long long d[8];
     float ms = 0;
@@ -817,8 +839,8 @@ void rmgpu_session::collect_score(ScoreSlot& sl, std::vector<int32_t>& pairbest,
     int64_t rows = 0;
     for (auto& sq : lib.seqs) rows += (int64_t)sq.size();
     const int warps = sl.grid * kScoreWarps;
-    fprintf(stderr, "[K1 dbg] records %d..%d tasks %llu  producer-wait %.1f%% of task cycles  slot-wait %.2e cyc  mean task %.0f cyc  grid %d nslot %d\n", sl.q0,
-            sl.q0 + sl.nQ - 1, d[2], 100.0 * (double)d[0] / (double)std::max(d[3], 1ull), (double)d[1], (double)d[3] / (double)std::max(d[2], 1ull), sl.grid, sl.nslot);
+    fprintf(stderr, "[K1 dbg] records %d..%d tasks %llu  producer-wait %.1f%% of task cycles  slot-wait %.2e cyc  segment-wait %.2e cyc  mean task %.0f cyc  grid %d nslot %d\n", sl.q0,
+            sl.q0 + sl.nQ - 1, d[2], 100.0 * (double)d[0] / (double)std::max(d[3], 1ull), (double)d[1], (double)d[6], (double)d[3] / (double)std::max(d[2], 1ull), sl.grid, sl.nslot);
     fprintf(stderr, "[K1 dbg] stripes %d  padded rows %.2f%%  warp busy until exit: mean %.1f%% of the last warp's (%.2f ms)  launch %.2f ms\n", nStripes,
             100.0 * ((double)nStripes * 32 * R - (double)rows) / (double)std::max<int64_t>(rows, 1),
             100.0 * (double)d[4] / ((double)warps * (double)std::max(d[5], 1ull)), (double)d[5] * 1e-6, ms);

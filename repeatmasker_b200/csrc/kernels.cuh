@@ -204,7 +204,7 @@ struct ScoreArgs {
   uint2* ck;                  // optional column checkpoints [(q*kHotBlocks + cb) * ckRows + g*R + r] = (H, E') before column cb*CB
   int64_t ckRows;             // nGroups * R
   unsigned long long* dbg;    // optional [8]: cycles waiting on the producer, cycles waiting on a slot, tasks, task cycles,
-                              // sum and max over warps of (exit time - first warp's start) in ns, -, base time
+                              // sum and max over warps of (exit time - first warp's start) in ns, cycles waiting on the previous segment, base time
   // column segments (see swg_score_kernel): a ticket is claimed as nSeg sub-tickets, one after the other
   int nSeg;                   // 1 = whole tickets
   int segWindow;              // tickets per window of the claim order (segment 0 of a window's tickets, then segment 1, ...)
@@ -212,6 +212,8 @@ struct ScoreArgs {
   const uint16_t* level;      // [nStripes] ticket position -> depth of the stripe in its chain (0 = no stripe above)
   uint32_t* segState;         // [nTickets][kSegStateWords][32 lanes] a ticket's registers between two of its segments
   int* segDone;               // [nTickets] segments of the ticket that are finished
+  unsigned long long* trace;  // optional [claims][4]: ticket * 16 + segment, claim time, start time (after the wait for the
+                              // previous segment), end time (globaltimer ns): RMGPU_K1_TRACE=<file>
 };
 
 constexpr int kSegStateWords = 40;  // H[16], E[16], best, bestBlk, outH, outF, diag, curSel, nextSel (+1 spare)
@@ -277,6 +279,8 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     if (lane == 0) t = atomicAdd(a.ticket, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= nClaims) break;
+    const int claim = t;
+    if (a.trace && lane == 0) a.trace[(int64_t)claim * 4 + 1] = globaltimer_ns();
     if (nSeg > 1) {
       // claim number -> (ticket, segment): windows of segWindow tickets, segment-major inside a window
       const int perWin = a.segWindow * nSeg;
@@ -334,6 +338,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
         break;
       }
     }
+    if (a.trace && lane == 0) a.trace[(int64_t)claim * 4 + 0] = (unsigned long long)t * 16 + seg;
     const long long task0 = clock64();
     long long waitCyc = 0;
     const int hotShift = a.hotShift[q];
@@ -348,8 +353,10 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
       if (bs > 0) {
         const uint32_t* segSt = a.segState + (int64_t)t * (kSegStateWords * 32) + lane;
         // the registers the previous segment left behind (written by another SM: read past L1)
+        const long long w0 = clock64();
         if (lane == 0) wait_ge(&a.segDone[t], seg, a.abort_flag);
         __syncwarp();
+        if (a.dbg && lane == 0) atomicAdd(&a.dbg[6], (unsigned long long)(clock64() - w0));
         __threadfence();
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -368,6 +375,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
         __syncwarp();
       }
     }
+    if (a.trace && lane == 0) a.trace[(int64_t)claim * 4 + 2] = globaltimer_ns();
     unsigned long long nextRaw = 0;
     if (hasPrev && bs < qBlocks) nextRaw = ld_relaxed_u64(&bndIn[bs * 32 + lane]);
     for (int b = bs; b < be; b++) {
@@ -517,6 +525,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
       __syncwarp();
       if (lane == 0) {
         st_release(&a.segDone[t], seg + 1);
+        if (a.trace) a.trace[(int64_t)claim * 4 + 3] = globaltimer_ns();
         if (a.dbg) {
           atomicAdd(&a.dbg[0], (unsigned long long)waitCyc);
           atomicAdd(&a.dbg[2], 1ull);
@@ -538,6 +547,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     __syncwarp();
     if (lane == 0) {
       st_release(&a.finished[t], 1);
+      if (a.trace) a.trace[(int64_t)claim * 4 + 3] = globaltimer_ns();
       if (a.dbg) {
         atomicAdd(&a.dbg[0], (unsigned long long)waitCyc);
         atomicAdd(&a.dbg[2], 1ull);
