@@ -99,6 +99,7 @@ constexpr int kTraceAttempts = 2;  // band widths K3 tries per launch (W, 2W) be
 constexpr int kPackRunStripes = 4;  // library packing: subjects are laid end to end in runs of at most this many stripes
 constexpr int64_t kCheckpointBudget = 48ll << 30;  // K1 column checkpoints: at most this many bytes per pass
 constexpr int kSegWindowRounds = 4;                 // K1 column segments: window of the claim order, in rounds of the resident warps
+constexpr int64_t kSegRingExtra = 4ll << 30;       // K1 column segments: extra boundary-ring bytes they may cost
 constexpr int64_t kSegStateBudget = 2ll << 30;     // K1 column segments: registers of every ticket between two segments (5 KB each)
 
 static double now_ms() {
@@ -729,12 +730,17 @@ void rmgpu_session::launch_score(const rmgpu_params& p, ScoreSlot& sl, int q0, i
   const int segWindow = (int)((nTickets + nWindows - 1) / nWindows);
   // ring slots: with segments the tickets of a window run interleaved, so the old reader of a slot must lie a whole
   // window back for it to have been claimed first (2 windows + the writer-reader distance)
-  const int64_t segSlots = nSeg > 1 ? 2 * (int64_t)segWindow + (int64_t)sl.orderGroup * nQ + 2 : 0;
-  const int nslot = (int)std::min<int64_t>(
-      nTickets, std::max<int64_t>(std::max<int64_t>(std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)sl.orderGroup * nQ + 2), segSlots),
-                                  nTickets / 14 + 1));
-  if ((nTickets + nslot - 1) / nslot > 15) throw Error("K1 boundary ring: more than 15 tag generations in one launch");
   const int64_t bndStride = (((int64_t)maxQ + 31) >> 5) * 32 + 32;
+  const int64_t wholeSlots = std::min<int64_t>(
+      nTickets, std::max<int64_t>(std::max<int64_t>(2 * (int64_t)warps + 2, 2 * (int64_t)sl.orderGroup * nQ + 2), nTickets / 14 + 1));
+  int64_t segSlots = nSeg > 1 ? std::min<int64_t>(nTickets, 2 * (int64_t)segWindow + (int64_t)sl.orderGroup * nQ + 2) : 0;
+  // ... unless that ring would be much larger than the one the pass was planned with (query_capacity): then whole tickets
+  if (segSlots > wholeSlots && (segSlots - wholeSlots) * bndStride * 8 > kSegRingExtra) {
+    nSeg = 1;
+    segSlots = 0;
+  }
+  const int nslot = (int)std::max<int64_t>(wholeSlots, segSlots);
+  if ((nTickets + nslot - 1) / nslot > 15) throw Error("K1 boundary ring: more than 15 tag generations in one launch");
   ScoreArgs a;
   a.prof = d_prof.p;
   a.gflags = d_gflags.p;
