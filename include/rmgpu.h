@@ -171,6 +171,15 @@ int rmgpu_contained_filter(int device, int32_t n, const int32_t *name_id, const 
  * Returns 16-bit-lane cell updates per second (GCUPS*1e9) in *cups and raw VIADDMNMX.S16x2 warp-instructions/s. */
 int rmgpu_measure_dpx_peak(int device, double *cups, double *dpx_instr_per_s);
 
+/* Host-only test hook for the score pass's column segments: claim number `claim` of a launch with n_tickets
+ * tickets cut into n_seg segments and claimed in windows of seg_window tickets -> the ticket and segment it stands for and
+ * the 32-column blocks [*bs, *be) of that segment for a record of n_blocks blocks whose stripe lies at depth `level` of its
+ * chain (records with fewer than seg_min_blocks blocks are not cut).  Computed by the functions the kernel itself calls.
+ * Returns 1 (the sub-ticket has work), 0 (empty: a short record's segment > 0) or -1 (bad arguments).
+ * tests/test_k1_schedule.py checks on the CPU that every sub-ticket only depends on sub-tickets claimed before it. */
+int rmgpu_debug_k1_schedule(int32_t n_tickets, int32_t n_seg, int32_t seg_window, int32_t claim, int32_t n_blocks,
+                            int32_t seg_min_blocks, int32_t level, int32_t *ticket, int32_t *seg, int32_t *bs, int32_t *be);
+
 /* Host-only helper behind rmgpu_hit::pct_kimura, exported so that it can be checked against the reference's Perl
  * (SearchResult.pm:1607-1683) without a GPU: rows in the orientation of rmgpu_hit::qaln/saln, strand as in rmgpu_hit.
  * Writes the "%4.2f" text; the optional outputs are transitions (fractional with the CpG rule), transversions,

@@ -2139,6 +2139,21 @@ void rmgpu_kimura_divergence(const char* qaln, const char* saln, int strand, cha
 }
 const char* rmgpu_last_error(void) { return g_last_error.c_str(); }
 
+// Host-only test hook: the schedule of K1's column segments, computed by the very functions the kernel calls
+// (kernels.cuh: seg_claim_decode, seg_block_range).
+int rmgpu_debug_k1_schedule(int32_t n_tickets, int32_t n_seg, int32_t seg_window, int32_t claim, int32_t n_blocks,
+                            int32_t seg_min_blocks, int32_t level, int32_t* ticket, int32_t* seg, int32_t* bs, int32_t* be) {
+  if (n_tickets <= 0 || n_seg <= 0 || seg_window <= 0 || claim < 0 || (int64_t)claim >= (int64_t)n_tickets * n_seg) return -1;
+  int t = claim, sg = 0, b0 = 0, b1 = n_blocks;
+  if (n_seg > 1) seg_claim_decode(claim, n_tickets, n_seg, seg_window, t, sg);
+  const int work = n_seg > 1 ? (seg_block_range(n_blocks, n_seg, sg, seg_min_blocks, level, b0, b1) ? 1 : 0) : 1;
+  *ticket = t;
+  *seg = sg;
+  *bs = b0;
+  *be = b1;
+  return work;
+}
+
 rmgpu_session* rmgpu_session_open(int device) {
   rmgpu_session* s = nullptr;
   int rc = guarded([&] {

@@ -218,6 +218,29 @@ struct ScoreArgs {
 
 constexpr int kSegStateWords = 40;  // H[16], E[16], best, bestBlk, outH, outF, diag, curSel, nextSel (+1 spare)
 
+// The schedule of the column segments, shared by the kernel and by the host-side test hook (rmgpu_debug_k1_schedule).
+// Claim number -> (ticket, segment): windows of segWindow tickets, segment-major inside a window.
+__host__ __device__ __forceinline__ void seg_claim_decode(int claim, int nTickets, int nSeg, int segWindow, int& t, int& seg) {
+  const int perWin = segWindow * nSeg;
+  const int w = claim / perWin, r = claim - w * perWin;
+  const int left = nTickets - w * segWindow;
+  const int nW = left < segWindow ? left : segWindow;
+  seg = r / nW;
+  t = w * segWindow + (r - seg * nW);
+}
+// 32-column blocks [bs, be) of segment seg of a ticket whose stripe lies at depth lvl of its chain: segment s covers
+// [s*len - lvl, (s+1)*len - lvl), the first one from 0 and the last one to nBlocks.  A record with fewer than segMinBlocks
+// blocks is not cut: its segment 0 is the whole ticket and the others are empty (returns false).
+__host__ __device__ __forceinline__ bool seg_block_range(int nBlocks, int nSeg, int seg, int segMinBlocks, int lvl, int& bs, int& be) {
+  bs = 0;
+  be = nBlocks;
+  if (nBlocks < segMinBlocks) return seg == 0;
+  const int segLen = (nBlocks + nSeg - 1) / nSeg;
+  if (seg > 0) bs = seg * segLen - lvl;
+  if (seg < nSeg - 1) be = (seg + 1) * segLen - lvl;
+  return true;
+}
+
 // Boundary elements are single 64-bit words {H | F' << 32}; every 16-bit half is < 32768, so bit 15 of each half is
 // free and carries a 4-bit generation tag: a consumer simply re-reads an element until the tag is the one its
 // producer writes (64-bit scalar accesses are single-copy atomic), so no fence, flag or progress counter is needed.
@@ -281,14 +304,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     if (t >= nClaims) break;
     const int claim = t;
     if (a.trace && lane == 0) a.trace[(int64_t)claim * 4 + 1] = globaltimer_ns();
-    if (nSeg > 1) {
-      // claim number -> (ticket, segment): windows of segWindow tickets, segment-major inside a window
-      const int perWin = a.segWindow * nSeg;
-      const int w = t / perWin, r = t - w * perWin;
-      const int nW = min(a.segWindow, nTickets - w * a.segWindow);
-      seg = r / nW;
-      t = w * a.segWindow + (r - seg * nW);
-    }
+    if (nSeg > 1) seg_claim_decode(claim, nTickets, nSeg, a.segWindow, t, seg);
     const int pos = t / a.nQueries, q = t - pos * a.nQueries;  // query fastest: a level of the order spans all queries
     const int k = a.order[pos];
     const int g = k * 32 + lane;
@@ -310,15 +326,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 2) swg_score_kernel(ScoreArg
     const int nBlocks = qBlocks + 1;  // lane 31 reaches column qBlocks*32 >= Q
     // this sub-ticket's blocks [bs, be)
     int bs = 0, be = nBlocks;
-    if (nSeg > 1) {
-      if (nBlocks < a.segMinBlocks) {
-        if (seg > 0) continue;  // a short record: segment 0 is the whole ticket
-      } else {
-        const int segLen = (nBlocks + nSeg - 1) / nSeg, lvl = a.level[pos];
-        if (seg > 0) bs = seg * segLen - lvl;
-        if (seg < nSeg - 1) be = (seg + 1) * segLen - lvl;
-      }
-    }
+    if (nSeg > 1 && !seg_block_range(nBlocks, nSeg, seg, a.segMinBlocks, a.level[pos], bs, be)) continue;
     const bool lastSeg = be == nBlocks;
     const int tProd = hasPrev ? a.prodPos[pos] * a.nQueries + q : 0;  // ticket of the stripe above (always older)
     const unsigned long long* bndIn = a.bnd + (int64_t)(tProd % a.nslot) * a.bndStride;

@@ -59,7 +59,7 @@ EXPORTS = ["rmgpu_version", "rmgpu_abi_version", "rmgpu_last_error", "rmgpu_sear
            "rmgpu_server_ping", "rmgpu_server_quit", "rmgpu_kimura_divergence", "rmgpu_matrix_info",
            "rmgpu_adjusted_score", "rmgpu_masklevel_filter", "rmgpu_contained_filter",
            "rmgpu_session_library_h2d_bytes", "rmgpu_session_set_queries_fasta_multi", "rmgpu_device_count",
-           "rmgpu_session_mask_queries", "rmgpu_format_alignment"]
+           "rmgpu_session_mask_queries", "rmgpu_format_alignment", "rmgpu_debug_k1_schedule"]
 
 
 def lib():
@@ -163,6 +163,19 @@ def format_alignment(query_name, subject_name, qaln, saln, qstart, qend, sstart,
     buf = C.create_string_buffer(need + 1)
     f(*args, buf, need + 1)
     return buf.value.decode()
+
+
+def k1_schedule(n_tickets, n_seg, seg_window, claim, n_blocks, seg_min_blocks, level):
+    """rmgpu_debug_k1_schedule(): (has_work, ticket, segment, first block, end block) of one claim of the score pass's
+    column-segment schedule.  Host-only test hook."""
+    f = lib().rmgpu_debug_k1_schedule
+    f.argtypes = [C.c_int32] * 7 + [C.POINTER(C.c_int32)] * 4
+    f.restype = C.c_int
+    t, s, b0, b1 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    rc = f(n_tickets, n_seg, seg_window, claim, n_blocks, seg_min_blocks, level, C.byref(t), C.byref(s), C.byref(b0), C.byref(b1))
+    if rc < 0:
+        raise ValueError("bad schedule arguments")
+    return rc, t.value, s.value, b0.value, b1.value
 
 
 def matrix_info(path):
